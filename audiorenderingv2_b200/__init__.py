@@ -1,0 +1,447 @@
+"""audiorenderingv2_b200 -- ctypes binding of libarv2.so (include/arv2.h).
+
+The product is the C-ABI shared library (hand-written sm_100a CUDA + C++ host code in
+``csrc/``); the C++ mirror of the reference's ``AudioRenderer`` class lives in
+``csrc/host/audio_renderer.hpp``.  This module is the thin Python face of the same ABI
+used by ``tests/`` and ``bench.py``; names follow the reference
+(prebuild/obj_raytracer/AudioRenderer.h:16-152, OptixModel.h, Context.cpp).
+
+There is no CPU fallback: the library must be built (``__graft_entry__.build()``) and
+anything that touches the GPU raises ``Arv2Error`` when no B200 / driver is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libarv2.so")
+MAX_BANDS = 8
+CONV_LINEAR, CONV_REFERENCE = 0, 1
+
+
+class Arv2Error(RuntimeError):
+    pass
+
+
+class Material(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("mat_absorption", C.c_float * MAX_BANDS), ("scattering", C.c_float)]
+
+
+class RendererDesc(C.Structure):
+    _fields_ = [
+        ("ir_length_in_seconds", C.c_uint32), ("sample_rate", C.c_int32),
+        ("rays_x", C.c_int32), ("rays_y", C.c_int32), ("rays_z", C.c_int32),
+        ("bands", C.c_int32), ("device", C.c_int32), ("record_rays", C.c_int32),
+        ("path_cache", C.c_int32), ("bvh_builder", C.c_int32),
+        ("materials", C.POINTER(Material)), ("n_materials", C.c_int32),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("initial_volume", C.c_float), ("ir_length_in_seconds", C.c_uint32),
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("write_first_ir_to_file", C.c_int32), ("write_first_output_to_file", C.c_int32),
+        ("re_render_distance_threshold", C.c_float), ("re_render_angle_threshold", C.c_float),
+        ("mono", C.c_int32),
+        ("scene_file_path", C.c_char * 512), ("audio_file_path", C.c_char * 512),
+        ("materials_file_path", C.c_char * 512),
+        ("initial_receiver_pos", C.c_float * 3), ("initial_emitter_pos", C.c_float * 3),
+        ("base_power", C.c_float), ("rays", C.c_float * 3), ("ray_energy_threshold", C.c_float),
+        ("ray_max_bounces", C.c_uint32), ("hrtf_absorption_rate", C.c_float),
+        ("n_materials", C.c_int32), ("material_names", (C.c_char * 64) * 64),
+        ("material_absorption", C.c_float * 64),
+        ("seed", C.c_uint64), ("bands", C.c_int32),
+    ]
+
+
+_lib = None
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+
+# every symbol include/arv2.h declares: (restype, argtypes)
+SYMBOLS = {
+    "arv2_last_error": (C.c_char_p, []),
+    "arv2_version": (C.c_char_p, []),
+    "arv2_scene_load_obj": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "arv2_scene_from_triangles": (C.c_int, [_fp, _ip, C.c_int64, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(_vp)]),
+    "arv2_scene_counts": (C.c_int, [_vp, C.POINTER(C.c_int64), _ip]),
+    "arv2_scene_get_triangles": (C.c_int, [_vp, _fp, _ip]),
+    "arv2_scene_mesh_material": (C.c_char_p, [_vp, C.c_int32]),
+    "arv2_scene_bounds": (C.c_int, [_vp, _fp, _fp]),
+    "arv2_scene_destroy": (None, [_vp]),
+    "arv2_receiver_load": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(_vp)]),
+    "arv2_receiver_from_triangles": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.POINTER(_vp)]),
+    "arv2_receiver_counts": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "arv2_receiver_place": (C.c_int, [_vp, _fp, C.c_float, _fp, _fp]),
+    "arv2_receiver_destroy": (None, [_vp]),
+    "arv2_material_absorption": (C.c_float, [C.c_char_p, C.POINTER(Material), C.c_int32]),
+    "arv2_config_parse": (C.c_int, [C.c_char_p, C.POINTER(Config)]),
+    "arv2_config_load": (C.c_int, [C.c_char_p, C.POINTER(Config)]),
+    "arv2_create": (C.c_int, [_vp, _vp, C.POINTER(RendererDesc), C.POINTER(_vp)]),
+    "arv2_destroy": (None, [_vp]),
+    "arv2_set_emitter": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float]),
+    "arv2_set_receiver": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "arv2_set_thresholds": (C.c_int, [_vp, C.c_float, C.c_uint32]),
+    "arv2_set_base_power": (C.c_int, [_vp, C.c_float]),
+    "arv2_set_hrtf_absorption_rate": (C.c_int, [_vp, C.c_float]),
+    "arv2_set_mono": (C.c_int, [_vp, C.c_int32]),
+    "arv2_set_seed": (C.c_int, [_vp, C.c_uint64]),
+    "arv2_set_stream": (C.c_int, [_vp, _vp]),
+    "arv2_render": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "arv2_render_range": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
+    "arv2_finalize": (C.c_int, [_vp]),
+    "arv2_rerender": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "arv2_ir_length": (C.c_int, [_vp, _ip, _ip]),
+    "arv2_get_ir": (C.c_int, [_vp, _fp, _fp]),
+    "arv2_set_ir": (C.c_int, [_vp, _fp, _fp]),
+    "arv2_ir_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "arv2_hist_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
+    "arv2_last_segments": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "arv2_get_records": (C.c_int, [_vp, _ip, _ip, _fp, _ip]),
+    "arv2_write_ir_text": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    "arv2_convolve_file": (C.c_int, [_vp, _fp, C.c_size_t, _fp, _fp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "arv2_stream_open": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    "arv2_stream_set_ir": (C.c_int, [_vp, C.c_int32, _fp, _fp]),
+    "arv2_stream_set_ir_device": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
+    "arv2_stream_process": (C.c_int, [_vp, _fp, _fp]),
+    "arv2_stream_process_device": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "arv2_stream_reset": (C.c_int, [_vp]),
+    "arv2_stream_close": (None, [_vp]),
+    "arv2_wav_read": (C.c_int, [C.c_char_p, C.POINTER(_fp), C.POINTER(C.c_size_t), _ip, _ip]),
+    "arv2_wav_write_stereo_normalized": (C.c_int, [C.c_char_p, _fp, _fp, C.c_size_t, C.c_int32]),
+    "arv2_free": (None, [_vp]),
+}
+
+
+def lib():
+    """Load libarv2.so (no fallback: a missing build is an error)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Arv2Error(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise Arv2Error(f"arv2 error {rc}: {lib().arv2_last_error().decode(errors='replace')}")
+
+
+def _f(a):
+    return a.ctypes.data_as(_fp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class Scene:
+    """struct OptixModel (OR/OptixModel.h:21-32)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def load_obj(cls, path):
+        """loadOBJ (OR/OptixModel.cpp:75-151)."""
+        h = _vp()
+        _check(lib().arv2_scene_load_obj(os.fsencode(path), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_triangles(cls, tri_verts, tri_mesh, material_names):
+        tv = np.ascontiguousarray(tri_verts, dtype=np.float32).reshape(-1, 9)
+        tm = np.ascontiguousarray(tri_mesh, dtype=np.int32)
+        names = (C.c_char_p * max(1, len(material_names)))(*[n.encode() for n in material_names])
+        h = _vp()
+        _check(lib().arv2_scene_from_triangles(_f(tv), _i(tm), tv.shape[0], names, len(material_names), C.byref(h)))
+        return cls(h)
+
+    def counts(self):
+        n = C.c_int64(); m = C.c_int32()
+        _check(lib().arv2_scene_counts(self._h, C.byref(n), C.byref(m)))
+        return n.value, m.value
+
+    def triangles(self):
+        n, _ = self.counts()
+        tv = np.empty((n, 3, 3), np.float32)
+        tm = np.empty(n, np.int32)
+        _check(lib().arv2_scene_get_triangles(self._h, _f(tv), _i(tm)))
+        return tv, tm
+
+    def mesh_materials(self):
+        _, m = self.counts()
+        return [lib().arv2_scene_mesh_material(self._h, i).decode() for i in range(m)]
+
+    def bounds(self):
+        lo = np.empty(3, np.float32); hi = np.empty(3, np.float32)
+        _check(lib().arv2_scene_bounds(self._h, _f(lo), _f(hi)))
+        return lo, hi
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.arv2_scene_destroy(self._h)
+            self._h = None
+
+
+class Receiver:
+    """class Sphere / HalfSphere (OR/Sphere.cpp, OR/HalfSphere.cpp)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def load(cls, left_obj, right_obj):
+        h = _vp()
+        _check(lib().arv2_receiver_load(os.fsencode(left_obj), os.fsencode(right_obj), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_triangles(cls, left, right):
+        l = np.ascontiguousarray(left, dtype=np.float32).reshape(-1, 9)
+        r = np.ascontiguousarray(right, dtype=np.float32).reshape(-1, 9)
+        h = _vp()
+        _check(lib().arv2_receiver_from_triangles(_f(l), l.shape[0], _f(r), r.shape[0], C.byref(h)))
+        return cls(h)
+
+    def counts(self):
+        a = C.c_int64(); b = C.c_int64()
+        _check(lib().arv2_receiver_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def place(self, cam, rotation_deg):
+        """placeReceiver (OR/OptixModel.cpp:153-257), host only."""
+        nl, nr = self.counts()
+        l = np.empty((nl, 3, 3), np.float32); r = np.empty((nr, 3, 3), np.float32)
+        c = np.ascontiguousarray(cam, dtype=np.float32)
+        _check(lib().arv2_receiver_place(self._h, _f(c), float(rotation_deg), _f(l), _f(r)))
+        return l, r
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.arv2_receiver_destroy(self._h)
+            self._h = None
+
+
+def material_absorption(name, materials=()):
+    """getMaterialAbsorption (OR/AudioRenderer.cpp:34-56); materials = [(name, absorption)]."""
+    arr = (Material * max(1, len(materials)))()
+    keep = []
+    for i, (n, a) in enumerate(materials):
+        b = n.encode(); keep.append(b)
+        arr[i].name = b
+        arr[i].mat_absorption[0] = a
+    return lib().arv2_material_absorption(name.encode(), arr, len(materials))
+
+
+def parse_config(text: str) -> Config:
+    """Context::loadContext (OR/Context.cpp:15-165)."""
+    cfg = Config()
+    _check(lib().arv2_config_parse(text.encode(), C.byref(cfg)))
+    return cfg
+
+
+def load_config(path) -> Config:
+    cfg = Config()
+    _check(lib().arv2_config_load(os.fsencode(path), C.byref(cfg)))
+    return cfg
+
+
+def config_materials(cfg: Config):
+    return [(cfg.material_names[i].value.decode(), cfg.material_absorption[i]) for i in range(cfg.n_materials)]
+
+
+class AudioRenderer:
+    """Mirror of class AudioRenderer (OR/AudioRenderer.h:16-152) over the C ABI."""
+
+    def __init__(self, model: Scene, ir_length_in_seconds, sample_rate, materials, rays_per_dimension,
+                 receiver: Receiver | None = None, bands=1, device=0, record_rays=False, path_cache=False,
+                 bvh_builder=0):
+        """materials: [(name, absorption | [absorption per band], scattering=0)]."""
+        d = RendererDesc()
+        d.ir_length_in_seconds = int(ir_length_in_seconds)
+        d.sample_rate = int(sample_rate)
+        d.rays_x, d.rays_y, d.rays_z = (int(v) for v in rays_per_dimension)
+        d.bands = bands; d.device = device
+        d.record_rays = 1 if record_rays else 0
+        d.path_cache = 1 if path_cache else 0
+        d.bvh_builder = bvh_builder
+        arr = (Material * max(1, len(materials)))()
+        self._keep = []
+        for i, m in enumerate(materials):
+            name, a = m[0], m[1]
+            b = name.encode(); self._keep.append(b)
+            arr[i].name = b
+            vals = list(a) if isinstance(a, (list, tuple, np.ndarray)) else [a] * MAX_BANDS
+            for k in range(MAX_BANDS):
+                arr[i].mat_absorption[k] = float(vals[min(k, len(vals) - 1)])
+            arr[i].scattering = float(m[2]) if len(m) > 2 else 0.0
+        d.materials = arr; d.n_materials = len(materials)
+        self._h = _vp()
+        self.bands = bands
+        self.n_rays = d.rays_x * d.rays_y * d.rays_z
+        self.sample_rate = int(sample_rate)
+        _check(lib().arv2_create(model._h, receiver._h if receiver is not None else None, C.byref(d), C.byref(self._h)))
+        n = C.c_int32(); b = C.c_int32()
+        _check(lib().arv2_ir_length(self._h, C.byref(n), C.byref(b)))
+        self.ir_length = n.value
+
+    # -- setters (reference names) ------------------------------------------------
+    def setEmitterPosInOptix(self, pos):
+        _check(lib().arv2_set_emitter(self._h, *[float(v) for v in pos]))
+
+    def setSphereCenterInOptix(self, pos, yaw_deg=0.0):
+        """placeReceiver + setSphereCenterInOptix."""
+        _check(lib().arv2_set_receiver(self._h, float(pos[0]), float(pos[1]), float(pos[2]), float(yaw_deg)))
+
+    def setThresholds(self, energy, max_bounces):
+        _check(lib().arv2_set_thresholds(self._h, float(energy), int(max_bounces)))
+
+    def setBasePower(self, p):
+        _check(lib().arv2_set_base_power(self._h, float(p)))
+
+    def set_hrtf_absorption_rate(self, r):
+        _check(lib().arv2_set_hrtf_absorption_rate(self._h, float(r)))
+
+    def setMonoOutput(self, v):
+        _check(lib().arv2_set_mono(self._h, 1 if v else 0))
+
+    def set_seed(self, seed):
+        _check(lib().arv2_set_seed(self._h, int(seed)))
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().arv2_set_stream(self._h, cuda_stream_ptr))
+
+    # -- rendering ------------------------------------------------------------------
+    def render(self):
+        """AudioRenderer::render; returns device milliseconds of the trace."""
+        ms = C.c_double()
+        _check(lib().arv2_render(self._h, C.byref(ms)))
+        return ms.value
+
+    def render_range(self, ray_begin, n_rays, zero_first=True):
+        ms = C.c_double()
+        _check(lib().arv2_render_range(self._h, int(ray_begin), int(n_rays), 1 if zero_first else 0, C.byref(ms)))
+        return ms.value
+
+    def finalize(self):
+        _check(lib().arv2_finalize(self._h))
+
+    def rerender(self):
+        ms = C.c_double()
+        _check(lib().arv2_rerender(self._h, C.byref(ms)))
+        return ms.value
+
+    def get_ir(self):
+        l = np.empty((self.bands, self.ir_length), np.float32)
+        r = np.empty((self.bands, self.ir_length), np.float32)
+        _check(lib().arv2_get_ir(self._h, _f(l), _f(r)))
+        return l, r
+
+    def set_ir(self, left, right):
+        l = np.ascontiguousarray(left, dtype=np.float32); r = np.ascontiguousarray(right, dtype=np.float32)
+        assert l.size == self.ir_length and r.size == self.ir_length
+        _check(lib().arv2_set_ir(self._h, _f(l), _f(r)))
+
+    def ir_device(self):
+        a = _vp(); b = _vp()
+        _check(lib().arv2_ir_device(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def hist_device(self):
+        p = _vp(); n = C.c_int64()
+        _check(lib().arv2_hist_device(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def last_segments(self):
+        s = C.c_int64()
+        _check(lib().arv2_last_segments(self._h, C.byref(s)))
+        return s.value
+
+    def records(self, n_rays=None):
+        n = self.n_rays if n_rays is None else n_rays
+        b = np.empty(n, np.int32); e = np.empty(n, np.int32); s = np.empty(n, np.int32)
+        en = np.empty((n, self.bands), np.float32)
+        _check(lib().arv2_get_records(self._h, _i(b), _i(e), _f(en), _i(s)))
+        return dict(bin=b, ear=e, energy=en, nseg=s)
+
+    def write_ir_text(self, left_path, right_path):
+        _check(lib().arv2_write_ir_text(self._h, os.fsencode(left_path), os.fsencode(right_path)))
+
+    # -- convolution ----------------------------------------------------------------
+    def convoluteAudioFile(self, samples, mode=CONV_LINEAR):
+        """AudioRenderer::convoluteAudioFile; returns (left, right, conv_ms, process_ms)."""
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        yl = np.empty_like(x); yr = np.empty_like(x)
+        t = C.c_double(); tp = C.c_double()
+        _check(lib().arv2_convolve_file(self._h, _f(x), x.size, _f(yl), _f(yr), mode, C.byref(t), C.byref(tp)))
+        return yl, yr, t.value, tp.value
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.arv2_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class ConvStream:
+    """Streaming partitioned convolver (replaces AudioRenderer::convoluteLiveInput)."""
+
+    def __init__(self, n_sources, block, ir_length, device=0):
+        self._h = _vp()
+        self.n_sources, self.block, self.ir_length = n_sources, block, ir_length
+        _check(lib().arv2_stream_open(device, n_sources, block, ir_length, C.byref(self._h)))
+
+    def set_ir(self, source, left, right):
+        l = np.ascontiguousarray(left, dtype=np.float32); r = np.ascontiguousarray(right, dtype=np.float32)
+        assert l.size == self.ir_length and r.size == self.ir_length
+        _check(lib().arv2_stream_set_ir(self._h, source, _f(l), _f(r)))
+
+    def set_ir_device(self, source, d_left, d_right):
+        _check(lib().arv2_stream_set_ir_device(self._h, source, d_left, d_right))
+
+    def process(self, block_in):
+        x = np.ascontiguousarray(block_in, dtype=np.float32).reshape(self.n_sources, self.block)
+        out = np.empty((self.n_sources, 2, self.block), np.float32)
+        _check(lib().arv2_stream_process(self._h, _f(x), _f(out)))
+        return out
+
+    def process_device(self, d_in, d_out, cuda_stream=None):
+        _check(lib().arv2_stream_process_device(self._h, d_in, d_out, cuda_stream))
+
+    def reset(self):
+        _check(lib().arv2_stream_reset(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.arv2_stream_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def wav_read(path):
+    p = _fp(); n = C.c_size_t(); sr = C.c_int32(); ch = C.c_int32()
+    _check(lib().arv2_wav_read(os.fsencode(path), C.byref(p), C.byref(n), C.byref(sr), C.byref(ch)))
+    try:
+        a = np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.float32)
+    finally:
+        lib().arv2_free(p)
+    return sr.value, ch.value, a
+
+
+def wav_write_stereo_normalized(path, left, right, sample_rate):
+    l = np.ascontiguousarray(left, dtype=np.float32); r = np.ascontiguousarray(right, dtype=np.float32)
+    _check(lib().arv2_wav_write_stereo_normalized(os.fsencode(path), _f(l), _f(r), l.size, int(sample_rate)))

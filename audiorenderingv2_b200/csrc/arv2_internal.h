@@ -1,0 +1,76 @@
+// arv2_internal.h -- types shared by the host front end, the BVH builders, the CUDA
+// kernels and the C ABI of libarv2.so.  Not part of the public interface.
+#pragma once
+
+#include <algorithm>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/arv2.h"
+
+namespace arv2 {
+
+struct Vec3 { float x, y, z; };
+
+// struct TriangleMesh / OptixModel (OR/OptixModel.h:9-32) flattened: the renderer
+// only ever needs positions, the mesh a triangle belongs to and the mesh's
+// material name.
+struct HostScene {
+    std::vector<float> tri_verts;          // [T][3][3]
+    std::vector<int32_t> tri_mesh;         // [T]
+    std::vector<std::string> mesh_material;
+    std::vector<std::string> mtl_names;    // materials of the MTL, file order
+    int64_t n_tris() const { return (int64_t)tri_mesh.size(); }
+};
+
+struct HostReceiver {
+    std::vector<float> left, right;        // [n][3][3] untransformed templates
+};
+
+// ---- device BVH layout --------------------------------------------------------
+// Binary BVH, 64 B per inner node (4 x float4), children boxes stored in the
+// parent so one node fetch decides both descents:
+//   q0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
+//   q1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+//   q2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+//   q3 = (int c0, int c1, -, -)   c >= 0: inner node index
+//                                 c <  0: leaf, ~c = (first_tri << 3) | (count - 1)
+// Triangles, 48 B each (3 x float4), stored in leaf order:
+//   t0 = (P1.xyz, bits(global triangle id))
+//   t1 = (P2.xyz, bits(material: >=0 wall material, -1 / -2 receiver ear))
+//   t2 = (P3.xyz, 0)
+struct BvhNode { float q[16]; };
+constexpr int kMaxLeafTris = 4;
+constexpr int kLeafShift = 3;
+// An absent child is a degenerate box far outside any scene: with the min/max slab
+// test an inverted (+inf,-inf) box would read as "everything", this one as a miss.
+constexpr float kEmptyBox = 3.0e38f;
+
+struct HostBvh {
+    std::vector<BvhNode> nodes;     // node 0 is the root (always an inner node)
+    std::vector<int32_t> order;     // leaf-order position -> input triangle index
+    float lo[3], hi[3];             // root bounds (padded)
+};
+
+// Binned-SAH top-down builder (host). `tri_verts` = [n][3][3].
+void build_bvh_sah(const float* tri_verts, int64_t n, HostBvh* out, int n_threads);
+// Recompute every box of an existing tree for moved vertices (same topology/order).
+void refit_bvh(const float* tri_verts, int64_t n, HostBvh* bvh);
+// Conservative padding applied to every box (relative to the scene extent).
+inline float bvh_pad(float extent) { return extent * 1e-5f + 1e-6f; }
+
+// ---- host front end -------------------------------------------------------------
+int load_obj(const std::string& path, HostScene* out, std::string* err);
+void place_receiver_half(const std::vector<float>& tmpl, const float cam[3], float rotation_deg,
+                         float* out);
+float material_absorption(const std::string& name, const arv2_material* mats, int n);
+int parse_config(const std::string& json, arv2_config* out, std::string* err);
+
+int wav_read(const std::string& path, float** samples, size_t* n, int32_t* rate, int32_t* channels, std::string* err);
+int wav_write_stereo_normalized(const std::string& path, const float* l, const float* r, size_t n, int32_t rate, std::string* err);
+
+void set_error(const std::string& msg);
+
+} // namespace arv2

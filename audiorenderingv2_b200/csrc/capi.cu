@@ -1,0 +1,895 @@
+// capi.cu -- C ABI of libarv2.so (include/arv2.h): scene / receiver / config objects and
+// the renderer context that stands in for class AudioRenderer
+// (OR/AudioRenderer.h:16-152, OR/AudioRenderer.cpp).
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <thread>
+
+#include <cuda_runtime.h>
+
+#include "arv2_internal.h"
+#include "conv.cuh"
+#include "trace.cuh"
+
+namespace arv2 {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+} // namespace arv2
+
+using namespace arv2;
+
+struct arv2_scene { HostScene s; };
+struct arv2_receiver { HostReceiver r; };
+
+#define CK(expr)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                             \
+            return ARV2_ERR_CUDA;                                                                      \
+        }                                                                                              \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                                                             \
+    do { if (!(cond)) { set_error(msg); return ARV2_ERR_INVALID; } } while (0)
+
+struct arv2_ctx {
+    int device = 0, sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    arv2_renderer_desc desc{};
+    int ir_len = 0, bands = 1;
+    long long n_rays_total = 0;
+
+    // host copies
+    HostScene scene;
+    HostReceiver receiver;
+    bool has_receiver = false;
+    HostBvh scene_bvh, recv_bvh;
+    bool recv_bvh_built = false;
+    std::vector<float> recv_world;     // [n_recv][3][3]
+    int64_t n_scene = 0, n_left = 0, n_right = 0;
+    int32_t n_scene_nodes = 0, n_recv_nodes = 0;
+
+    // parameters (LaunchParams)
+    float emitter[3] = {0, 0, 0}, center[3] = {0, 0, 0}, yaw = 0.f;
+    float base_power = 100.f, energy_thres = 0.f, hrtf = 0.9f;
+    unsigned max_bounces = 10;
+    int mono = 0;
+    unsigned long long seed = 1;
+    bool recv_dirty = true, cache_valid = false;
+    int any_scatter = 0;
+
+    // device
+    float4* d_nodes = nullptr; float4* d_tris = nullptr;
+    float* d_keep = nullptr; float* d_scatter = nullptr;
+    double* d_hist = nullptr; float* d_ir_l = nullptr; float* d_ir_r = nullptr;
+    unsigned long long* d_counters = nullptr;
+    int* d_rec_bin = nullptr; int* d_rec_ear = nullptr; int* d_rec_nseg = nullptr; float* d_rec_energy = nullptr;
+    long long rec_capacity = 0, last_range_rays = 0;
+    float4* d_pc_org = nullptr; float4* d_pc_dir = nullptr; float* d_pc_energy = nullptr; int* d_pc_nseg = nullptr;
+    long long pc_rays = 0; unsigned pc_bounces = 0;
+    // pinned staging for the receiver sub-tree
+    float4* h_stage = nullptr; size_t stage_f4 = 0;
+    unsigned long long* h_counters = nullptr;
+    long long last_segments = 0;
+    // file-convolver workspace, grown on demand (the reference mallocs per call)
+    struct ConvWork {
+        float2* d_tw = nullptr; float* d_x = nullptr; float* d_out = nullptr; float2* d_X = nullptr; float2* d_H = nullptr;
+        size_t cap_x = 0, cap_X = 0, cap_H = 0;
+    } conv;
+};
+
+struct arv2_stream {
+    int device = 0, n_src = 0, block = 0, ir_len = 0, P = 0, slot = 0;
+    cudaStream_t stream = nullptr;
+    float2* d_tw = nullptr; float2* d_fdl = nullptr; float2* d_H[2] = {nullptr, nullptr};
+    float2** d_Hptr = nullptr; float2** h_Hptr = nullptr;
+    std::vector<int> active;
+    float* d_tail = nullptr; float* d_in = nullptr; float* d_out = nullptr; float* d_ir = nullptr;
+    float* h_in = nullptr; float* h_out = nullptr; float* h_ir = nullptr;
+};
+
+namespace {
+
+int upload_receiver(arv2_ctx* c)
+{
+    if (!c->has_receiver || !c->recv_dirty) return ARV2_OK;
+    const int64_t nl = c->n_left, nr = c->n_right, n = nl + nr;
+    c->recv_world.resize((size_t)n * 9);
+    place_receiver_half(c->receiver.left, c->center, c->yaw, c->recv_world.data());
+    place_receiver_half(c->receiver.right, c->center, c->yaw, c->recv_world.data() + nl * 9);
+    if (!c->recv_bvh_built) {
+        build_bvh_sah(c->recv_world.data(), n, &c->recv_bvh, 1);
+        c->recv_bvh_built = true;
+        if ((int32_t)c->recv_bvh.nodes.size() > c->n_recv_nodes) { set_error("receiver BVH larger than reserved"); return ARV2_ERR_STATE; }
+    } else {
+        refit_bvh(c->recv_world.data(), n, &c->recv_bvh);
+    }
+    // stage: [top node (4 f4)] [recv nodes] [recv tris]
+    const int32_t nn = (int32_t)c->recv_bvh.nodes.size();
+    const int32_t node_base = 1 + c->n_scene_nodes;
+    const int64_t tri_base = c->n_scene;
+    float4* st = c->h_stage;
+    // top node: child0 = scene root (node 1), child1 = receiver root
+    {
+        BvhNode top{};
+        const float* slo = c->scene_bvh.lo; const float* shi = c->scene_bvh.hi;
+        const float* rlo = c->recv_bvh.lo; const float* rhi = c->recv_bvh.hi;
+        top.q[0] = slo[0]; top.q[1] = shi[0]; top.q[2] = slo[1]; top.q[3] = shi[1];
+        top.q[4] = rlo[0]; top.q[5] = rhi[0]; top.q[6] = rlo[1]; top.q[7] = rhi[1];
+        top.q[8] = slo[2]; top.q[9] = shi[2]; top.q[10] = rlo[2]; top.q[11] = rhi[2];
+        int32_t ch[4] = {1, node_base, 0, 0};
+        std::memcpy(&top.q[12], ch, sizeof ch);
+        std::memcpy(st, &top, sizeof top);
+    }
+    float4* sn = st + 4;
+    for (int32_t i = 0; i < nn; ++i) {
+        BvhNode d = c->recv_bvh.nodes[i];
+        int32_t ch[4];
+        std::memcpy(ch, &d.q[12], sizeof ch);
+        for (int w = 0; w < 2; ++w) {
+            if (ch[w] >= 0) ch[w] += node_base;
+            else { const int32_t code = ~ch[w]; ch[w] = ~(int32_t)((((int64_t)(code >> kLeafShift) + tri_base) << kLeafShift) | (code & 7)); }
+        }
+        std::memcpy(&d.q[12], ch, sizeof ch);
+        std::memcpy(sn + 4 * i, &d, sizeof d);
+    }
+    float4* stt = sn + 4 * (size_t)c->n_recv_nodes;
+    for (int64_t s = 0; s < n; ++s) {
+        const int32_t src = c->recv_bvh.order[s];
+        const float* v = c->recv_world.data() + 9 * (size_t)src;
+        const int32_t gid = (int32_t)(tri_base + src);
+        const int32_t mat = src < nl ? -1 : -2;
+        float idf, matf;
+        std::memcpy(&idf, &gid, 4); std::memcpy(&matf, &mat, 4);
+        stt[3 * s + 0] = make_float4(v[0], v[1], v[2], idf);
+        stt[3 * s + 1] = make_float4(v[3], v[4], v[5], matf);
+        stt[3 * s + 2] = make_float4(v[6], v[7], v[8], 0.f);
+    }
+    CK(cudaMemcpyAsync(c->d_nodes, st, sizeof(float4) * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_nodes + 4 * (size_t)node_base, sn, sizeof(float4) * 4 * (size_t)nn, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_tris + 3 * (size_t)tri_base, stt, sizeof(float4) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    c->recv_dirty = false;
+    return ARV2_OK;
+}
+
+void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_rays)
+{
+    std::memset(p, 0, sizeof *p);
+    p->nodes = c->d_nodes; p->tris = c->d_tris; p->keep = c->d_keep; p->scattering = c->d_scatter;
+    p->hist = c->d_hist; p->counters = c->d_counters;
+    if (c->desc.record_rays && n_rays <= c->rec_capacity) {
+        p->rec_bin = c->d_rec_bin; p->rec_ear = c->d_rec_ear; p->rec_energy = c->d_rec_energy; p->rec_nseg = c->d_rec_nseg;
+    }
+    p->pc_org_t = c->d_pc_org; p->pc_dir_d = c->d_pc_dir; p->pc_energy = c->d_pc_energy; p->pc_nseg = c->d_pc_nseg;
+    p->pc_stride = c->pc_rays;
+    p->seed = c->seed; p->ray_begin = ray_begin; p->n_rays = n_rays;
+    for (int a = 0; a < 3; ++a) { p->emitter[a] = c->emitter[a]; p->center[a] = c->center[a]; }
+    // OR/devicePrograms.cu:208  base_power / ((x*y*z) * 4.18879020478), double then narrowed
+    p->energy0 = (float)((double)c->base_power / ((double)(int)c->n_rays_total * 4.18879020478));
+    p->energy_thres = c->energy_thres;
+    // :227-228
+    int ir_sec = c->ir_len / c->desc.sample_rate;
+    ir_sec = ir_sec < 1 ? 1 : (ir_sec > 999 ? 999 : ir_sec);
+    p->dist_thr = (float)(ir_sec * 343 + 1);
+    p->cross_gain = 1.0f - c->hrtf;                      // :139 (1 - hrtf_absorption_rate)
+    p->fs = (float)c->desc.sample_rate;
+    p->max_bounces = c->max_bounces;
+    p->delay = (int)((double)c->desc.sample_rate * 0.00044);   // :125
+    p->ir_len = c->ir_len; p->mono = c->mono;
+    p->root = 0; p->recv_root = 1 + c->n_scene_nodes;
+    p->any_scatter = c->any_scatter;
+}
+
+int ensure_cache(arv2_ctx* c)
+{
+    const long long n = c->n_rays_total;
+    if (c->d_pc_org && c->pc_rays == n && c->pc_bounces >= c->max_bounces) return ARV2_OK;
+    cudaFree(c->d_pc_org); cudaFree(c->d_pc_dir); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg);
+    c->d_pc_org = c->d_pc_dir = nullptr; c->d_pc_energy = nullptr; c->d_pc_nseg = nullptr;
+    const size_t segs = (size_t)n * c->max_bounces;
+    CK(cudaMalloc(&c->d_pc_org, segs * sizeof(float4)));
+    CK(cudaMalloc(&c->d_pc_dir, segs * sizeof(float4)));
+    CK(cudaMalloc(&c->d_pc_energy, segs * sizeof(float) * c->bands));
+    CK(cudaMalloc(&c->d_pc_nseg, (size_t)n * sizeof(int)));
+    c->pc_rays = n; c->pc_bounces = c->max_bounces; c->cache_valid = false;
+    return ARV2_OK;
+}
+
+int finish_timed(arv2_ctx* c, double* ms)
+{
+    CK(cudaMemcpyAsync(c->h_counters, c->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));                    // CUDA_SYNC_CHECK, OR/AudioRenderer.cpp:511
+    c->last_segments = (long long)c->h_counters[1];
+    if (ms) { float t = 0.f; CK(cudaEventElapsedTime(&t, c->ev0, c->ev1)); *ms = t; }
+    return ARV2_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* arv2_last_error(void) { return g_error.c_str(); }
+const char* arv2_version(void) { return "arv2-b200 0.1 (sm_100a)"; }
+
+/* ------------------------------------------------------------------ scene -- */
+int arv2_scene_load_obj(const char* path, arv2_scene** out)
+{
+    REQUIRE(path && out, "arv2_scene_load_obj: null argument");
+    auto* s = new arv2_scene;
+    std::string err;
+    const int rc = load_obj(path, &s->s, &err);
+    if (rc != ARV2_OK) { set_error(err); delete s; return rc; }
+    *out = s;
+    return ARV2_OK;
+}
+
+int arv2_scene_from_triangles(const float* tv, const int32_t* tm, int64_t n, const char* const* names, int32_t n_meshes,
+                              arv2_scene** out)
+{
+    REQUIRE(out && n >= 0 && n_meshes >= 0 && (n == 0 || (tv && tm)), "arv2_scene_from_triangles: bad argument");
+    auto* s = new arv2_scene;
+    s->s.tri_verts.assign(tv, tv + 9 * n);
+    s->s.tri_mesh.assign(tm, tm + n);
+    for (int64_t i = 0; i < n; ++i)
+        if (tm[i] < 0 || tm[i] >= n_meshes) { delete s; set_error("tri_mesh out of range"); return ARV2_ERR_INVALID; }
+    for (int32_t m = 0; m < n_meshes; ++m) s->s.mesh_material.push_back(names && names[m] ? names[m] : "");
+    *out = s;
+    return ARV2_OK;
+}
+
+int arv2_scene_counts(const arv2_scene* s, int64_t* n_tris, int32_t* n_meshes)
+{
+    REQUIRE(s, "null scene");
+    if (n_tris) *n_tris = s->s.n_tris();
+    if (n_meshes) *n_meshes = (int32_t)s->s.mesh_material.size();
+    return ARV2_OK;
+}
+
+int arv2_scene_get_triangles(const arv2_scene* s, float* tv, int32_t* tm)
+{
+    REQUIRE(s, "null scene");
+    if (tv) std::memcpy(tv, s->s.tri_verts.data(), s->s.tri_verts.size() * sizeof(float));
+    if (tm) std::memcpy(tm, s->s.tri_mesh.data(), s->s.tri_mesh.size() * sizeof(int32_t));
+    return ARV2_OK;
+}
+
+const char* arv2_scene_mesh_material(const arv2_scene* s, int32_t mesh)
+{
+    if (!s || mesh < 0 || mesh >= (int32_t)s->s.mesh_material.size()) return nullptr;
+    return s->s.mesh_material[mesh].c_str();
+}
+
+int arv2_scene_bounds(const arv2_scene* s, float* lo, float* hi)
+{
+    REQUIRE(s && lo && hi, "null argument");
+    for (int a = 0; a < 3; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+    const size_t nv = s->s.tri_verts.size() / 3;
+    for (size_t i = 0; i < nv; ++i)
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::fmin(lo[a], s->s.tri_verts[3 * i + a]);
+            hi[a] = std::fmax(hi[a], s->s.tri_verts[3 * i + a]);
+        }
+    return ARV2_OK;
+}
+
+void arv2_scene_destroy(arv2_scene* s) { delete s; }
+
+int arv2_receiver_load(const char* left_obj, const char* right_obj, arv2_receiver** out)
+{
+    REQUIRE(left_obj && right_obj && out, "arv2_receiver_load: null argument");
+    HostScene l, r;
+    std::string err;
+    int rc = load_obj(left_obj, &l, &err);
+    if (rc == ARV2_OK) rc = load_obj(right_obj, &r, &err);
+    if (rc != ARV2_OK) { set_error("Could not read sphere OBJ model: " + err); return rc; }
+    auto* o = new arv2_receiver;
+    // HalfSphere keeps shapes[0] only (OR/OptixModel.cpp:199-203); both assets have one mesh
+    auto first_mesh = [](const HostScene& s, std::vector<float>* dst) {
+        for (int64_t i = 0; i < s.n_tris() && s.tri_mesh[i] == 0; ++i) dst->insert(dst->end(), s.tri_verts.begin() + 9 * i, s.tri_verts.begin() + 9 * i + 9);
+    };
+    first_mesh(l, &o->r.left);
+    first_mesh(r, &o->r.right);
+    *out = o;
+    return ARV2_OK;
+}
+
+int arv2_receiver_from_triangles(const float* left, int64_t nl, const float* right, int64_t nr, arv2_receiver** out)
+{
+    REQUIRE(out && nl >= 0 && nr >= 0 && (nl == 0 || left) && (nr == 0 || right), "arv2_receiver_from_triangles: bad argument");
+    auto* o = new arv2_receiver;
+    o->r.left.assign(left, left + 9 * nl);
+    o->r.right.assign(right, right + 9 * nr);
+    *out = o;
+    return ARV2_OK;
+}
+
+int arv2_receiver_counts(const arv2_receiver* r, int64_t* nl, int64_t* nr)
+{
+    REQUIRE(r, "null receiver");
+    if (nl) *nl = (int64_t)r->r.left.size() / 9;
+    if (nr) *nr = (int64_t)r->r.right.size() / 9;
+    return ARV2_OK;
+}
+
+int arv2_receiver_place(const arv2_receiver* r, const float cam[3], float rotation_deg, float* left_out, float* right_out)
+{
+    REQUIRE(r && cam, "null argument");
+    if (left_out) place_receiver_half(r->r.left, cam, rotation_deg, left_out);
+    if (right_out) place_receiver_half(r->r.right, cam, rotation_deg, right_out);
+    return ARV2_OK;
+}
+
+void arv2_receiver_destroy(arv2_receiver* r) { delete r; }
+
+float arv2_material_absorption(const char* name, const arv2_material* mats, int32_t n)
+{
+    return material_absorption(name ? name : "", mats, mats ? n : 0);
+}
+
+/* ----------------------------------------------------------------- config -- */
+int arv2_config_parse(const char* json, arv2_config* out)
+{
+    REQUIRE(json && out, "null argument");
+    std::string err;
+    const int rc = parse_config(json, out, &err);
+    if (rc != ARV2_OK) set_error(err);
+    return rc;
+}
+
+int arv2_config_load(const char* path, arv2_config* out)
+{
+    REQUIRE(path && out, "null argument");
+    std::ifstream in(path);
+    if (!in) { set_error(std::string("cannot open ") + path); return ARV2_ERR_IO; }
+    std::stringstream ss;
+    ss << in.rdbuf();
+    return arv2_config_parse(ss.str().c_str(), out);
+}
+
+/* --------------------------------------------------------------- renderer -- */
+int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const arv2_renderer_desc* desc, arv2_ctx** out)
+{
+    REQUIRE(scene && desc && out, "arv2_create: null argument");
+    REQUIRE(desc->bands == 1 || desc->bands == ARV2_MAX_BANDS, "bands must be 1 or 8");
+    REQUIRE(desc->sample_rate > 0 && desc->ir_length_in_seconds > 0, "bad ir length / sample rate");
+    REQUIRE(desc->rays_x > 0 && desc->rays_y > 0 && desc->rays_z > 0, "bad ray counts");
+    const long long n_total = (long long)desc->rays_x * desc->rays_y * desc->rays_z;
+    REQUIRE(n_total <= 2147483647LL, "x*y*z must fit the reference's int launch size");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    REQUIRE(desc->device >= 0 && desc->device < ndev, "no such CUDA device");
+    CK(cudaSetDevice(desc->device));
+
+    auto* c = new arv2_ctx;
+    c->desc = *desc; c->desc.materials = nullptr; c->desc.n_materials = 0;
+    c->device = desc->device;
+    c->bands = desc->bands;
+    c->ir_len = (int)(desc->ir_length_in_seconds * (unsigned)desc->sample_rate);  // OR/AudioRenderer.cpp:78
+    c->n_rays_total = n_total;
+    c->scene = scene->s;
+    c->n_scene = c->scene.n_tris();
+    if (receiver) {
+        c->receiver = receiver->r; c->has_receiver = true;
+        c->n_left = (int64_t)c->receiver.left.size() / 9; c->n_right = (int64_t)c->receiver.right.size() / 9;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    int rc = ARV2_OK;
+    auto fail = [&](int code) { arv2_destroy(c); return code; };
+#define CKC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); return fail(ARV2_ERR_CUDA); } } while (0)
+    CKC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CKC(cudaEventCreate(&c->ev0));
+    CKC(cudaEventCreate(&c->ev1));
+
+    // per-mesh materials: keep = 1 - absorption (OR/devicePrograms.cu:174), scattering
+    const int n_mesh = (int)c->scene.mesh_material.size();
+    std::vector<float> keep((size_t)std::max(1, n_mesh) * c->bands, 0.5f), scat((size_t)std::max(1, n_mesh), 0.f);
+    for (int m = 0; m < n_mesh; ++m) {
+        const std::string& name = c->scene.mesh_material[m];
+        const arv2_material* hit = nullptr;
+        for (int i = 0; i < desc->n_materials && !hit; ++i)
+            if (desc->materials[i].name && name == desc->materials[i].name) hit = &desc->materials[i];
+        for (int b = 0; b < c->bands; ++b) {
+            const float a = hit ? hit->mat_absorption[b] : 0.5f;      // default, OR/AudioRenderer.cpp:54-55
+            keep[(size_t)m * c->bands + b] = 1.0f - a;
+        }
+        scat[m] = hit ? hit->scattering : 0.f;
+        if (scat[m] > 0.f) c->any_scatter = 1;
+    }
+
+    // scene BVH (built once; OR/AudioRenderer.cpp:95-218 rebuilds on every move)
+    const unsigned hc = std::thread::hardware_concurrency();
+    build_bvh_sah(c->scene.tri_verts.data(), c->n_scene, &c->scene_bvh, hc ? (int)hc : 1);
+    c->n_scene_nodes = (int32_t)c->scene_bvh.nodes.size();
+    const int64_t n_recv = c->n_left + c->n_right;
+    c->n_recv_nodes = (int32_t)std::max<int64_t>(1, n_recv);
+    const size_t total_nodes = 1 + (size_t)c->n_scene_nodes + (size_t)c->n_recv_nodes;
+    const size_t total_tris = (size_t)std::max<int64_t>(1, c->n_scene + n_recv);
+    CKC(cudaMalloc(&c->d_nodes, total_nodes * 4 * sizeof(float4)));
+    CKC(cudaMalloc(&c->d_tris, total_tris * 3 * sizeof(float4)));
+    CKC(cudaMalloc(&c->d_keep, keep.size() * sizeof(float)));
+    CKC(cudaMalloc(&c->d_scatter, scat.size() * sizeof(float)));
+    CKC(cudaMemcpy(c->d_keep, keep.data(), keep.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(c->d_scatter, scat.data(), scat.size() * sizeof(float), cudaMemcpyHostToDevice));
+    {
+        // scene nodes at [1, 1+ns), scene tris at [0, n_scene)
+        std::vector<BvhNode> nodes = c->scene_bvh.nodes;
+        for (auto& d : nodes) {
+            int32_t ch[4];
+            std::memcpy(ch, &d.q[12], sizeof ch);
+            for (int w = 0; w < 2; ++w) if (ch[w] >= 0) ch[w] += 1;
+            std::memcpy(&d.q[12], ch, sizeof ch);
+        }
+        // top node without a receiver: child1 empty
+        BvhNode top{};
+        const float* slo = c->scene_bvh.lo; const float* shi = c->scene_bvh.hi;
+        top.q[0] = slo[0]; top.q[1] = shi[0]; top.q[2] = slo[1]; top.q[3] = shi[1];
+        top.q[4] = top.q[5] = top.q[6] = top.q[7] = kEmptyBox;
+        top.q[8] = slo[2]; top.q[9] = shi[2]; top.q[10] = top.q[11] = kEmptyBox;
+        int32_t ch[4] = {1, ~0, 0, 0};
+        std::memcpy(&top.q[12], ch, sizeof ch);
+        CKC(cudaMemcpy(c->d_nodes, &top, sizeof top, cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(c->d_nodes + 4, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+        std::vector<float4> tris((size_t)c->n_scene * 3);
+        for (int64_t s = 0; s < c->n_scene; ++s) {
+            const int32_t src = c->scene_bvh.order[s];
+            const float* v = c->scene.tri_verts.data() + 9 * (size_t)src;
+            const int32_t mat = c->scene.tri_mesh[src];
+            float idf, matf;
+            std::memcpy(&idf, &src, 4); std::memcpy(&matf, &mat, 4);
+            tris[3 * s + 0] = make_float4(v[0], v[1], v[2], idf);
+            tris[3 * s + 1] = make_float4(v[3], v[4], v[5], matf);
+            tris[3 * s + 2] = make_float4(v[6], v[7], v[8], 0.f);
+        }
+        if (c->n_scene) CKC(cudaMemcpy(c->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    c->stage_f4 = 4 + 4 * (size_t)c->n_recv_nodes + 3 * (size_t)std::max<int64_t>(1, n_recv);
+    CKC(cudaMallocHost(&c->h_stage, c->stage_f4 * sizeof(float4)));
+    CKC(cudaMallocHost(&c->h_counters, 2 * sizeof(unsigned long long)));
+
+    // IR buffers (OR/AudioRenderer.cpp:81-85) and the fp64 accumulation histogram
+    const size_t irn = (size_t)c->bands * c->ir_len;
+    CKC(cudaMalloc(&c->d_hist, 2 * irn * sizeof(double)));
+    CKC(cudaMalloc(&c->d_ir_l, irn * sizeof(float)));
+    CKC(cudaMalloc(&c->d_ir_r, irn * sizeof(float)));
+    CKC(cudaMemset(c->d_hist, 0, 2 * irn * sizeof(double)));
+    CKC(cudaMemset(c->d_ir_l, 0, irn * sizeof(float)));
+    CKC(cudaMemset(c->d_ir_r, 0, irn * sizeof(float)));
+    CKC(cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
+    if (desc->record_rays) {
+        c->rec_capacity = n_total;
+        CKC(cudaMalloc(&c->d_rec_bin, (size_t)n_total * sizeof(int)));
+        CKC(cudaMalloc(&c->d_rec_ear, (size_t)n_total * sizeof(int)));
+        CKC(cudaMalloc(&c->d_rec_nseg, (size_t)n_total * sizeof(int)));
+        CKC(cudaMalloc(&c->d_rec_energy, (size_t)n_total * c->bands * sizeof(float)));
+    }
+#undef CKC
+    (void)rc;
+    *out = c;
+    return ARV2_OK;
+}
+
+void arv2_destroy(arv2_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_keep); cudaFree(c->d_scatter);
+    cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_ir_r); cudaFree(c->d_counters);
+    cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
+    cudaFree(c->d_pc_org); cudaFree(c->d_pc_dir); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg);
+    cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int arv2_set_emitter(arv2_ctx* c, float x, float y, float z)
+{
+    REQUIRE(c, "null ctx");
+    c->emitter[0] = x; c->emitter[1] = y; c->emitter[2] = z;
+    c->cache_valid = false;
+    return ARV2_OK;
+}
+
+int arv2_set_receiver(arv2_ctx* c, float x, float y, float z, float yaw_deg)
+{
+    REQUIRE(c, "null ctx");
+    c->center[0] = x; c->center[1] = y; c->center[2] = z; c->yaw = yaw_deg;
+    c->recv_dirty = true;
+    return ARV2_OK;
+}
+
+int arv2_set_thresholds(arv2_ctx* c, float energy, uint32_t max_bounces)
+{
+    REQUIRE(c, "null ctx");
+    c->energy_thres = energy; c->max_bounces = max_bounces; c->cache_valid = false;
+    return ARV2_OK;
+}
+
+int arv2_set_base_power(arv2_ctx* c, float v) { REQUIRE(c, "null ctx"); c->base_power = v; c->cache_valid = false; return ARV2_OK; }
+int arv2_set_hrtf_absorption_rate(arv2_ctx* c, float v) { REQUIRE(c, "null ctx"); c->hrtf = v; return ARV2_OK; }
+int arv2_set_mono(arv2_ctx* c, int32_t v) { REQUIRE(c, "null ctx"); c->mono = v ? 1 : 0; return ARV2_OK; }
+int arv2_set_seed(arv2_ctx* c, uint64_t s) { REQUIRE(c, "null ctx"); c->seed = s; c->cache_valid = false; return ARV2_OK; }
+int arv2_set_stream(arv2_ctx* c, void* s) { REQUIRE(c, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return ARV2_OK; }
+
+int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t zero_first, double* ms)
+{
+    REQUIRE(c, "null ctx");
+    REQUIRE(ray_begin >= 0 && n_rays >= 0 && ray_begin + n_rays <= c->n_rays_total, "ray range outside the seeded set");
+    CK(cudaSetDevice(c->device));
+    int rc = upload_receiver(c);
+    if (rc != ARV2_OK) return rc;
+    const size_t irn = (size_t)c->bands * c->ir_len;
+    if (zero_first) CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));   // fillZeros, OR/AudioRenderer.cpp:491-492
+    CK(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    TraceParams p;
+    fill_params(c, &p, ray_begin, n_rays);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (n_rays > 0) CK(launch_trace(p, c->bands, 0, c->sm_count, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->last_range_rays = n_rays;
+    return finish_timed(c, ms);
+}
+
+int arv2_finalize(arv2_ctx* c)
+{
+    REQUIRE(c, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(launch_finalize(c->d_hist, c->bands, c->ir_len, c->mono, c->d_ir_l, c->d_ir_r, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ARV2_OK;
+}
+
+int arv2_rerender(arv2_ctx* c, double* ms)
+{
+    REQUIRE(c, "null ctx");
+    if (!c->desc.path_cache || !c->cache_valid) { set_error("arv2_rerender: no valid path cache (desc.path_cache + arv2_render first)"); return ARV2_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    int rc = upload_receiver(c);
+    if (rc != ARV2_OK) return rc;
+    const size_t irn = (size_t)c->bands * c->ir_len;
+    TraceParams p;
+    fill_params(c, &p, 0, c->n_rays_total);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    CK(launch_rerender(p, c->bands, c->sm_count, c->stream));
+    CK(launch_finalize(c->d_hist, c->bands, c->ir_len, c->mono, c->d_ir_l, c->d_ir_r, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->last_range_rays = c->n_rays_total;
+    return finish_timed(c, ms);
+}
+
+int arv2_render(arv2_ctx* c, double* ms)
+{
+    REQUIRE(c, "null ctx");
+    if (!c->desc.path_cache) {
+        int rc = arv2_render_range(c, 0, c->n_rays_total, 1, ms);
+        if (rc != ARV2_OK) return rc;
+        return arv2_finalize(c);
+    }
+    // path-cache mode: trace the receiver-independent paths once, then scan them
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_cache(c);
+    if (rc != ARV2_OK) return rc;
+    double ms_build = 0.0;
+    if (!c->cache_valid) {
+        rc = upload_receiver(c);
+        if (rc != ARV2_OK) return rc;
+        CK(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+        TraceParams p;
+        fill_params(c, &p, 0, c->n_rays_total);
+        p.root = 1;                                       // scene sub-tree only
+        p.rec_bin = nullptr; p.rec_ear = nullptr; p.rec_energy = nullptr; p.rec_nseg = nullptr;
+        CK(cudaEventRecord(c->ev0, c->stream));
+        CK(launch_trace(p, c->bands, 1, c->sm_count, c->stream));
+        CK(cudaEventRecord(c->ev1, c->stream));
+        rc = finish_timed(c, &ms_build);
+        if (rc != ARV2_OK) return rc;
+        c->cache_valid = true;
+    }
+    double ms_scan = 0.0;
+    rc = arv2_rerender(c, &ms_scan);
+    if (ms) *ms = ms_build + ms_scan;
+    return rc;
+}
+
+int arv2_ir_length(const arv2_ctx* c, int32_t* ir_length, int32_t* bands)
+{
+    REQUIRE(c, "null ctx");
+    if (ir_length) *ir_length = c->ir_len;
+    if (bands) *bands = c->bands;
+    return ARV2_OK;
+}
+
+int arv2_get_ir(arv2_ctx* c, float* l, float* r)
+{
+    REQUIRE(c, "null ctx");
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->bands * c->ir_len * sizeof(float);
+    CK(cudaStreamSynchronize(c->stream));
+    if (l) CK(cudaMemcpy(l, c->d_ir_l, bytes, cudaMemcpyDeviceToHost));
+    if (r) CK(cudaMemcpy(r, c->d_ir_r, bytes, cudaMemcpyDeviceToHost));
+    return ARV2_OK;
+}
+
+int arv2_set_ir(arv2_ctx* c, const float* l, const float* r)
+{
+    REQUIRE(c && l && r, "null argument");
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->ir_len * sizeof(float);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(c->d_ir_l, l, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_ir_r, r, bytes, cudaMemcpyHostToDevice));
+    return ARV2_OK;
+}
+
+int arv2_ir_device(arv2_ctx* c, float** l, float** r)
+{
+    REQUIRE(c, "null ctx");
+    if (l) *l = c->d_ir_l;
+    if (r) *r = c->d_ir_r;
+    return ARV2_OK;
+}
+
+int arv2_hist_device(arv2_ctx* c, double** h, int64_t* count)
+{
+    REQUIRE(c, "null ctx");
+    if (h) *h = c->d_hist;
+    if (count) *count = 2LL * c->bands * c->ir_len;
+    return ARV2_OK;
+}
+
+int arv2_last_segments(arv2_ctx* c, int64_t* segs)
+{
+    REQUIRE(c && segs, "null argument");
+    *segs = c->last_segments;
+    return ARV2_OK;
+}
+
+int arv2_get_records(arv2_ctx* c, int32_t* bin, int32_t* ear, float* energy, int32_t* nseg)
+{
+    REQUIRE(c, "null ctx");
+    if (!c->desc.record_rays) { set_error("records not enabled (desc.record_rays)"); return ARV2_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)c->last_range_rays;
+    if (bin) CK(cudaMemcpy(bin, c->d_rec_bin, n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (ear) CK(cudaMemcpy(ear, c->d_rec_ear, n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (nseg) CK(cudaMemcpy(nseg, c->d_rec_nseg, n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (energy) CK(cudaMemcpy(energy, c->d_rec_energy, n * c->bands * sizeof(float), cudaMemcpyDeviceToHost));
+    return ARV2_OK;
+}
+
+int arv2_write_ir_text(arv2_ctx* c, const char* left_path, const char* right_path)
+{
+    REQUIRE(c && left_path && right_path, "null argument");
+    std::vector<float> l((size_t)c->bands * c->ir_len), r(l.size());
+    const int rc = arv2_get_ir(c, l.data(), r.data());
+    if (rc != ARV2_OK) return rc;
+    std::ofstream fl(left_path), fr(right_path);
+    if (!fl.is_open() && !fr.is_open()) { set_error("Error opening the file."); return ARV2_ERR_IO; }   // OR/AudioRenderer.cpp:544-547
+    for (int i = 0; i < c->ir_len; ++i) { fl << l[i] << std::endl; fr << r[i] << std::endl; }         // :553-557
+    return ARV2_OK;
+}
+
+/* ------------------------------------------------------------ convolution -- */
+int arv2_convolve_file(arv2_ctx* c, const float* x, size_t n, float* y_left, float* y_right, int32_t mode,
+                       double* conv_ms, double* process_ms)
+{
+    REQUIRE(c && x && y_left && y_right, "arv2_convolve_file: null argument");
+    REQUIRE(mode == ARV2_CONV_LINEAR || mode == ARV2_CONV_REFERENCE, "unknown convolution mode");
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    CK(cudaSetDevice(c->device));
+    if (n == 0) { if (conv_ms) *conv_ms = 0; if (process_ms) *process_ms = 0; return ARV2_OK; }
+    const int block = 512, N = 2 * block;
+    const int ir_len = c->ir_len;
+    const int P = (ir_len + block - 1) / block;
+    const long long fs = c->desc.sample_rate;
+    long long seg_len, wrap, seg_out; int n_seg, bps; float gain;
+    if (mode == ARV2_CONV_LINEAR) {
+        seg_len = (long long)n; n_seg = 1; wrap = 0; seg_out = (long long)n; gain = 1.0f;
+        bps = (int)((n + block - 1) / block);
+    } else {
+        // OR/kernels.cu:410  secondsToProcess = samples_len / sample_rate; FFT size == ir_len
+        seg_len = fs; n_seg = (int)((long long)n / fs); wrap = ir_len; seg_out = ir_len;
+        gain = (float)ir_len / (float)(ir_len / 2);          // OR/AudioRenderer.cpp:709
+        bps = (int)((fs + block - 1) / block);
+    }
+    arv2_ctx::ConvWork& w = c->conv;
+    if (!w.d_tw) {
+        CK(cudaMalloc(&w.d_tw, N * sizeof(float2)));
+        CK(conv_upload_twiddles(w.d_tw, N, c->stream));
+    }
+    const size_t need_x = n, need_X = (size_t)std::max(1, n_seg * bps) * block, need_H = (size_t)2 * P * block;
+    if (w.cap_x < need_x) {
+        cudaFree(w.d_x); cudaFree(w.d_out);
+        w.d_x = nullptr; w.d_out = nullptr; w.cap_x = 0;
+        CK(cudaMalloc(&w.d_x, need_x * sizeof(float)));
+        CK(cudaMalloc(&w.d_out, 2 * need_x * sizeof(float)));
+        w.cap_x = need_x;
+    }
+    if (w.cap_X < need_X) { cudaFree(w.d_X); w.d_X = nullptr; w.cap_X = 0; CK(cudaMalloc(&w.d_X, need_X * sizeof(float2))); w.cap_X = need_X; }
+    if (w.cap_H < need_H) { cudaFree(w.d_H); w.d_H = nullptr; w.cap_H = 0; CK(cudaMalloc(&w.d_H, need_H * sizeof(float2))); w.cap_H = need_H; }
+
+    CK(cudaMemcpyAsync(w.d_x, x, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));      // OR/AudioRenderer.cpp:673
+    CK(cudaMemsetAsync(w.d_out, 0, 2 * n * sizeof(float), c->stream));                        // :682-683
+    CK(cudaEventRecord(c->ev0, c->stream));
+    // IR spectra of both ears (band 0): items = {ir_left, ir_right}
+    CK(conv_ir_spectra(c->d_ir_l, 1, ir_len, block, P, w.d_tw, w.d_H, c->stream));
+    CK(conv_ir_spectra(c->d_ir_r, 1, ir_len, block, P, w.d_tw, w.d_H + (size_t)P * block, c->stream));
+    if (n_seg > 0) {
+        CK(conv_block_spectra(w.d_x, (long long)n, seg_len, n_seg, bps, block, w.d_tw, w.d_X, c->stream));
+        ConvFileArgs a{};
+        a.X = w.d_X; a.H = w.d_H; a.out_l = w.d_out; a.out_r = w.d_out + n; a.tw = w.d_tw;
+        a.n = (long long)n; a.seg_len = seg_len; a.wrap = wrap; a.seg_out = seg_out;
+        a.n_seg = n_seg; a.blocks_per_seg = bps; a.block = block; a.P = P; a.gain = gain;
+        CK(conv_file(a, c->stream));
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaMemcpyAsync(y_left, w.d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));   // :702-703
+    CK(cudaMemcpyAsync(y_right, w.d_out + n, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (conv_ms) { float t = 0.f; CK(cudaEventElapsedTime(&t, c->ev0, c->ev1)); *conv_ms = t; }
+    if (process_ms) *process_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    return ARV2_OK;
+}
+
+int arv2_stream_open(int32_t device, int32_t n_sources, int32_t block, int32_t ir_length, arv2_stream** out)
+{
+    REQUIRE(out && n_sources > 0 && ir_length > 0, "arv2_stream_open: bad argument");
+    REQUIRE(block >= 64 && block <= 1024 && (block & (block - 1)) == 0, "block must be a power of two in [64,1024]");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    auto* s = new arv2_stream;
+    s->device = device; s->n_src = n_sources; s->block = block; s->ir_len = ir_length;
+    s->P = (ir_length + block - 1) / block;
+    const size_t spec = (size_t)s->P * block;          // float2 per (source) FDL or per ear
+#define CKS(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); arv2_stream_close(s); return ARV2_ERR_CUDA; } } while (0)
+    CKS(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CKS(cudaMalloc(&s->d_tw, 2 * block * sizeof(float2)));
+    CKS(conv_upload_twiddles(s->d_tw, 2 * block, s->stream));
+    CKS(cudaMalloc(&s->d_fdl, (size_t)n_sources * spec * sizeof(float2)));
+    for (int b = 0; b < 2; ++b) {
+        CKS(cudaMalloc(&s->d_H[b], (size_t)n_sources * 2 * spec * sizeof(float2)));
+        CKS(cudaMemsetAsync(s->d_H[b], 0, (size_t)n_sources * 2 * spec * sizeof(float2), s->stream));
+    }
+    CKS(cudaMalloc(&s->d_Hptr, n_sources * sizeof(float2*)));
+    CKS(cudaMallocHost(&s->h_Hptr, n_sources * sizeof(float2*)));
+    s->active.assign(n_sources, 0);
+    for (int i = 0; i < n_sources; ++i) s->h_Hptr[i] = s->d_H[0] + (size_t)i * 2 * spec;
+    CKS(cudaMemcpyAsync(s->d_Hptr, s->h_Hptr, n_sources * sizeof(float2*), cudaMemcpyHostToDevice, s->stream));
+    CKS(cudaMalloc(&s->d_tail, (size_t)n_sources * 2 * block * sizeof(float)));
+    CKS(cudaMalloc(&s->d_in, (size_t)n_sources * block * sizeof(float)));
+    CKS(cudaMalloc(&s->d_out, (size_t)n_sources * 2 * block * sizeof(float)));
+    CKS(cudaMalloc(&s->d_ir, (size_t)2 * ir_length * sizeof(float)));
+    CKS(cudaMallocHost(&s->h_in, (size_t)n_sources * block * sizeof(float)));
+    CKS(cudaMallocHost(&s->h_out, (size_t)n_sources * 2 * block * sizeof(float)));
+    CKS(cudaMallocHost(&s->h_ir, (size_t)2 * ir_length * sizeof(float)));
+#undef CKS
+    *out = s;
+    return arv2_stream_reset(s);
+}
+
+int arv2_stream_reset(arv2_stream* s)
+{
+    REQUIRE(s, "null stream");
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemsetAsync(s->d_fdl, 0, (size_t)s->n_src * s->P * s->block * sizeof(float2), s->stream));
+    CK(cudaMemsetAsync(s->d_tail, 0, (size_t)s->n_src * 2 * s->block * sizeof(float), s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->slot = s->P - 1;
+    return ARV2_OK;
+}
+
+static int stream_swap_ir(arv2_stream* s, int32_t source)
+{
+    // spectra go into the inactive buffer; the pointer table flips in stream order, i.e.
+    // exactly at a block boundary
+    const size_t spec = (size_t)s->P * s->block;
+    const int nb = 1 - s->active[source];
+    float2* H = s->d_H[nb] + (size_t)source * 2 * spec;
+    CK(conv_ir_spectra(s->d_ir, 2, s->ir_len, s->block, s->P, s->d_tw, H, s->stream));
+    s->active[source] = nb;
+    s->h_Hptr[source] = H;
+    CK(cudaMemcpyAsync(s->d_Hptr + source, s->h_Hptr + source, sizeof(float2*), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return ARV2_OK;
+}
+
+int arv2_stream_set_ir(arv2_stream* s, int32_t source, const float* l, const float* r)
+{
+    REQUIRE(s && l && r && source >= 0 && source < s->n_src, "arv2_stream_set_ir: bad argument");
+    CK(cudaSetDevice(s->device));
+    std::memcpy(s->h_ir, l, (size_t)s->ir_len * sizeof(float));
+    std::memcpy(s->h_ir + s->ir_len, r, (size_t)s->ir_len * sizeof(float));
+    CK(cudaMemcpyAsync(s->d_ir, s->h_ir, (size_t)2 * s->ir_len * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    return stream_swap_ir(s, source);
+}
+
+int arv2_stream_set_ir_device(arv2_stream* s, int32_t source, const float* dl, const float* dr)
+{
+    REQUIRE(s && dl && dr && source >= 0 && source < s->n_src, "arv2_stream_set_ir_device: bad argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemcpyAsync(s->d_ir, dl, (size_t)s->ir_len * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_ir + s->ir_len, dr, (size_t)s->ir_len * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+    return stream_swap_ir(s, source);
+}
+
+int arv2_stream_process_device(arv2_stream* s, const float* d_in, float* d_out, void* cuda_stream)
+{
+    REQUIRE(s && d_in && d_out, "arv2_stream_process_device: null argument");
+    s->slot = (s->slot + 1) % s->P;
+    ConvStreamArgs a{};
+    a.in = d_in; a.out = d_out; a.fdl = s->d_fdl; a.H = (const float2* const*)s->d_Hptr; a.tail = s->d_tail; a.tw = s->d_tw;
+    a.n_src = s->n_src; a.block = s->block; a.P = s->P; a.slot = s->slot;
+    CK(conv_stream_step(a, cuda_stream ? (cudaStream_t)cuda_stream : s->stream));
+    return ARV2_OK;
+}
+
+int arv2_stream_process(arv2_stream* s, const float* in, float* out)
+{
+    REQUIRE(s && in && out, "arv2_stream_process: null argument");
+    CK(cudaSetDevice(s->device));
+    const size_t nin = (size_t)s->n_src * s->block, nout = 2 * nin;
+    std::memcpy(s->h_in, in, nin * sizeof(float));
+    CK(cudaMemcpyAsync(s->d_in, s->h_in, nin * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    const int rc = arv2_stream_process_device(s, s->d_in, s->d_out, nullptr);
+    if (rc != ARV2_OK) return rc;
+    CK(cudaMemcpyAsync(s->h_out, s->d_out, nout * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    std::memcpy(out, s->h_out, nout * sizeof(float));
+    return ARV2_OK;
+}
+
+void arv2_stream_close(arv2_stream* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaFree(s->d_tw); cudaFree(s->d_fdl); cudaFree(s->d_H[0]); cudaFree(s->d_H[1]); cudaFree(s->d_Hptr);
+    cudaFree(s->d_tail); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_ir);
+    if (s->h_Hptr) cudaFreeHost(s->h_Hptr);
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->h_ir) cudaFreeHost(s->h_ir);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+/* ------------------------------------------------------------------ audio -- */
+int arv2_wav_read(const char* path, float** samples, size_t* n, int32_t* sample_rate, int32_t* channels)
+{
+    REQUIRE(path && samples && n && sample_rate && channels, "arv2_wav_read: null argument");
+    std::string err;
+    const int rc = wav_read(path, samples, n, sample_rate, channels, &err);
+    if (rc != ARV2_OK) set_error(err);
+    return rc;
+}
+
+int arv2_wav_write_stereo_normalized(const char* path, const float* l, const float* r, size_t n, int32_t rate)
+{
+    REQUIRE(path && l && r, "arv2_wav_write_stereo_normalized: null argument");
+    std::string err;
+    const int rc = wav_write_stereo_normalized(path, l, r, n, rate, &err);
+    if (rc != ARV2_OK) set_error(err);
+    return rc;
+}
+
+void arv2_free(void* p) { std::free(p); }
+
+} // extern "C"

@@ -1,0 +1,56 @@
+// conv.cuh -- launch interface of the sm_100a partitioned FFT convolver (conv.cu).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace arv2 {
+
+// Spectra are stored "packed": N = 2*block real samples -> block complex values, bin 0
+// holding (DC, Nyquist) in (re, im) -- both are purely real for a real signal -- so a
+// spectrum is exactly `block` float2 (4 KB at block = 512) and rows stay 16 B aligned.
+
+constexpr int kConvThreads = 256;
+constexpr int kConvCluster = 8;      // CTAs cooperating on one (source, block) via DSMEM
+
+// Twiddle table W_N^k = exp(-2*pi*i*k/N), k < N, computed in fp64 on the host.
+cudaError_t conv_upload_twiddles(float2* d_tw, int N, cudaStream_t stream);
+
+// K10: IR -> partition spectra.  h: [n_items][ir_len] (device), H: [n_items][P][block].
+cudaError_t conv_ir_spectra(const float* d_h, int n_items, int ir_len, int block, int P, const float2* d_tw,
+                            float2* d_H, cudaStream_t stream);
+
+// Forward spectra of consecutive zero-padded input blocks (file mode).
+// x: [n] samples; block j of segment s covers x[s*seg_len + j*block ...) clipped to the
+// segment and to n.  X: [n_seg*blocks_per_seg][block].
+cudaError_t conv_block_spectra(const float* d_x, long long n, long long seg_len, int n_seg, int blocks_per_seg,
+                               int block, const float2* d_tw, float2* d_X, cudaStream_t stream);
+
+struct ConvStreamArgs {
+    const float* in;         // [n_src][block] newest input block per source
+    float* out;              // [n_src][2][block]
+    float2* fdl;             // [n_src][P][block] ring of input spectra
+    const float2* const* H;  // [n_src] -> [2][P][block] active IR spectra of each source
+    float* tail;             // [n_src][2][block] overlap-add tails
+    const float2* tw;
+    int n_src, block, P, slot; // slot = ring position of the newest block
+};
+// One streaming step for all sources: forward FFT + FDL write + partitioned spectral MAC
+// + DSMEM reduction + stereo inverse FFT + overlap-add, in ONE cluster launch.
+cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream);
+
+struct ConvFileArgs {
+    const float2* X;         // [n_seg*blocks_per_seg][block]
+    const float2* H;         // [2][P][block]
+    float* out_l; float* out_r; // [n] pre-zeroed, accumulated with RED.ADD.F32
+    const float2* tw;
+    long long n;             // output length
+    long long seg_len;       // samples between segment starts (== n for one segment)
+    long long wrap;          // circular length (reference mode: ir_len); <=0: linear
+    long long seg_out;       // samples of a segment's result that are kept (reference: ir_len)
+    int n_seg, blocks_per_seg, block, P;
+    float gain;
+};
+cudaError_t conv_file(const ConvFileArgs& a, cudaStream_t stream);
+
+} // namespace arv2

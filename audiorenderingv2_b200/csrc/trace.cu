@@ -1,0 +1,421 @@
+// trace.cu -- sm_100a sound-ray tracing kernels of libarv2.
+//
+// Replaces the OptiX pipeline of the reference (B200 has no RT cores):
+//   __raygen__renderFrame     OR/devicePrograms.cu:192-254  -> trace_kernel (path loop)
+//   optixTrace / GAS traversal OR/devicePrograms.cu:240-251 -> closest_hit (software BVH)
+//   __closesthit__radiance    OR/devicePrograms.cu:62-180   -> shade step in trace_kernel
+//   __miss__radiance          OR/devicePrograms.cu:186-190  -> "no hit" branch
+//   fillZeros / addIRs        OR/kernels.cu:77-97,519-536   -> cudaMemsetAsync / finalize_kernel
+//
+// Design: persistent CTAs; every warp keeps 32 paths in flight and refills lanes whose
+// path ended from a warp-local chunk of the seeded ray set (ballot + popc compaction),
+// so no ray state ever goes through HBM.  Receiver deposits are aggregated across the
+// warp (match.any) and accumulated in an fp64 histogram with native RED.F64, which
+// makes the result independent of the deposit order to ~1e-16.
+#include <climits>
+
+#include "arv2_model.cuh"
+#include "trace.cuh"
+
+namespace arv2 {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kChunk = 128;          // rays a warp claims per global atomic
+constexpr int kStack = 64;
+constexpr int kThreads = 256;
+constexpr int kSentinel = INT_MIN;
+
+struct Hit { float t, u, v; int slot, id; };
+
+__device__ __forceinline__ float safe_rcp(float d)
+{
+    const float eps = 1e-20f;
+    return 1.0f / (fabsf(d) > eps ? d : copysignf(eps, d));
+}
+
+// Closest hit = min (t, global triangle id) over all triangles whose exact test
+// accepts; the BVH only prunes (boxes are padded, comparison is <=).
+__device__ __forceinline__ void closest_hit(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                            int root, F3 org, F3 dir, float tmax, Hit& h)
+{
+    const float ix = safe_rcp(dir.x), iy = safe_rcp(dir.y), iz = safe_rcp(dir.z);
+    const float ox = org.x * ix, oy = org.y * iy, oz = org.z * iz;
+    int stack[kStack];
+    int sp = 0;
+    stack[sp++] = kSentinel;
+    int cur = root;
+    h.t = tmax; h.u = 0.f; h.v = 0.f; h.slot = -1; h.id = INT_MAX;
+
+    while (cur != kSentinel) {
+        while (cur >= 0) {
+            const float4 n0 = __ldg(nodes + cur * 4 + 0);
+            const float4 n1 = __ldg(nodes + cur * 4 + 1);
+            const float4 n2 = __ldg(nodes + cur * 4 + 2);
+            const float4 n3 = __ldg(nodes + cur * 4 + 3);
+            const float c0lox = fmaf(n0.x, ix, -ox), c0hix = fmaf(n0.y, ix, -ox);
+            const float c0loy = fmaf(n0.z, iy, -oy), c0hiy = fmaf(n0.w, iy, -oy);
+            const float c0loz = fmaf(n2.x, iz, -oz), c0hiz = fmaf(n2.y, iz, -oz);
+            const float c1lox = fmaf(n1.x, ix, -ox), c1hix = fmaf(n1.y, ix, -ox);
+            const float c1loy = fmaf(n1.z, iy, -oy), c1hiy = fmaf(n1.w, iy, -oy);
+            const float c1loz = fmaf(n2.z, iz, -oz), c1hiz = fmaf(n2.w, iz, -oz);
+            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.f));
+            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
+            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.f));
+            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
+            const bool go0 = c0min <= c0max, go1 = c1min <= c1max;
+            const int i0 = __float_as_int(n3.x), i1 = __float_as_int(n3.y);
+            if (!go0 && !go1) {
+                cur = stack[--sp];
+            } else {
+                cur = go0 ? i0 : i1;
+                if (go0 && go1) {
+                    int far = i1;
+                    if (c1min < c0min) { cur = i1; far = i0; }
+                    stack[sp++] = far;
+                }
+            }
+        }
+        if (cur == kSentinel) break;
+        // leaf
+        const int code = ~cur;
+        const int first = code >> 3;
+        const int cnt = (code & 7) + 1;
+        for (int i = 0; i < cnt; ++i) {
+            const int slot = first + i;
+            const float4 a = __ldg(tris + slot * 3 + 0);
+            const float4 b = __ldg(tris + slot * 3 + 1);
+            const float4 c = __ldg(tris + slot * 3 + 2);
+            float t, u, v;
+            if (tri_test(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), org, dir, &t, &u, &v)) {
+                const int id = __float_as_int(a.w);
+                if (t < h.t || (t == h.t && id < h.id)) { h.t = t; h.u = u; h.v = v; h.slot = slot; h.id = id; }
+            }
+        }
+        cur = stack[--sp];
+    }
+}
+
+// Warp-aggregated deposit into the fp64 histogram (OR/devicePrograms.cu:128-170).
+// Called by all 32 lanes; `dep` lanes carry (bin, primary ear, energy[]).
+template <int NB>
+__device__ __forceinline__ void deposit_warp(const TraceParams& p, bool dep, int bin, int primary, const float* energy)
+{
+    const unsigned dm = __ballot_sync(FULL, dep);
+    if (dm == 0 || !dep) return;
+    const int key = bin | (primary << 30);
+    const unsigned peers = __match_any_sync(dm, key);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    const int obin = (bin + p.delay < p.ir_len) ? bin + p.delay : bin;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        double s = 0.0, sc = 0.0;
+        const float cross = __fmul_rn(energy[b], p.cross_gain);
+        unsigned m = peers;
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            s += (double)__shfl_sync(peers, energy[b], src);
+            sc += (double)__shfl_sync(peers, cross, src);
+        }
+        if (lane == leader) {
+            atomicAdd(p.hist + ((size_t)(primary * NB + b) * p.ir_len + bin), s);
+            if (!p.mono) atomicAdd(p.hist + ((size_t)((1 - primary) * NB + b) * p.ir_len + obin), sc);
+        }
+    }
+}
+
+// Receiver hit: chord weighting and bin (OR/devicePrograms.cu:91-133).
+template <int NB>
+__device__ __forceinline__ int receiver_hit(const TraceParams& p, F3 pt, F3 dir, float distance, float* energy)
+{
+    const float dinv = __fdiv_rn(1.0f, __fsqrt_rn(dot3(dir, dir)));
+    const F3 nd = f3(__fmul_rn(dir.x, dinv), __fmul_rn(dir.y, dinv), __fmul_rn(dir.z, dinv));
+    const F3 oc = sub3(pt, f3(p.center[0], p.center[1], p.center[2]));
+    const float a = dot3(nd, nd);
+    const float bq = __fmul_rn(2.0f, dot3(oc, nd));
+    const float c = __fsub_rn(dot3(oc, oc), 1.0f);
+    const float disc = __fmaf_rn(bq, bq, -__fmul_rn(__fmul_rn(4.0f, a), c));
+    float wgt = 0.f;
+    if (disc > 0.f) {
+        const float sq = __fsqrt_rn(disc);
+        const float a2 = __fmul_rn(2.0f, a);
+        const float t1 = __fdiv_rn(__fsub_rn(-bq, sq), a2);
+        const float t2 = __fdiv_rn(__fadd_rn(-bq, sq), a2);
+        const F3 i1 = f3(__fmaf_rn(t1, nd.x, pt.x), __fmaf_rn(t1, nd.y, pt.y), __fmaf_rn(t1, nd.z, pt.z));
+        const F3 i2 = f3(__fmaf_rn(t2, nd.x, pt.x), __fmaf_rn(t2, nd.y, pt.y), __fmaf_rn(t2, nd.z, pt.z));
+        const F3 df = sub3(i1, i2);
+        wgt = __fsqrt_rn(dot3(df, df));
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) energy[b] = __fmul_rn(energy[b], wgt);
+    const float elapsed = __fdiv_rn(distance, 343.0f);
+    return __float2int_rz(roundf(__fmul_rn(elapsed, p.fs)));
+}
+
+// Hit point and path length (OR/devicePrograms.cu:79-83).
+__device__ __forceinline__ F3 hit_point(F3 p1, F3 p2, F3 p3, float u, float v)
+{
+    const float w = __fsub_rn(__fsub_rn(1.0f, u), v);
+    return f3(__fmaf_rn(v, p3.x, __fmaf_rn(u, p2.x, __fmul_rn(w, p1.x))),
+              __fmaf_rn(v, p3.y, __fmaf_rn(u, p2.y, __fmul_rn(w, p1.y))),
+              __fmaf_rn(v, p3.z, __fmaf_rn(u, p2.z, __fmul_rn(w, p1.z))));
+}
+
+template <int NB, int MODE>
+__global__ void __launch_bounds__(kThreads) trace_kernel(const TraceParams p)
+{
+    const int lane = threadIdx.x & 31;
+    long long chunk_next = 0, chunk_end = 0;      // warp-uniform
+    bool have = false, exhausted = false;
+    long long ray = 0;
+    F3 org = f3(0, 0, 0), dir = f3(0, 0, 0);
+    float energy[NB];
+    float dist = 0.f;
+    int depth = 0, nseg = 0;
+    unsigned long long segs = 0;
+
+    for (;;) {
+        // ---- refill idle lanes from the warp's chunk (ballot/popc compaction)
+        unsigned need = __ballot_sync(FULL, !have && !exhausted);
+        while (need) {
+            if (chunk_next >= chunk_end) {
+                unsigned long long b = 0;
+                if (lane == 0) b = atomicAdd(p.counters, (unsigned long long)kChunk);
+                b = __shfl_sync(FULL, b, 0);
+                chunk_next = (long long)b;
+                chunk_end = min((long long)b + kChunk, p.n_rays);
+                if (chunk_next >= chunk_end) {
+                    if (!have) exhausted = true;
+                    break;
+                }
+            }
+            const int avail = (int)min((long long)32, chunk_end - chunk_next);
+            const int rank = __popc(need & ((1u << lane) - 1u));
+            if (((need >> lane) & 1u) && rank < avail) {
+                ray = chunk_next + rank;
+                have = true;
+                org = f3(p.emitter[0], p.emitter[1], p.emitter[2]);          // :210
+                dir = emit_direction(p.seed, (uint64_t)(p.ray_begin + ray)); // :216-224
+#pragma unroll
+                for (int b = 0; b < NB; ++b) energy[b] = p.energy0;          // :208
+                dist = 0.f; depth = 0; nseg = 0;                             // :209,:211
+            }
+            chunk_next += min(__popc(need), avail);
+            need = __ballot_sync(FULL, !have && !exhausted);
+        }
+        if (!__any_sync(FULL, have)) break;
+
+        bool ended = false, dep = false;
+        int bin = -1, ear = 0, primary = 0;
+        if (have) {
+            float emax = energy[0];
+#pragma unroll
+            for (int b = 1; b < NB; ++b) emax = fmaxf(emax, energy[b]);
+            const bool zero_dir = !(dir.x != 0.f || dir.y != 0.f || dir.z != 0.f);            // :230
+            if (zero_dir || !(dist < p.dist_thr && emax > p.energy_thres && (unsigned)depth < p.max_bounces)) {
+                ended = true;                                                                   // :233-236
+            } else {
+                const size_t ci = (size_t)nseg * (size_t)p.pc_stride + (size_t)ray;
+                if (MODE == 1) {
+                    p.pc_dir_d[ci] = make_float4(dir.x, dir.y, dir.z, dist);
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) p.pc_energy[ci * NB + b] = energy[b];
+                }
+                nseg++;
+                Hit h;
+                closest_hit(p.nodes, p.tris, p.root, org, dir, 1e20f, h);
+                if (MODE == 1) p.pc_org_t[ci] = make_float4(org.x, org.y, org.z, h.t);
+                if (h.slot < 0) {
+                    ended = true;                                                               // miss :186-190
+                } else {
+                    const float4 a = __ldg(p.tris + h.slot * 3 + 0);
+                    const float4 b4 = __ldg(p.tris + h.slot * 3 + 1);
+                    const float4 c4 = __ldg(p.tris + h.slot * 3 + 2);
+                    const F3 p1 = f3(a.x, a.y, a.z), p2 = f3(b4.x, b4.y, b4.z), p3 = f3(c4.x, c4.y, c4.z);
+                    const int mat = __float_as_int(b4.w);
+                    const F3 pt = hit_point(p1, p2, p3, h.u, h.v);
+                    const F3 dp = sub3(pt, org);
+                    dist = __fadd_rn(dist, __fsqrt_rn(dot3(dp, dp)));                           // :83
+                    if (mat < 0) {
+                        bin = receiver_hit<NB>(p, pt, dir, dist, energy);
+                        ear = (mat == -1) ? 1 : 2;
+                        primary = (mat == -1) ? 0 : 1;
+                        dep = bin >= 0 && bin < p.ir_len;
+                        ended = true;                                                           // :147,:169
+                    } else {
+                        // :75-77  Ng = normalize(cross(P2-P1, P3-P1))
+                        const F3 nc = cross3(sub3(p2, p1), sub3(p3, p1));
+                        const float ninv = __fdiv_rn(1.0f, __fsqrt_rn(dot3(nc, nc)));
+                        const F3 ng = f3(__fmul_rn(nc.x, ninv), __fmul_rn(nc.y, ninv), __fmul_rn(nc.z, ninv));
+                        bool diffuse = false;
+                        uint32_t r[4];
+                        if (p.any_scatter) {
+                            const float sc = __ldg(p.scattering + mat);
+                            if (sc > 0.f) {
+                                philox4x32(p.seed, (uint64_t)(p.ray_begin + ray), (uint32_t)depth, 1u, r);
+                                diffuse = __fmul_rn((float)(r[0] >> 8), 0x1p-24f) < sc;
+                            }
+                        }
+                        if (diffuse) {
+                            dir = lambert_direction(r, dir, ng);
+                        } else {
+                            const float k = __fmul_rn(2.0f, dot3(dir, ng));                     // :173
+                            dir = f3(__fmaf_rn(-k, ng.x, dir.x), __fmaf_rn(-k, ng.y, dir.y), __fmaf_rn(-k, ng.z, dir.z));
+                        }
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) energy[b] = __fmul_rn(energy[b], __ldg(p.keep + mat * NB + b)); // :174
+                        depth++;                                                                // :175
+                        org = f3(__fmaf_rn(1e-3f, dir.x, pt.x), __fmaf_rn(1e-3f, dir.y, pt.y), __fmaf_rn(1e-3f, dir.z, pt.z)); // :179
+                    }
+                }
+            }
+        }
+        if (MODE == 0) deposit_warp<NB>(p, dep, bin, primary, energy);
+        if (ended) {
+            if (p.rec_bin) p.rec_bin[ray] = bin;
+            if (p.rec_ear) p.rec_ear[ray] = ear;
+            if (p.rec_nseg) p.rec_nseg[ray] = nseg;
+            if (p.rec_energy) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = ear ? energy[b] : 0.f;
+            }
+            if (MODE == 1) p.pc_nseg[ray] = nseg;
+            segs += (unsigned long long)nseg;
+            have = false;
+        }
+    }
+    // one atomic per warp for the segment counter
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
+    if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+}
+
+// Receiver move: walk each ray's cached receiver-independent segments in order and
+// deposit at the first one the receiver intercepts before the wall (t_recv < t_wall;
+// ties go to the scene because scene triangle ids are lower).  One thread per ray,
+// lanes = consecutive rays, so every load of segment k is a coalesced 512 B row.
+template <int NB>
+__global__ void __launch_bounds__(kThreads) rerender_kernel(const TraceParams p)
+{
+    const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = ray < p.n_rays;
+    const int n = valid ? p.pc_nseg[ray] : 0;
+    // receiver bounds = child 1 of the top node
+    const float4 t1 = __ldg(p.nodes + 1), t2 = __ldg(p.nodes + 2);
+    int k = 0;
+    bool done = !valid;
+    int rbin = -1, rear = 0, rnseg = n;
+    float energy[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) energy[b] = 0.f;
+    for (;;) {
+        if (!__any_sync(FULL, !done && k < n)) break;
+        bool dep = false;
+        int bin = -1, primary = 0;
+        if (!done && k < n) {
+            const size_t ci = (size_t)k * (size_t)p.pc_stride + (size_t)ray;
+            const float4 ot = __ldcs(p.pc_org_t + ci);
+            const float4 dd = __ldcs(p.pc_dir_d + ci);
+            const F3 org = f3(ot.x, ot.y, ot.z), dir = f3(dd.x, dd.y, dd.z);
+            // slab test against the receiver's box first
+            const float ix = safe_rcp(dir.x), iy = safe_rcp(dir.y), iz = safe_rcp(dir.z);
+            const float lx = (t1.x - org.x) * ix, hx = (t1.y - org.x) * ix;
+            const float ly = (t1.z - org.y) * iy, hy = (t1.w - org.y) * iy;
+            const float lz = (t2.z - org.z) * iz, hz = (t2.w - org.z) * iz;
+            const float tmin = fmaxf(fmaxf(fminf(lx, hx), fminf(ly, hy)), fmaxf(fminf(lz, hz), 0.f));
+            const float tmax = fminf(fminf(fmaxf(lx, hx), fmaxf(ly, hy)), fminf(fmaxf(lz, hz), ot.w));
+            if (tmin <= tmax) {
+                Hit h;
+                closest_hit(p.nodes, p.tris, p.recv_root, org, dir, ot.w, h);
+                if (h.slot >= 0 && h.t < ot.w) {
+                    const float4 a = __ldg(p.tris + h.slot * 3 + 0);
+                    const float4 b4 = __ldg(p.tris + h.slot * 3 + 1);
+                    const float4 c4 = __ldg(p.tris + h.slot * 3 + 2);
+                    const int mat = __float_as_int(b4.w);
+                    const F3 pt = hit_point(f3(a.x, a.y, a.z), f3(b4.x, b4.y, b4.z), f3(c4.x, c4.y, c4.z), h.u, h.v);
+                    const F3 dp = sub3(pt, org);
+                    const float dist = __fadd_rn(dd.w, __fsqrt_rn(dot3(dp, dp)));
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) energy[b] = p.pc_energy[ci * NB + b];
+                    bin = receiver_hit<NB>(p, pt, dir, dist, energy);
+                    primary = (mat == -1) ? 0 : 1;
+                    dep = bin >= 0 && bin < p.ir_len;
+                    rbin = bin; rear = (mat == -1) ? 1 : 2; rnseg = k + 1;
+                    done = true;
+                }
+            }
+            k++;
+        }
+        deposit_warp<NB>(p, dep, bin, primary, energy);
+    }
+    if (valid) {
+        if (p.rec_bin) p.rec_bin[ray] = rbin;
+        if (p.rec_ear) p.rec_ear[ray] = rear;
+        if (p.rec_nseg) p.rec_nseg[ray] = rnseg;
+        if (p.rec_energy) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = rear ? energy[b] : 0.f;
+        }
+    }
+    unsigned long long segs = (unsigned long long)rnseg;
+    if (!valid) segs = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
+    if ((threadIdx.x & 31) == 0 && segs) atomicAdd(p.counters + 1, segs);
+}
+
+__global__ void finalize_kernel(const double* __restrict__ hist, int n, int mono, float* __restrict__ l, float* __restrict__ r)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = __double2float_rn(hist[i]), b = __double2float_rn(hist[n + i]);
+    if (mono) { const float s = __fadd_rn(a, b); l[i] = s; r[i] = s; }
+    else { l[i] = a; r[i] = b; }
+}
+
+template <int NB, int MODE>
+cudaError_t launch_trace_t(const TraceParams& p, int sm_count, cudaStream_t stream)
+{
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<NB, MODE>, kThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long want = (p.n_rays + kThreads - 1) / kThreads;
+    long long grid = (long long)sm_count * per_sm;
+    if (want < grid) grid = want < 1 ? 1 : want;
+    trace_kernel<NB, MODE><<<(unsigned)grid, kThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+cudaError_t launch_trace(const TraceParams& p, int bands, int mode, int sm_count, cudaStream_t stream)
+{
+    if (bands == 1) return mode == 0 ? launch_trace_t<1, 0>(p, sm_count, stream) : launch_trace_t<1, 1>(p, sm_count, stream);
+    if (bands == 8) return mode == 0 ? launch_trace_t<8, 0>(p, sm_count, stream) : launch_trace_t<8, 1>(p, sm_count, stream);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaStream_t stream)
+{
+    (void)sm_count;
+    const unsigned grid = (unsigned)((p.n_rays + kThreads - 1) / kThreads);
+    if (grid == 0) return cudaSuccess;
+    if (bands == 1) rerender_kernel<1><<<grid, kThreads, 0, stream>>>(p);
+    else if (bands == 8) rerender_kernel<8><<<grid, kThreads, 0, stream>>>(p);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const double* hist, int bands, int ir_len, int mono, float* ir_left, float* ir_right,
+                            cudaStream_t stream)
+{
+    const int n = bands * ir_len;
+    finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(hist, n, mono, ir_left, ir_right);
+    return cudaGetLastError();
+}
+
+} // namespace arv2

@@ -1,0 +1,45 @@
+// trace.cuh -- launch interface of the sm_100a trace kernels (trace.cu).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace arv2 {
+
+// Everything one render needs, passed by value as the kernel parameter
+// (the role of LaunchParams, OR/LaunchParams.h:20-43).
+struct TraceParams {
+    const float4* nodes;        // combined two-level BVH (arv2_internal.h layout)
+    const float4* tris;         // 3 x float4 per triangle, leaf order
+    const float* keep;          // [n_mats][bands]  1 - mat_absorption
+    const float* scattering;    // [n_mats]
+    double* hist;               // [2][bands][ir_len] fp64 accumulation
+    unsigned long long* counters; // [0] next ray chunk, [1] segments traced
+    int* rec_bin; int* rec_ear; float* rec_energy; int* rec_nseg;   // optional per-ray records
+    // receiver-independent path cache (optional): per segment k of ray r at [k*stride + r]
+    float4* pc_org_t;           // (origin.xyz, t_wall or 1e20 on miss)
+    float4* pc_dir_d;           // (dir.xyz, distance before the segment)
+    float* pc_energy;           // [k*stride + r][bands]
+    int* pc_nseg;               // [r] segments cached
+    long long pc_stride;
+    unsigned long long seed;
+    long long ray_begin, n_rays;
+    float emitter[3], center[3];
+    float energy0, energy_thres, dist_thr, cross_gain, fs;
+    unsigned max_bounces;
+    int delay, ir_len, mono;
+    int root;                   // node index traversal starts at
+    int recv_root;              // root of the receiver sub-tree
+    int any_scatter;            // 0: skip the diffuse-bounce RNG entirely
+};
+
+// mode 0: full trace (scene + receiver), deposits into hist.
+// mode 1: scene-only trace that fills the path cache (no deposits).
+cudaError_t launch_trace(const TraceParams& p, int bands, int mode, int sm_count, cudaStream_t stream);
+// Re-deposit from the path cache against the current receiver sub-tree.
+cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaStream_t stream);
+// hist (fp64) -> ir_left / ir_right (fp32); mono: L = R = L + R (OR/kernels.cu:519-527).
+cudaError_t launch_finalize(const double* hist, int bands, int ir_len, int mono, float* ir_left, float* ir_right,
+                            cudaStream_t stream);
+
+} // namespace arv2

@@ -1,0 +1,144 @@
+"""Parity of the CUDA convolver (through the C ABI) against the oracle: fp64 direct
+linear convolution (north_star: <= 1e-5 relative L2) and the restated reference file /
+live semantics."""
+import os
+
+import numpy as np
+import pytest
+
+import audiorenderingv2_b200 as arv
+import oracle
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def renderer(sample_rate, ir_seconds):
+    scene = arv.Scene.from_triangles(np.zeros((0, 3, 3), np.float32), np.zeros(0, np.int32), [])
+    return arv.AudioRenderer(scene, ir_seconds, sample_rate, [], (1, 1, 1))
+
+
+def decaying_ir(n, seed, rt60_s, fs):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / fs
+    return (rng.standard_normal(n) * np.exp(-6.9 * t / rt60_s)).astype(np.float32)
+
+
+def test_file_linear_vs_direct_fp64():
+    fs = 16000
+    r = renderer(fs, 1)
+    hl, hr = decaying_ir(fs, 1, 0.4, fs), decaying_ir(fs, 2, 0.3, fs)
+    r.set_ir(hl, hr)
+    x = np.load(os.path.join(GOLDEN, "guitar_2s.npy"))
+    yl, yr, _, _ = r.convoluteAudioFile(x, arv.CONV_LINEAR)
+    assert rel_l2(yl, oracle.direct_conv(x, hl)[: len(x)]) <= TOL
+    assert rel_l2(yr, oracle.direct_conv(x, hr)[: len(x)]) <= TOL
+
+
+def test_file_impulse_and_ragged_lengths():
+    fs = 8000
+    r = renderer(fs, 1)
+    rng = np.random.default_rng(3)
+    for n in (1, 511, 512, 513, 5000, 8000 + 77):
+        x = rng.standard_normal(n).astype(np.float32)
+        d = np.zeros(fs, np.float32); d[0] = 1.0
+        s = np.zeros(fs, np.float32); s[700] = 0.5
+        r.set_ir(d, s)
+        yl, yr, _, _ = r.convoluteAudioFile(x)
+        assert np.allclose(yl, x, rtol=0, atol=2e-6 * max(1.0, np.abs(x).max()))
+        exp = np.zeros(n, np.float32); exp[700:] = 0.5 * x[: max(0, n - 700)]
+        assert np.allclose(yr, exp, rtol=0, atol=2e-6 * max(1.0, np.abs(x).max()))
+    # linearity
+    a, b = rng.standard_normal(4000).astype(np.float32), rng.standard_normal(4000).astype(np.float32)
+    r.set_ir(decaying_ir(fs, 4, 0.2, fs), decaying_ir(fs, 5, 0.2, fs))
+    ya = r.convoluteAudioFile(a)[0]; yb = r.convoluteAudioFile(b)[0]; yab = r.convoluteAudioFile(a + b)[0]
+    assert rel_l2(yab, (ya.astype(np.float64) + yb)) <= 5e-6
+
+
+def test_file_reference_mode_c1():
+    """BASELINE config 1 convolution semantics: ir_len == fs == 16000 => the reference's
+    FFT of size ir_len is a pure circular convolution per second, gain 2, whole seconds
+    only, output truncated to the input length."""
+    fs = 16000
+    r = renderer(fs, 1)
+    hl, hr = decaying_ir(fs, 11, 0.5, fs), decaying_ir(fs, 12, 0.25, fs)
+    r.set_ir(hl, hr)
+    x = np.load(os.path.join(GOLDEN, "guitar_2s.npy"))
+    x = np.concatenate([x, x[:5000]])          # 2.3125 s: last partial second is dropped
+    yl, yr, _, _ = r.convoluteAudioFile(x, arv.CONV_REFERENCE)
+    assert rel_l2(yl, oracle.reference_file_conv(x, hl, fs)) <= TOL
+    assert rel_l2(yr, oracle.reference_file_conv(x, hr, fs)) <= TOL
+
+
+def test_file_reference_mode_two_second_ir():
+    fs = 8000
+    r = renderer(fs, 2)                        # ir_len = 2 fs: linear when support + fs <= ir_len
+    hl = np.zeros(2 * fs, np.float32); hl[: fs // 2] = decaying_ir(fs // 2, 21, 0.1, fs)
+    hr = decaying_ir(2 * fs, 22, 0.6, fs)      # wraps
+    r.set_ir(hl, hr)
+    x = np.random.default_rng(23).standard_normal(3 * fs + 100).astype(np.float32)
+    yl, yr, _, _ = r.convoluteAudioFile(x, arv.CONV_REFERENCE)
+    assert rel_l2(yl, oracle.reference_file_conv(x, hl, fs)) <= TOL
+    assert rel_l2(yr, oracle.reference_file_conv(x, hr, fs)) <= TOL
+    # left ear never wraps: equals 2 x the true linear convolution of the whole seconds
+    lin = 2.0 * oracle.direct_conv(x[: 3 * fs], hl)[: len(x)]
+    assert rel_l2(yl, lin) <= TOL
+
+
+@pytest.mark.parametrize("block,n_src,ir_len", [(512, 3, 4800), (128, 2, 1000), (256, 1, 256), (1024, 2, 5000), (64, 1, 130)])
+def test_stream_matches_direct(block, n_src, ir_len):
+    rng = np.random.default_rng(block + n_src)
+    st = arv.ConvStream(n_src, block, ir_len)
+    irs = [(decaying_ir(ir_len, 30 + i, 0.05, 48000), decaying_ir(ir_len, 60 + i, 0.03, 48000)) for i in range(n_src)]
+    for i, (a, b) in enumerate(irs):
+        st.set_ir(i, a, b)
+    nb = 3 * ((ir_len + block - 1) // block) + 5       # several trips around the delay line
+    x = (0.1 * rng.standard_normal((n_src, nb * block))).astype(np.float32)
+    out = np.concatenate([st.process(x[:, k * block:(k + 1) * block]) for k in range(nb)], axis=2)
+    for i, (a, b) in enumerate(irs):
+        assert rel_l2(out[i, 0], oracle.direct_conv(x[i], a)[: nb * block]) <= TOL
+        assert rel_l2(out[i, 1], oracle.direct_conv(x[i], b)[: nb * block]) <= TOL
+    # the oracle's own scalar UPOLA port agrees too (it is the CPU baseline of the bench)
+    ol, orr, _ = oracle.upola(x[0], irs[0][0], irs[0][1], block)
+    assert rel_l2(ol, oracle.direct_conv(x[0], irs[0][0])[: nb * block]) <= 1e-4
+
+
+def test_stream_ir_swap_and_reset():
+    block, ir_len = 256, 2000
+    st = arv.ConvStream(1, block, ir_len)
+    a = decaying_ir(ir_len, 1, 0.02, 48000); b = decaying_ir(ir_len, 2, 0.02, 48000)
+    x = (0.1 * np.random.default_rng(9).standard_normal(40 * block)).astype(np.float32)
+    st.set_ir(0, a, a)
+    y1 = np.concatenate([st.process(x[k * block:(k + 1) * block])[0, 0] for k in range(20)])
+    st.set_ir(0, b, b)                                   # takes effect at the block boundary
+    y2 = np.concatenate([st.process(x[k * block:(k + 1) * block])[0, 0] for k in range(20, 40)])
+    assert rel_l2(y1, oracle.direct_conv(x[: 20 * block], a)[: 20 * block]) <= TOL
+    # after the swap every partition uses the new IR on the full input history
+    assert rel_l2(y2[-8 * block:], oracle.direct_conv(x, b)[32 * block: 40 * block]) <= TOL
+    st.reset()
+    y3 = np.concatenate([st.process(x[k * block:(k + 1) * block])[0, 0] for k in range(5)])
+    assert rel_l2(y3, oracle.direct_conv(x[: 5 * block], b)[: 5 * block]) <= TOL
+
+
+def test_live_reference_semantics():
+    """convoluteLiveInput (one 4096-sample callback, OR/AudioRenderer.cpp:593-661): the
+    first ir_len output samples of the stream convolver x2 equal the reference's circular
+    result whenever it does not wrap (4096 + support <= ir_len)."""
+    fs, ir_len = 44100, 44100
+    hl = np.zeros(ir_len, np.float32); hl[:20000] = decaying_ir(20000, 5, 0.1, fs)
+    hr = np.zeros(ir_len, np.float32); hr[:30000] = decaying_ir(30000, 6, 0.2, fs)
+    x = np.random.default_rng(7).standard_normal(4096)
+    ref = oracle.reference_live_conv(x, hl, hr)         # interleaved LRLR, 2*ir_len doubles
+    st = arv.ConvStream(1, 512, ir_len)
+    st.set_ir(0, hl, hr)
+    xin = np.zeros(ir_len + 512, np.float32); xin[:4096] = x
+    nb = ir_len // 512
+    out = np.concatenate([st.process(xin[k * 512:(k + 1) * 512]) for k in range(nb)], axis=2)
+    assert rel_l2(2.0 * out[0, 0], ref[0:2 * nb * 512:2]) <= TOL
+    assert rel_l2(2.0 * out[0, 1], ref[1:2 * nb * 512:2]) <= TOL
