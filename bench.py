@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of AudioRenderingV2 on B200: IR trace, IR re-render, streaming
+convolution (BASELINE.json metric: "Grays/s IR trace at 1/2/4/8 B200; IR re-render ms;
+conv us per 512-sample block").
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # CPU port of the same tracer on host cores
+
+A step = one IR render of this rank's slice of the seeded ray set (arv2_render_range:
+zero the fp64 histogram, trace, then all-reduce the histogram over NCCL and finalise).
+Workload (BASELINE.json configs[1]): procedural conference-scale room (331k triangles --
+conference.obj is a missing blob in the reference checkout), 1M rays per GPU, 50 bounces,
+2 s IR @48 kHz, 1 source / 1 receiver.  1 ray = 1 traced segment = 1 closest-hit query.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS = (100, 100, 100)          # per GPU
+MAX_BOUNCES = 50
+FS = 48000
+IR_SECONDS = 2
+EMITTER = (2.0, 1.5, 2.0)
+RECEIVER = (9.0, 1.4, 5.5)
+YAW = 30.0
+SEED = 7
+BYTES_PER_SEGMENT = 17 * 64 + 4 * 36 + 64      # 1296 B for T ~ 332k
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_receiver():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "receiver.npz"))
+    return d["left"], d["right"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def scene_case():
+    from audiorenderingv2_b200 import scenes
+    tv, tm, names = scenes.conference_room()
+    return tv, tm, names, scenes.materials()
+
+
+def oracle_flat(tv, tm, names, mats, recv):
+    import oracle  # noqa: F401  (cpu_baseline / --impl reference only)
+    from oracle import scene as osc
+    model = osc.Model(meshes=[osc.Mesh(names[i], np.ascontiguousarray(tv[tm == i])) for i in range(len(names))])
+    flat = osc.flatten(model, osc.ReceiverTemplate(*recv), RECEIVER, YAW, [(m[0], m[1]) for m in mats])
+    return flat
+
+
+def cpu_port_rate(n_total_rays, budget_s, chunk):
+    """Times the oracle (CPU port of the identical tracer) on all host cores on a bounded
+    sample of the same workload.  Returns (Grays/s, cores, sample description, segments/ray)."""
+    import oracle
+    tv, tm, names, mats = scene_case()
+    flat = oracle_flat(tv, tm, names, mats, load_receiver())
+    prep = oracle.PreparedScene(flat)            # BVH build untimed (as on the GPU side)
+    p = oracle.make_params(rays=(n_total_rays, 1, 1), emitter=EMITTER, sphere_center=RECEIVER, base_power=100.0,
+                           max_bounces=MAX_BOUNCES, hrtf=0.9, sample_rate=FS, ir_length=IR_SECONDS * FS, seed=SEED)
+    cores = os.cpu_count() or 1
+    segs, rays, t = 0, 0, 0.0
+    while t < budget_s and rays + chunk <= n_total_rays:
+        t0 = time.perf_counter()
+        s, _ = prep.trace(p, rays, chunk, n_threads=cores)
+        t += time.perf_counter() - t0
+        segs += s; rays += chunk
+    return segs / t / 1e9, cores, f"first {rays} rays of the same seeded set ({segs} segments, {t:.1f} s)", segs / max(rays, 1)
+
+
+def run_reference(args):
+    """--impl reference: the reference is CUDA/OptiX on Windows and has no CPU path; its
+    arm is the CPU port of the identical tracer (oracle/) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_total = RAYS[0] * RAYS[1] * RAYS[2] * args.gpus
+    chunk = 100_000
+    import oracle
+    tv, tm, names, mats = scene_case()
+    flat = oracle_flat(tv, tm, names, mats, load_receiver())
+    prep = oracle.PreparedScene(flat)
+    p = oracle.make_params(rays=(n_total, 1, 1), emitter=EMITTER, sphere_center=RECEIVER, base_power=100.0,
+                           max_bounces=MAX_BOUNCES, hrtf=0.9, sample_rate=FS, ir_length=IR_SECONDS * FS, seed=SEED)
+    cores = os.cpu_count() or 1
+    for i in range(args.warmup):
+        prep.trace(p, 0, 20_000, n_threads=cores)
+    t, segs = 0.0, 0
+    for i in range(args.steps):
+        t0 = time.perf_counter()
+        s, _ = prep.trace(p, (i * chunk) % max(1, n_total - chunk), chunk, n_threads=cores)
+        t += time.perf_counter() - t0
+        segs += s
+    val = segs / t / 1e9
+    line = {
+        "impl": "reference", "metric": "Grays/s IR trace", "value": val, "unit": "Grays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "Grays/s", "cores": cores, "kind": "port",
+                         "sample": f"{chunk} rays per step of the same seeded set (OptiX reference not buildable offline)"},
+        "e2e": {"value": val, "unit": "Grays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: conference-scale room (procedural stand-in, 331004 triangles + 1020 receiver), "
+                        "1M rays per GPU, 50 bounces, 2 s IR @48 kHz",
+            "rays_per_gpu": RAYS[0] * RAYS[1] * RAYS[2], "total_rays": RAYS[0] * RAYS[1] * RAYS[2] * n_gpus,
+            "max_bounces": MAX_BOUNCES, "sample_rate": FS, "ir_seconds": IR_SECONDS, "bands": 1,
+            "parallelism": f"ray-range sharding x{n_gpus}, NCCL all-reduce of the fp64 IR histogram",
+            "l2": "flushed between timed steps (512 MiB write)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="arv2", choices=["arv2", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the re-render and convolution sub-metrics")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "arv2" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import audiorenderingv2_b200 as arv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs {args.gpus} ranks (launch with torch.distributed.run); WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    tv, tm, names, mats = scene_case()
+    recv = load_receiver()
+    per_gpu = RAYS[0] * RAYS[1] * RAYS[2]
+    total_rays = per_gpu * world
+    scene = arv.Scene.from_triangles(tv, tm, names)
+    receiver = arv.Receiver.from_triangles(*recv)
+    t_build = time.perf_counter()
+    # the seeded ray set has total_rays rays; this rank traces [rank*per_gpu, (rank+1)*per_gpu)
+    r = arv.AudioRenderer(scene, IR_SECONDS, FS, mats, (total_rays, 1, 1), receiver=receiver, device=local)
+    t_build = time.perf_counter() - t_build
+    r.setBasePower(100.0); r.setThresholds(0.0, MAX_BOUNCES); r.set_hrtf_absorption_rate(0.9)
+    r.setEmitterPosInOptix(EMITTER); r.setSphereCenterInOptix(RECEIVER, YAW); r.set_seed(SEED)
+    stream = torch.cuda.Stream(device=dev)
+    r.set_stream(stream.cuda_stream)
+
+    hist_ptr, hist_n = r.hist_device()
+
+    class _Ext:
+        __cuda_array_interface__ = {"shape": (hist_n,), "typestr": "<f8", "data": (hist_ptr, False), "version": 3}
+    hist = torch.as_tensor(_Ext(), device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        """one IR render of this rank's shard; returns kernel ms (device events inside the library)"""
+        ms = r.render_range(rank * per_gpu, per_gpu, zero_first=True)
+        if world > 1:
+            dist.all_reduce(hist)
+        r.finalize()
+        return ms
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        clocks = ClockSampler(local)
+        step_ms, kern_ms, segs = [], [], 0
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        for _ in range(args.steps):
+            flush.fill_(1)                     # evict the BVH from L2 between timed steps
+            barrier()
+            ev0.record(stream)
+            kern_ms.append(step())
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            step_ms.append(ev0.elapsed_time(ev1))
+            segs += r.last_segments()
+        barrier()
+        clk = clocks.stop()
+
+        # max over ranks per step, summed: the whole job advances at the slowest rank
+        t_steps = torch.tensor(step_ms, dtype=torch.float64, device=dev)
+        seg_t = torch.tensor([float(segs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_steps, op=dist.ReduceOp.MAX)
+            dist.all_reduce(seg_t)
+        total_ms = float(t_steps.sum().item())
+        total_segs = float(seg_t.item())
+        value = total_segs / (total_ms * 1e-3) / 1e9
+
+        # ---- e2e: the call a user of the reference makes (full_render_cycle minus the
+        # convolution): move the receiver (host -> device upload of its sub-tree), render,
+        # read both IRs back to host memory.
+        ir_bytes = 2 * r.ir_length * 4
+        e2e_ms, e2e_segs = [], 0
+        for k in range(args.steps):
+            flush.fill_(1)
+            barrier()
+            t0 = time.perf_counter()
+            r.setSphereCenterInOptix((RECEIVER[0] + 0.01 * (k + 1), RECEIVER[1], RECEIVER[2]), YAW)
+            step()
+            r.get_ir()
+            e2e_ms.append(1e3 * (time.perf_counter() - t0))
+            e2e_segs += r.last_segments()
+        t_e2e = torch.tensor(e2e_ms, dtype=torch.float64, device=dev)
+        seg_e = torch.tensor([float(e2e_segs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+            dist.all_reduce(seg_e)
+        e2e_value = float(seg_e.item()) / (float(t_e2e.sum().item()) * 1e-3) / 1e9
+        r.setSphereCenterInOptix(RECEIVER, YAW)
+
+    kernel_ms = float(np.mean(kern_ms))
+    segs_per_launch = segs / args.steps
+    achieved = segs_per_launch * BYTES_PER_SEGMENT / (kernel_ms * 1e-3) / 1e9
+    peak = 6650.0; peak_src = "fallback"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); peak_src = "measured"
+    except (OSError, KeyError, ValueError):
+        pass
+
+    extras = {}
+    if not args.skip_extras:
+        extras.update(bench_rerender(arv, torch, dev, local, scene, receiver, mats, args))
+        extras.update(bench_conv(arv, torch, dist, dev, local, rank, world, args))
+
+    line = {
+        "metric": "Grays/s IR trace", "value": value, "unit": "Grays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "segments_per_step": total_segs / args.steps, "paths_per_s": total_rays * args.steps / (total_ms * 1e-3),
+        "bvh_build_s": t_build,
+        "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": 16 * (4 + 4 * 1020 + 3 * 1020),
+                "d2h_bytes_per_step": ir_bytes + 16, "ms_per_step": float(t_e2e.sum().item()) / args.steps},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "trace_kernel<1,0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_segment": BYTES_PER_SEGMENT, "kernel_ms": kernel_ms},
+    }
+    line.update(extras)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, _ = cpu_port_rate(per_gpu, 12.0, 50_000)
+        line["cpu_baseline"] = {"value": v, "unit": "Grays/s", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_rerender(arv, torch, dev, local, scene, receiver, mats, args):
+    """IR re-render ms: receiver moves re-deposit from the cached receiver-independent
+    paths (BASELINE target: < 1 ms for the conference scene at 1M rays)."""
+    per_gpu = RAYS[0] * RAYS[1] * RAYS[2]
+    r = arv.AudioRenderer(scene, IR_SECONDS, FS, mats, (per_gpu, 1, 1), receiver=receiver, device=local, path_cache=True)
+    r.setBasePower(100.0); r.setThresholds(0.0, MAX_BOUNCES); r.set_hrtf_absorption_rate(0.9)
+    r.setEmitterPosInOptix(EMITTER); r.setSphereCenterInOptix(RECEIVER, YAW); r.set_seed(SEED)
+    build_ms = r.render()
+    ms, wall = [], []
+    for k in range(max(args.steps, 10) + 3):
+        r.setSphereCenterInOptix((RECEIVER[0] - 0.1 * k, RECEIVER[1], RECEIVER[2] - 0.05 * k), YAW + 3.0 * k)
+        t0 = time.perf_counter()
+        m = r.rerender()
+        wall.append(1e3 * (time.perf_counter() - t0))
+        ms.append(m)
+    segs = r.last_segments()
+    r.close()
+    return {"rerender_ms": float(np.median(ms[3:])), "rerender_wall_ms": float(np.median(wall[3:])),
+            "rerender_cached_segments": segs, "path_cache_build_ms": build_ms}
+
+
+def bench_conv(arv, torch, dist, dev, local, rank, world, args):
+    """conv us per 512-sample block: 16 sources x 2 s IR @48 kHz (96000 taps -> 188
+    partitions), sources sharded over the GPUs (BASELINE config 5)."""
+    n_src_total, block, ir_len = 16, 512, IR_SECONDS * FS
+    n_src = max(1, n_src_total // world)
+    st = arv.ConvStream(n_src, block, ir_len, device=local)
+    rng = np.random.default_rng(200 + rank)
+    t = np.arange(ir_len) / FS
+    for s in range(n_src):
+        env = np.exp(-6.9 * t / 1.2)
+        st.set_ir(s, (rng.standard_normal(ir_len) * env).astype(np.float32), (rng.standard_normal(ir_len) * env).astype(np.float32))
+    n_blocks = 256
+    x = (0.1 * torch.randn(n_blocks, n_src, block, device=dev)).contiguous()
+    y = torch.empty(n_src, 2, block, device=dev)
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        for k in range(32):
+            st.process_device(x[k].data_ptr(), y.data_ptr(), s.cuda_stream)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for k in range(n_blocks):
+            st.process_device(x[k].data_ptr(), y.data_ptr(), s.cuda_stream)
+        e1.record(s)
+        torch.cuda.synchronize()
+        dev_us = 1e3 * e0.elapsed_time(e1) / n_blocks
+    # host-buffer path (H2D + step + D2H + sync per block): the live-callback call
+    xin = (0.1 * rng.standard_normal((n_src, block))).astype(np.float32)
+    for _ in range(8):
+        st.process(xin)
+    t0 = time.perf_counter()
+    for _ in range(64):
+        st.process(xin)
+    host_us = 1e6 * (time.perf_counter() - t0) / 64
+    tt = torch.tensor([dev_us, host_us], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    st.close()
+    bytes_per_block_src = 3 * 188 * 512 * 8 + 4096 + 6144
+    return {"conv_us_per_block": float(tt[0].item()), "conv_us_per_block_host_buffers": float(tt[1].item()),
+            "conv_sources_per_gpu": n_src, "conv_deadline_us": 1e6 * block / FS,
+            "conv_achieved_gbs": n_src * bytes_per_block_src / (float(tt[0].item()) * 1e-6) / 1e9}
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,11 @@ def lib():
         L.oracle_trace.restype = C.c_int64
         L.oracle_trace.argtypes = [C.POINTER(Params), fp, ip, C.c_int64, fp, fp, C.c_int32, C.c_int64,
                                    C.c_int64, C.c_int32, C.c_int32, dp, ip, ip, fp, ip]
+        L.oracle_scene_create.restype = C.c_void_p
+        L.oracle_scene_create.argtypes = [fp, ip, C.c_int64, fp, fp, C.c_int32, C.c_int32, C.c_int32]
+        L.oracle_scene_destroy.argtypes = [C.c_void_p]
+        L.oracle_trace_scene.restype = C.c_int64
+        L.oracle_trace_scene.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_int64, C.c_int32, dp, ip, ip, fp, ip]
         L.oracle_ray_direction.argtypes = [C.c_uint64, C.c_uint64, fp]
         L.oracle_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.oracle_closest_hit.restype = C.c_int64
@@ -116,6 +121,35 @@ def trace(p: Params, scene, ray_begin=0, n_rays=None, use_bvh=None, n_threads=No
     if segs < 0:
         raise RuntimeError("oracle_trace failed")
     return dict(hist=hist, bin=rb, ear=re_, energy=en, nseg=rn, segments=int(segs))
+
+
+class PreparedScene:
+    """Scene + oracle BVH built once (bench.py's CPU baseline keeps the build untimed)."""
+
+    def __init__(self, scene, bands=1, use_bvh=True):
+        L = lib()
+        self._tv = np.ascontiguousarray(scene.tri_verts, dtype=np.float32)
+        tm = np.ascontiguousarray(scene.tri_mat, dtype=np.int32)
+        ab = np.ascontiguousarray(scene.absorption, dtype=np.float32)
+        sc = np.ascontiguousarray(scene.scattering, dtype=np.float32)
+        self.bands = bands
+        self._h = L.oracle_scene_create(_fp(self._tv), _ip(tm), self._tv.shape[0], _fp(ab), _fp(sc), ab.shape[0], bands,
+                                        1 if use_bvh else 0)
+        if not self._h:
+            raise RuntimeError("oracle_scene_create failed")
+
+    def trace(self, p: Params, ray_begin, n_rays, n_threads=None, want_hist=True):
+        hist = np.zeros((2, p.bands, p.ir_length), np.float64) if want_hist else None
+        segs = lib().oracle_trace_scene(self._h, C.byref(p), int(ray_begin), int(n_rays), n_threads or (os.cpu_count() or 1),
+                                        _dp(hist), None, None, None, None)
+        if segs < 0:
+            raise RuntimeError("oracle_trace_scene failed")
+        return int(segs), hist
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.oracle_scene_destroy(self._h)
+            self._h = None
 
 
 def finalize_ir(hist, mono=False):

@@ -70,6 +70,15 @@ int64_t oracle_trace(const oracle_params* p,
                      double* hist, int32_t* rec_bin, int32_t* rec_ear,
                      float* rec_energy, int32_t* rec_nseg);
 
+/* Same, with the scene (and the oracle's BVH) prepared once: create / trace / destroy. */
+void* oracle_scene_create(const float* tri_verts, const int32_t* tri_mat, int64_t n_tris,
+                          const float* absorption, const float* scattering, int32_t n_mats,
+                          int32_t bands, int32_t use_bvh);
+int64_t oracle_trace_scene(void* scene, const oracle_params* p, int64_t ray_begin, int64_t n_rays,
+                           int32_t n_threads, double* hist, int32_t* rec_bin, int32_t* rec_ear,
+                           float* rec_energy, int32_t* rec_nseg);
+void oracle_scene_destroy(void* scene);
+
 /* Direction of ray `ray_id` of the seeded set (unit vector, float[3]). */
 void oracle_ray_direction(uint64_t seed, uint64_t ray_id, float* dir3);
 

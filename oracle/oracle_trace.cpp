@@ -406,24 +406,48 @@ void trace_ray(const oracle_params& P, const Scene& S, uint64_t ray, float energ
 
 extern "C" {
 
-int64_t oracle_trace(const oracle_params* p, const float* tri_verts, const int32_t* tri_mat, int64_t n_tris,
-                     const float* absorption, const float* scattering, int32_t n_mats, int64_t ray_begin,
-                     int64_t n_rays, int32_t use_bvh, int32_t n_threads, double* hist, int32_t* rec_bin,
-                     int32_t* rec_ear, float* rec_energy, int32_t* rec_nseg)
-{
-    (void)n_mats;
-    if (!p || p->bands < 1 || p->bands > MAX_BANDS || n_tris < 0 || n_rays < 0) return -1;
-    const oracle_params P = *p;
+/* Scene handle: triangles + the oracle's BVH, built once and traced many times (used
+ * by bench.py's CPU baseline so that the BVH build stays outside the timed region). */
+struct oracle_scene_t {
     Scene S;
+    std::vector<int32_t> mat;
+    std::vector<float> absorption, scattering;
+    int bands;
+};
+
+void* oracle_scene_create(const float* tri_verts, const int32_t* tri_mat, int64_t n_tris, const float* absorption,
+                          const float* scattering, int32_t n_mats, int32_t bands, int32_t use_bvh)
+{
+    if (n_tris < 0 || bands < 1 || bands > MAX_BANDS) return nullptr;
+    auto* h = new oracle_scene_t;
+    h->bands = bands;
+    h->mat.assign(tri_mat, tri_mat + n_tris);
+    h->absorption.assign(absorption, absorption + (size_t)n_mats * bands);
+    if (scattering) h->scattering.assign(scattering, scattering + n_mats);
+    Scene& S = h->S;
     S.tris = make_tris(tri_verts, n_tris);
     S.p2.resize(n_tris); S.p3.resize(n_tris);
     for (int64_t i = 0; i < n_tris; ++i) {
         const float* q = tri_verts + 9 * i;
         S.p2[i] = {q[3], q[4], q[5]}; S.p3[i] = {q[6], q[7], q[8]};
     }
-    S.mat = tri_mat; S.absorption = absorption; S.scattering = scattering;
+    S.mat = h->mat.data(); S.absorption = h->absorption.data();
+    S.scattering = h->scattering.empty() ? nullptr : h->scattering.data();
     S.use_bvh = use_bvh != 0;
     if (S.use_bvh) S.bvh = build_bvh(S.tris);
+    return h;
+}
+
+void oracle_scene_destroy(void* h) { delete (oracle_scene_t*)h; }
+
+int64_t oracle_trace_scene(void* handle, const oracle_params* p, int64_t ray_begin, int64_t n_rays, int32_t n_threads,
+                           double* hist, int32_t* rec_bin, int32_t* rec_ear, float* rec_energy, int32_t* rec_nseg)
+{
+    if (!handle || !p || n_rays < 0) return -1;
+    const oracle_scene_t* h = (const oracle_scene_t*)handle;
+    if (p->bands != h->bands) return -1;
+    const oracle_params P = *p;
+    const Scene& S = h->S;
 
     /* devicePrograms.cu:208  base_power / ((x*y*z) * 4.18879020478) in double, narrowed */
     const int n_total = P.size_x * P.size_y * P.size_z;
@@ -442,15 +466,15 @@ int64_t oracle_trace(const oracle_params* p, const float* tri_verts, const int32
     std::atomic<int64_t> next{0};
     const int64_t chunk = 4096;
     auto work = [&](int tid) {
-        double* h = hist;
-        if (nt > 1 && hist) { priv[tid].assign(hsz, 0.0); h = priv[tid].data(); }
+        double* hh = hist;
+        if (nt > 1 && hist) { priv[tid].assign(hsz, 0.0); hh = priv[tid].data(); }
         for (;;) {
             const int64_t b = next.fetch_add(chunk);
             if (b >= n_rays) break;
             const int64_t e = std::min(n_rays, b + chunk);
             for (int64_t i = b; i < e; ++i) {
                 RayOut o;
-                trace_ray(P, S, (uint64_t)(ray_begin + i), energy0, dist_thr, delay, h, o);
+                trace_ray(P, S, (uint64_t)(ray_begin + i), energy0, dist_thr, delay, hh, o);
                 segs[tid] += o.nseg;
                 if (rec_bin) rec_bin[i] = o.bin;
                 if (rec_ear) rec_ear[i] = o.ear;
@@ -469,6 +493,19 @@ int64_t oracle_trace(const oracle_params* p, const float* tri_verts, const int32
     int64_t total = 0;
     for (auto s : segs) total += s;
     return total;
+}
+
+int64_t oracle_trace(const oracle_params* p, const float* tri_verts, const int32_t* tri_mat, int64_t n_tris,
+                     const float* absorption, const float* scattering, int32_t n_mats, int64_t ray_begin,
+                     int64_t n_rays, int32_t use_bvh, int32_t n_threads, double* hist, int32_t* rec_bin,
+                     int32_t* rec_ear, float* rec_energy, int32_t* rec_nseg)
+{
+    if (!p) return -1;
+    void* h = oracle_scene_create(tri_verts, tri_mat, n_tris, absorption, scattering, n_mats, p->bands, use_bvh);
+    if (!h) return -1;
+    const int64_t r = oracle_trace_scene(h, p, ray_begin, n_rays, n_threads, hist, rec_bin, rec_ear, rec_energy, rec_nseg);
+    oracle_scene_destroy(h);
+    return r;
 }
 
 void oracle_ray_direction(uint64_t seed, uint64_t ray_id, float* dir3)
