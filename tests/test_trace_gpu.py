@@ -69,13 +69,13 @@ def test_torus_box(golden_scenes, golden_receiver):
 def test_free_field_energy(golden_receiver):
     """No walls: sum(L+R) -> P/(4 pi D^2), and empty-scene handling."""
     D = 6.0
-    case = Case(np.zeros((0, 3, 3), np.float32), np.zeros(0, np.int32), [], golden_receiver, rays=(200, 100, 10),
+    case = Case(np.zeros((0, 3, 3), np.float32), np.zeros(0, np.int32), [], golden_receiver, rays=(500, 400, 5),
                 emitter=(0, 0, 0), center=(D, 0, 0), base_power=100.0, hrtf=1.0)
     r, rec, l, rr, segs, _ = run(case)
     o = case.oracle_run()
     assert check_parity(rec, l, rr, segs, o) == 1.0
     total = float(l.sum() + rr.sum())
-    assert abs(total - 100.0 / (4 * np.pi * D * D)) < 0.05 * 100.0 / (4 * np.pi * D * D)
+    assert abs(total - 100.0 / (4 * np.pi * D * D)) < 0.08 * 100.0 / (4 * np.pi * D * D)
 
 
 def test_no_receiver_no_deposit(golden_scenes):
