@@ -29,6 +29,19 @@ constexpr int kSentinel = INT_MIN;
 
 struct Hit { float t, u, v; int slot, id; };
 
+// 256-bit read-only global load (sm_100+: LDG.E.ENL2.256.CONSTANT).  A divergent gather
+// costs the L1 data pipe one wavefront per load instruction and lane, so a 64 B node is
+// fetched with 2 of these instead of 4 x LDG.128 (profiles/micro/gather.cu: 1.34x).
+struct __align__(32) F8 { float4 lo, hi; };
+__device__ __forceinline__ F8 ldg256(const float4* p)
+{
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+        : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ float safe_rcp(float d)
 {
     const float eps = 1e-20f;
@@ -50,10 +63,8 @@ __device__ __forceinline__ void closest_hit(const float4* __restrict__ nodes, co
 
     while (cur != kSentinel) {
         while (cur >= 0) {
-            const float4 n0 = __ldg(nodes + cur * 4 + 0);
-            const float4 n1 = __ldg(nodes + cur * 4 + 1);
-            const float4 n2 = __ldg(nodes + cur * 4 + 2);
-            const float4 n3 = __ldg(nodes + cur * 4 + 3);
+            const F8 na = ldg256(nodes + cur * 4), nb = ldg256(nodes + cur * 4 + 2);
+            const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
             const float c0lox = fmaf(n0.x, ix, -ox), c0hix = fmaf(n0.y, ix, -ox);
             const float c0loy = fmaf(n0.z, iy, -oy), c0hiy = fmaf(n0.w, iy, -oy);
             const float c0loz = fmaf(n2.x, iz, -oz), c0hiz = fmaf(n2.y, iz, -oz);
