@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libarv2.so")
+LIB_PATH = os.environ.get("ARV2_LIB") or os.path.join(_HERE, "lib", "libarv2.so")   # ARV2_LIB: A/B builds while tuning
 MAX_BANDS = 8
 CONV_LINEAR, CONV_REFERENCE = 0, 1
 

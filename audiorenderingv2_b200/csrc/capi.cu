@@ -65,6 +65,7 @@ struct arv2_ctx {
     int mono = 0;
     unsigned long long seed = 1;
     bool recv_dirty = true, cache_valid = false;
+    float recv_radius = 0.f;
     int any_scatter = 0;
 
     // device
@@ -106,6 +107,15 @@ int upload_receiver(arv2_ctx* c)
     c->recv_world.resize((size_t)n * 9);
     place_receiver_half(c->receiver.left, c->center, c->yaw, c->recv_world.data());
     place_receiver_half(c->receiver.right, c->center, c->yaw, c->recv_world.data() + nl * 9);
+    {
+        double r2 = 0.0;
+        for (int64_t i = 0; i < n * 3; ++i) {
+            const float* v = c->recv_world.data() + 3 * i;
+            const double dx = (double)v[0] - c->center[0], dy = (double)v[1] - c->center[1], dz = (double)v[2] - c->center[2];
+            r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+        }
+        c->recv_radius = (float)(std::sqrt(r2) * 1.001 + 1e-3);
+    }
     if (!c->recv_bvh_built) {
         build_bvh_sah(c->recv_world.data(), n, &c->recv_bvh, 1);
         c->recv_bvh_built = true;
@@ -173,6 +183,7 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     p->pc_stride = c->pc_rays;
     p->seed = c->seed; p->ray_begin = ray_begin; p->n_rays = n_rays;
     for (int a = 0; a < 3; ++a) { p->emitter[a] = c->emitter[a]; p->center[a] = c->center[a]; }
+    p->recv_radius = c->recv_radius;
     // OR/devicePrograms.cu:208  base_power / ((x*y*z) * 4.18879020478), double then narrowed
     p->energy0 = (float)((double)c->base_power / ((double)(int)c->n_rays_total * 4.18879020478));
     p->energy_thres = c->energy_thres;
@@ -206,9 +217,10 @@ int ensure_cache(arv2_ctx* c)
 
 int finish_timed(arv2_ctx* c, double* ms)
 {
-    CK(cudaMemcpyAsync(c->h_counters, c->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_counters, c->d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));                    // CUDA_SYNC_CHECK, OR/AudioRenderer.cpp:511
     c->last_segments = (long long)c->h_counters[1];
+    if (getenv("ARV2_PRINT_STATS")) { for (int i = 0; i < 12; ++i) fprintf(stderr, "%llu ", c->h_counters[i]); fprintf(stderr, "\n"); }
     if (ms) { float t = 0.f; CK(cudaEventElapsedTime(&t, c->ev0, c->ev1)); *ms = t; }
     return ARV2_OK;
 }
@@ -455,7 +467,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     }
     c->stage_f4 = 4 + 4 * (size_t)c->n_recv_nodes + 3 * (size_t)std::max<int64_t>(1, n_recv);
     CKC(cudaMallocHost(&c->h_stage, c->stage_f4 * sizeof(float4)));
-    CKC(cudaMallocHost(&c->h_counters, 2 * sizeof(unsigned long long)));
+    CKC(cudaMallocHost(&c->h_counters, 16 * sizeof(unsigned long long)));
 
     // IR buffers (OR/AudioRenderer.cpp:81-85) and the fp64 accumulation histogram
     const size_t irn = (size_t)c->bands * c->ir_len;
@@ -465,7 +477,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     CKC(cudaMemset(c->d_hist, 0, 2 * irn * sizeof(double)));
     CKC(cudaMemset(c->d_ir_l, 0, irn * sizeof(float)));
     CKC(cudaMemset(c->d_ir_r, 0, irn * sizeof(float)));
-    CKC(cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
+    CKC(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
     if (desc->record_rays) {
         c->rec_capacity = n_total;
         CKC(cudaMalloc(&c->d_rec_bin, (size_t)n_total * sizeof(int)));
@@ -534,7 +546,7 @@ int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t ze
     if (rc != ARV2_OK) return rc;
     const size_t irn = (size_t)c->bands * c->ir_len;
     if (zero_first) CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));   // fillZeros, OR/AudioRenderer.cpp:491-492
-    CK(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
     TraceParams p;
     fill_params(c, &p, ray_begin, n_rays);
     CK(cudaEventRecord(c->ev0, c->stream));
@@ -565,7 +577,7 @@ int arv2_rerender(arv2_ctx* c, double* ms)
     fill_params(c, &p, 0, c->n_rays_total);
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));
-    CK(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
     CK(launch_rerender(p, c->bands, c->sm_count, c->stream));
     CK(launch_finalize(c->d_hist, c->bands, c->ir_len, c->mono, c->d_ir_l, c->d_ir_r, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -589,7 +601,7 @@ int arv2_render(arv2_ctx* c, double* ms)
     if (!c->cache_valid) {
         rc = upload_receiver(c);
         if (rc != ARV2_OK) return rc;
-        CK(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+        CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
         TraceParams p;
         fill_params(c, &p, 0, c->n_rays_total);
         p.root = 1;                                       // scene sub-tree only

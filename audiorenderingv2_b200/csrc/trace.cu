@@ -24,8 +24,16 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kChunk = 128;          // rays a warp claims per global atomic
 constexpr int kStack = 64;
-constexpr int kThreads = 256;
+#ifndef ARV2_THREADS
+#define ARV2_THREADS 128
+#endif
+#ifndef ARV2_MINB
+#define ARV2_MINB 8
+#endif
+constexpr int kThreads = ARV2_THREADS;
 constexpr int kSentinel = INT_MIN;
+constexpr int kRerenderThreads = 256;
+constexpr int kRerenderBatch = 12;   // lanes that must hold a candidate before the receiver walk
 
 struct Hit { float t, u, v; int slot, id; };
 
@@ -60,9 +68,15 @@ __device__ __forceinline__ void closest_hit(const float4* __restrict__ nodes, co
     stack[sp++] = kSentinel;
     int cur = root;
     h.t = tmax; h.u = 0.f; h.v = 0.f; h.slot = -1; h.id = INT_MAX;
+#ifdef ARV2_STATS
+    int n_inner = 0, n_tri = 0, n_leaf = 0;
+#endif
 
     while (cur != kSentinel) {
         while (cur >= 0) {
+#ifdef ARV2_STATS
+            n_inner++;
+#endif
             const F8 na = ldg256(nodes + cur * 4), nb = ldg256(nodes + cur * 4 + 2);
             const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
             const float c0lox = fmaf(n0.x, ix, -ox), c0hix = fmaf(n0.y, ix, -ox);
@@ -93,6 +107,9 @@ __device__ __forceinline__ void closest_hit(const float4* __restrict__ nodes, co
         const int code = ~cur;
         const int first = code >> 3;
         const int cnt = (code & 7) + 1;
+#ifdef ARV2_STATS
+        n_leaf++; n_tri += cnt;
+#endif
         for (int i = 0; i < cnt; ++i) {
             const int slot = first + i;
             const float4 a = __ldg(tris + slot * 3 + 0);
@@ -106,6 +123,9 @@ __device__ __forceinline__ void closest_hit(const float4* __restrict__ nodes, co
         }
         cur = stack[--sp];
     }
+#ifdef ARV2_STATS
+    h.id = n_inner | (n_leaf << 10) | (n_tri << 20);
+#endif
 }
 
 // Warp-aggregated deposit into the fp64 histogram (OR/devicePrograms.cu:128-170).
@@ -176,7 +196,7 @@ __device__ __forceinline__ F3 hit_point(F3 p1, F3 p2, F3 p3, float u, float v)
 }
 
 template <int NB, int MODE>
-__global__ void __launch_bounds__(kThreads) trace_kernel(const TraceParams p)
+__global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceParams p)
 {
     const int lane = threadIdx.x & 31;
     long long chunk_next = 0, chunk_end = 0;      // warp-uniform
@@ -239,6 +259,21 @@ __global__ void __launch_bounds__(kThreads) trace_kernel(const TraceParams p)
                 Hit h;
                 closest_hit(p.nodes, p.tris, p.root, org, dir, 1e20f, h);
                 if (MODE == 1) p.pc_org_t[ci] = make_float4(org.x, org.y, org.z, h.t);
+#ifdef ARV2_STATS
+                {
+                    // counters[2..]: sum inner, sum warp-max inner * lanes, sum leaf, sum max leaf, sum tri, sum max tri, segments, warp-rounds*32
+                    const unsigned am = __activemask();
+                    const int ni = h.id & 1023, nl = (h.id >> 10) & 1023, nt = (h.id >> 20) & 1023;
+                    const int mi = __reduce_max_sync(am, ni), ml = __reduce_max_sync(am, nl), mt = __reduce_max_sync(am, nt);
+                    const int si = __reduce_add_sync(am, ni), sl = __reduce_add_sync(am, nl), st = __reduce_add_sync(am, nt);
+                    if ((threadIdx.x & 31) == __ffs(am) - 1) {
+                        atomicAdd(p.counters + 2, (unsigned long long)si); atomicAdd(p.counters + 3, (unsigned long long)mi * 32);
+                        atomicAdd(p.counters + 4, (unsigned long long)sl); atomicAdd(p.counters + 5, (unsigned long long)ml * 32);
+                        atomicAdd(p.counters + 6, (unsigned long long)st); atomicAdd(p.counters + 7, (unsigned long long)mt * 32);
+                        atomicAdd(p.counters + 8, (unsigned long long)__popc(am)); atomicAdd(p.counters + 9, 32ull);
+                    }
+                }
+#endif
                 if (h.slot < 0) {
                     ended = true;                                                               // miss :186-190
                 } else {
@@ -308,37 +343,56 @@ __global__ void __launch_bounds__(kThreads) trace_kernel(const TraceParams p)
 // deposit at the first one the receiver intercepts before the wall (t_recv < t_wall;
 // ties go to the scene because scene triangle ids are lower).  One thread per ray,
 // lanes = consecutive rays, so every load of segment k is a coalesced 512 B row.
+// A segment is first tested against the receiver's bounding ball (a few FMAs, exact-
+// conservative); lanes whose segment passes park it and keep waiting until enough lanes of
+// the warp hold a candidate (or nobody is scanning), then those lanes walk the receiver
+// sub-tree together -- the r01 profile had this traversal running at 2.9 of 32 lanes.
 template <int NB>
-__global__ void __launch_bounds__(kThreads) rerender_kernel(const TraceParams p)
+__global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceParams p)
 {
     const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = ray < p.n_rays;
     const int n = valid ? p.pc_nseg[ray] : 0;
-    // receiver bounds = child 1 of the top node
-    const float4 t1 = __ldg(p.nodes + 1), t2 = __ldg(p.nodes + 2);
+    const F3 ctr = f3(p.center[0], p.center[1], p.center[2]);
+    const float r2 = p.recv_radius * p.recv_radius;
     int k = 0;
-    bool done = !valid;
+    bool done = n == 0, cand = false;
+    float4 ot = make_float4(0, 0, 0, 0), dd = make_float4(0, 0, 0, 0);
     int rbin = -1, rear = 0, rnseg = n;
     float energy[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) energy[b] = 0.f;
     for (;;) {
-        if (!__any_sync(FULL, !done && k < n)) break;
-        bool dep = false;
-        int bin = -1, primary = 0;
-        if (!done && k < n) {
-            const size_t ci = (size_t)k * (size_t)p.pc_stride + (size_t)ray;
-            const float4 ot = __ldcs(p.pc_org_t + ci);
-            const float4 dd = __ldcs(p.pc_dir_d + ci);
-            const F3 org = f3(ot.x, ot.y, ot.z), dir = f3(dd.x, dd.y, dd.z);
-            // slab test against the receiver's box first
-            const float ix = safe_rcp(dir.x), iy = safe_rcp(dir.y), iz = safe_rcp(dir.z);
-            const float lx = (t1.x - org.x) * ix, hx = (t1.y - org.x) * ix;
-            const float ly = (t1.z - org.y) * iy, hy = (t1.w - org.y) * iy;
-            const float lz = (t2.z - org.z) * iz, hz = (t2.w - org.z) * iz;
-            const float tmin = fmaxf(fmaxf(fminf(lx, hx), fminf(ly, hy)), fmaxf(fminf(lz, hz), 0.f));
-            const float tmax = fminf(fminf(fmaxf(lx, hx), fmaxf(ly, hy)), fminf(fmaxf(lz, hz), ot.w));
-            if (tmin <= tmax) {
+        // ---- scan: advance to the next segment that enters the bounding ball
+        if (!done && !cand) {
+#pragma unroll 1
+            for (int burst = 0; burst < 16 && !cand && !done; ++burst) {
+                const size_t ci = (size_t)k * (size_t)p.pc_stride + (size_t)ray;
+                ot = __ldcs(p.pc_org_t + ci);
+                dd = __ldcs(p.pc_dir_d + ci);
+                const float ocx = ot.x - ctr.x, ocy = ot.y - ctr.y, ocz = ot.z - ctr.z;
+                const float b = ocx * dd.x + ocy * dd.y + ocz * dd.z;
+                const float c = ocx * ocx + ocy * ocy + ocz * ocz - r2;
+                const float d2 = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
+                const float disc = b * b - d2 * c;
+                // enters the ball at t0 = (-b - sqrt(disc))/d2, leaves at t1; needs t1 >= 0 and t0 <= t_wall
+                bool pass = false;
+                if (disc >= 0.f) {
+                    const float sq = sqrtf(disc);
+                    pass = (-b + sq) >= 0.f && (-b - sq) <= ot.w * d2;
+                }
+                if (pass) cand = true;
+                else if (++k >= n) done = true;
+            }
+        }
+        const unsigned cm = __ballot_sync(FULL, cand);
+        const unsigned sm = __ballot_sync(FULL, !done && !cand);
+        if (cm == 0 && sm == 0) break;
+        if (cm != 0 && (__popc(cm) >= kRerenderBatch || sm == 0)) {
+            bool dep = false;
+            int bin = -1, primary = 0;
+            if (cand) {
+                const F3 org = f3(ot.x, ot.y, ot.z), dir = f3(dd.x, dd.y, dd.z);
                 Hit h;
                 closest_hit(p.nodes, p.tris, p.recv_root, org, dir, ot.w, h);
                 if (h.slot >= 0 && h.t < ot.w) {
@@ -349,6 +403,7 @@ __global__ void __launch_bounds__(kThreads) rerender_kernel(const TraceParams p)
                     const F3 pt = hit_point(f3(a.x, a.y, a.z), f3(b4.x, b4.y, b4.z), f3(c4.x, c4.y, c4.z), h.u, h.v);
                     const F3 dp = sub3(pt, org);
                     const float dist = __fadd_rn(dd.w, __fsqrt_rn(dot3(dp, dp)));
+                    const size_t ci = (size_t)k * (size_t)p.pc_stride + (size_t)ray;
 #pragma unroll
                     for (int b = 0; b < NB; ++b) energy[b] = p.pc_energy[ci * NB + b];
                     bin = receiver_hit<NB>(p, pt, dir, dist, energy);
@@ -356,11 +411,13 @@ __global__ void __launch_bounds__(kThreads) rerender_kernel(const TraceParams p)
                     dep = bin >= 0 && bin < p.ir_len;
                     rbin = bin; rear = (mat == -1) ? 1 : 2; rnseg = k + 1;
                     done = true;
+                } else if (++k >= n) {
+                    done = true;
                 }
+                cand = false;
             }
-            k++;
+            deposit_warp<NB>(p, dep, bin, primary, energy);
         }
-        deposit_warp<NB>(p, dep, bin, primary, energy);
     }
     if (valid) {
         if (p.rec_bin) p.rec_bin[ray] = rbin;
@@ -371,8 +428,7 @@ __global__ void __launch_bounds__(kThreads) rerender_kernel(const TraceParams p)
             for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = rear ? energy[b] : 0.f;
         }
     }
-    unsigned long long segs = (unsigned long long)rnseg;
-    if (!valid) segs = 0;
+    unsigned long long segs = valid ? (unsigned long long)rnseg : 0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
     if ((threadIdx.x & 31) == 0 && segs) atomicAdd(p.counters + 1, segs);
@@ -413,10 +469,10 @@ cudaError_t launch_trace(const TraceParams& p, int bands, int mode, int sm_count
 cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaStream_t stream)
 {
     (void)sm_count;
-    const unsigned grid = (unsigned)((p.n_rays + kThreads - 1) / kThreads);
+    const unsigned grid = (unsigned)((p.n_rays + kRerenderThreads - 1) / kRerenderThreads);
     if (grid == 0) return cudaSuccess;
-    if (bands == 1) rerender_kernel<1><<<grid, kThreads, 0, stream>>>(p);
-    else if (bands == 8) rerender_kernel<8><<<grid, kThreads, 0, stream>>>(p);
+    if (bands == 1) rerender_kernel<1><<<grid, kRerenderThreads, 0, stream>>>(p);
+    else if (bands == 8) rerender_kernel<8><<<grid, kRerenderThreads, 0, stream>>>(p);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

@@ -25,6 +25,7 @@ struct TraceParams {
     unsigned long long seed;
     long long ray_begin, n_rays;
     float emitter[3], center[3];
+    float recv_radius;          // ball about `center` that contains the placed receiver mesh (padded)
     float energy0, energy_thres, dist_thr, cross_gain, fs;
     unsigned max_bounces;
     int delay, ir_len, mono;
