@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "arv2_internal.h"
+#include "bvh_lbvh.cuh"
 #include "conv.cuh"
 #include "trace.cuh"
 
@@ -420,12 +421,16 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     }
 
     // scene BVH (built once; OR/AudioRenderer.cpp:95-218 rebuilds on every move)
-    const unsigned hc = std::thread::hardware_concurrency();
-    build_bvh_sah(c->scene.tri_verts.data(), c->n_scene, &c->scene_bvh, hc ? (int)hc : 1);
-    c->n_scene_nodes = (int32_t)c->scene_bvh.nodes.size();
     const int64_t n_recv = c->n_left + c->n_right;
     c->n_recv_nodes = (int32_t)std::max<int64_t>(1, n_recv);
-    const size_t total_nodes = 1 + (size_t)c->n_scene_nodes + (size_t)c->n_recv_nodes;
+    const bool gpu_build = desc->bvh_builder == 1 && c->n_scene > kMaxLeafTris;
+    const unsigned hc = std::thread::hardware_concurrency();
+    if (!gpu_build) {
+        build_bvh_sah(c->scene.tri_verts.data(), c->n_scene, &c->scene_bvh, hc ? (int)hc : 1);
+        c->n_scene_nodes = (int32_t)c->scene_bvh.nodes.size();
+    }
+    const size_t scene_node_cap = gpu_build ? (size_t)c->n_scene : (size_t)c->n_scene_nodes;
+    const size_t total_nodes = 1 + scene_node_cap + (size_t)c->n_recv_nodes;
     const size_t total_tris = (size_t)std::max<int64_t>(1, c->n_scene + n_recv);
     CKC(cudaMalloc(&c->d_nodes, total_nodes * 4 * sizeof(float4)));
     CKC(cudaMalloc(&c->d_tris, total_tris * 3 * sizeof(float4)));
@@ -433,15 +438,21 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     CKC(cudaMalloc(&c->d_scatter, scat.size() * sizeof(float)));
     CKC(cudaMemcpy(c->d_keep, keep.data(), keep.size() * sizeof(float), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_scatter, scat.data(), scat.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (gpu_build) {
+        // K1: Morton / radix sort / Karras tree / refit / collapse, all on the device
+        float* d_v = nullptr; int* d_m = nullptr;
+        CKC(cudaMalloc(&d_v, (size_t)c->n_scene * 9 * sizeof(float)));
+        cudaError_t e = cudaMalloc(&d_m, (size_t)c->n_scene * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpy(d_v, c->scene.tri_verts.data(), (size_t)c->n_scene * 9 * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_m, c->scene.tri_mesh.data(), (size_t)c->n_scene * sizeof(int), cudaMemcpyHostToDevice);
+        LbvhResult res{};
+        if (e == cudaSuccess) e = build_bvh_lbvh(d_v, d_m, (int)c->n_scene, 0, c->d_nodes + 4, c->d_tris, 1, 0, &res, c->stream);
+        cudaFree(d_v); cudaFree(d_m);
+        if (e != cudaSuccess) { set_error(std::string("build_bvh_lbvh: ") + cudaGetErrorString(e)); return fail(ARV2_ERR_CUDA); }
+        c->n_scene_nodes = res.n_nodes;
+        for (int a = 0; a < 3; ++a) { c->scene_bvh.lo[a] = res.lo[a]; c->scene_bvh.hi[a] = res.hi[a]; }
+    }
     {
-        // scene nodes at [1, 1+ns), scene tris at [0, n_scene)
-        std::vector<BvhNode> nodes = c->scene_bvh.nodes;
-        for (auto& d : nodes) {
-            int32_t ch[4];
-            std::memcpy(ch, &d.q[12], sizeof ch);
-            for (int w = 0; w < 2; ++w) if (ch[w] >= 0) ch[w] += 1;
-            std::memcpy(&d.q[12], ch, sizeof ch);
-        }
         // top node without a receiver: child1 empty
         BvhNode top{};
         const float* slo = c->scene_bvh.lo; const float* shi = c->scene_bvh.hi;
@@ -451,6 +462,16 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
         int32_t ch[4] = {1, ~0, 0, 0};
         std::memcpy(&top.q[12], ch, sizeof ch);
         CKC(cudaMemcpy(c->d_nodes, &top, sizeof top, cudaMemcpyHostToDevice));
+    }
+    if (!gpu_build) {
+        // scene nodes at [1, 1+ns), scene tris at [0, n_scene)
+        std::vector<BvhNode> nodes = c->scene_bvh.nodes;
+        for (auto& d : nodes) {
+            int32_t ch[4];
+            std::memcpy(ch, &d.q[12], sizeof ch);
+            for (int w = 0; w < 2; ++w) if (ch[w] >= 0) ch[w] += 1;
+            std::memcpy(&d.q[12], ch, sizeof ch);
+        }
         CKC(cudaMemcpy(c->d_nodes + 4, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
         std::vector<float4> tris((size_t)c->n_scene * 3);
         for (int64_t s = 0; s < c->n_scene; ++s) {

@@ -295,6 +295,7 @@ def main():
     if not args.skip_extras:
         extras.update(bench_rerender(arv, torch, dev, local, scene, receiver, mats, args))
         extras.update(bench_conv(arv, torch, dist, dev, local, rank, world, args))
+        extras.update(bench_lbvh(arv, scene, receiver, mats, local))
 
     line = {
         "metric": "Grays/s IR trace", "value": value, "unit": "Grays/s", "n_gpus": world, "steps": args.steps,
@@ -339,6 +340,27 @@ def bench_rerender(arv, torch, dev, local, scene, receiver, mats, args):
     r.close()
     return {"rerender_ms": float(np.median(ms[3:])), "rerender_wall_ms": float(np.median(wall[3:])),
             "rerender_cached_segments": segs, "path_cache_build_ms": build_ms}
+
+
+def bench_lbvh(arv, scene, receiver, mats, local):
+    """K1: GPU LBVH build (Morton + radix sort + Karras + refit + collapse) of the same scene,
+    and the trace rate on that tree (the host SAH tree is the default for static scenes)."""
+    per_gpu = RAYS[0] * RAYS[1] * RAYS[2]
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r = arv.AudioRenderer(scene, IR_SECONDS, FS, mats, (per_gpu, 1, 1), receiver=receiver, device=local, bvh_builder=1)
+        dt = 1e3 * (time.perf_counter() - t0)
+        best = dt if best is None else min(best, dt)
+        if _ < 2:
+            r.close()
+    r.setBasePower(100.0); r.setThresholds(0.0, MAX_BOUNCES); r.set_hrtf_absorption_rate(0.9)
+    r.setEmitterPosInOptix(EMITTER); r.setSphereCenterInOptix(RECEIVER, YAW); r.set_seed(SEED)
+    r.render()
+    ms = r.render()
+    segs = r.last_segments()
+    r.close()
+    return {"lbvh_create_ms": best, "lbvh_trace_grays_per_s": segs / (ms * 1e-3) / 1e9}
 
 
 def bench_conv(arv, torch, dist, dev, local, rank, world, args):

@@ -159,3 +159,26 @@ def test_write_ir_text(golden_scenes, golden_receiver, tmp_path):
     got = np.array([float(x.strip()) for x in open(a)])          # utils/printIR.py:9-12
     assert got.shape == (16000,)
     assert np.allclose(got, l[0], rtol=1e-5, atol=0)
+
+
+def test_gpu_lbvh_builder_gives_identical_hits(golden_scenes, golden_receiver):
+    """K1 (bvh_lbvh.cu): the GPU-built LBVH and the host SAH tree are different trees over
+    the same triangles; closest hit = min (t, id) over exact tests, so every per-ray
+    record must be identical (and equal to the oracle)."""
+    tv, tm, names = scenes.conference_room(target_tris=60_000)
+    cases = [
+        Case(tv, tm, names, golden_receiver, rays=(100, 100, 1), emitter=(2.0, 1.5, 2.0), center=(9.0, 1.4, 5.5), yaw=30.0,
+             materials=scenes.materials(), max_bounces=30, sample_rate=48000, ir_seconds=1),
+        Case(golden_scenes["toro_verts"], golden_scenes["toro_mesh"], golden_scenes["toro_names"], golden_receiver,
+             rays=(50, 50, 4), emitter=(0, 5, 0), center=(6, 2, 3), max_bounces=20),
+        c1(golden_scenes, golden_receiver, rays=(100, 100, 1)),
+    ]
+    for case in cases:
+        ra, reca, la, rra, segsa, _ = run(case, bvh_builder=0)
+        rb, recb, lb, rrb, segsb, _ = run(case, bvh_builder=1)
+        assert segsa == segsb
+        for k in ("bin", "ear", "nseg", "energy"):
+            assert np.array_equal(reca[k], recb[k]), k
+        assert np.allclose(la, lb, rtol=1e-6, atol=0) and np.allclose(rra, rrb, rtol=1e-6, atol=0)
+    r, rec, l, rr, segs, _ = run(cases[0], bvh_builder=1)
+    assert check_parity(rec, l, rr, segs, cases[0].oracle_run()) >= 0.9999
