@@ -339,6 +339,240 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceP
     if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
 }
 
+// ---------------------------------------------------------------------------------------
+// trace2_kernel: the same path tracer as trace_kernel with the lanes of a warp decoupled.
+// r01/r02 profiles: per-segment node-visit counts vary so much inside a warp (sum / (32 x max)
+// = 49 %) that the inner loop of trace_kernel runs at 12 of 32 lanes.  Here a lane that has
+// finished its segment parks (cur == kSentinel) while the others keep traversing; three
+// warp-uniform phases are scheduled by ballots:
+//   A  shade + deposit + refill + start the next segment -- when >= kTA lanes are parked
+//   L  one leaf (<= 4 triangle tests) per lane           -- when >= kTL lanes stand at a leaf
+//   I  up to kBurst inner-node steps                      -- otherwise
+// so every phase runs with many lanes and nobody waits for the slowest traversal.
+#ifndef ARV2_TA
+#define ARV2_TA 12
+#endif
+#ifndef ARV2_TL
+#define ARV2_TL 8
+#endif
+#ifndef ARV2_BURST
+#define ARV2_BURST 4
+#endif
+template <int NB, int MODE>
+__global__ void __launch_bounds__(kThreads, ARV2_MINB) trace2_kernel(const TraceParams p)
+{
+    const int lane = threadIdx.x & 31;
+    long long chunk_next = 0, chunk_end = 0;      // warp-uniform
+    bool have = false, exhausted = false, pending = false;
+    long long ray = 0;
+    F3 org = f3(0, 0, 0), dir = f3(0, 0, 0);
+    float energy[NB];
+    float dist = 0.f;
+    int depth = 0, nseg = 0;
+    unsigned long long segs = 0;
+    // traversal state of the segment in flight
+    int stack[kStack];
+    int sp = 0, cur = kSentinel;
+    float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+    Hit h;
+    h.t = 1e20f; h.u = 0.f; h.v = 0.f; h.slot = -1; h.id = INT_MAX;
+    const float4* __restrict__ nodes = p.nodes;
+    const float4* __restrict__ tris = p.tris;
+
+    for (;;) {
+        const bool at_inner = cur >= 0;
+        const bool at_leaf = cur < 0 && cur != kSentinel;
+        const bool parked = cur == kSentinel && !exhausted;
+        const unsigned inner_m = __ballot_sync(FULL, at_inner);
+        const unsigned leaf_m = __ballot_sync(FULL, at_leaf);
+        const unsigned park_m = __ballot_sync(FULL, parked);
+        if ((inner_m | leaf_m | park_m) == 0) break;
+
+        if (park_m != 0 && (__popc(park_m) >= ARV2_TA || (inner_m | leaf_m) == 0)) {
+            // ======================= phase A: shade, deposit, refill, start next segment
+            bool ended = false, dep = false;
+            int bin = -1, ear = 0, primary = 0;
+            if (parked && have && pending) {
+                pending = false;
+                if (MODE == 1) p.pc_org_t[(size_t)(nseg - 1) * (size_t)p.pc_stride + (size_t)ray] = make_float4(org.x, org.y, org.z, h.t);
+                if (h.slot < 0) {
+                    ended = true;                                                               // miss :186-190
+                } else {
+                    const float4 a = __ldg(tris + h.slot * 3 + 0);
+                    const float4 b4 = __ldg(tris + h.slot * 3 + 1);
+                    const float4 c4 = __ldg(tris + h.slot * 3 + 2);
+                    const F3 p1 = f3(a.x, a.y, a.z), p2 = f3(b4.x, b4.y, b4.z), p3 = f3(c4.x, c4.y, c4.z);
+                    const int mat = __float_as_int(b4.w);
+                    const F3 pt = hit_point(p1, p2, p3, h.u, h.v);
+                    const F3 dp = sub3(pt, org);
+                    dist = __fadd_rn(dist, __fsqrt_rn(dot3(dp, dp)));                           // :83
+                    if (mat < 0) {
+                        bin = receiver_hit<NB>(p, pt, dir, dist, energy);
+                        ear = (mat == -1) ? 1 : 2;
+                        primary = (mat == -1) ? 0 : 1;
+                        dep = bin >= 0 && bin < p.ir_len;
+                        ended = true;                                                           // :147,:169
+                    } else {
+                        const F3 nc = cross3(sub3(p2, p1), sub3(p3, p1));                       // :75-77
+                        const float ninv = __fdiv_rn(1.0f, __fsqrt_rn(dot3(nc, nc)));
+                        const F3 ng = f3(__fmul_rn(nc.x, ninv), __fmul_rn(nc.y, ninv), __fmul_rn(nc.z, ninv));
+                        bool diffuse = false;
+                        uint32_t r[4];
+                        if (p.any_scatter) {
+                            const float sc = __ldg(p.scattering + mat);
+                            if (sc > 0.f) {
+                                philox4x32(p.seed, (uint64_t)(p.ray_begin + ray), (uint32_t)depth, 1u, r);
+                                diffuse = __fmul_rn((float)(r[0] >> 8), 0x1p-24f) < sc;
+                            }
+                        }
+                        if (diffuse) {
+                            dir = lambert_direction(r, dir, ng);
+                        } else {
+                            const float k = __fmul_rn(2.0f, dot3(dir, ng));                     // :173
+                            dir = f3(__fmaf_rn(-k, ng.x, dir.x), __fmaf_rn(-k, ng.y, dir.y), __fmaf_rn(-k, ng.z, dir.z));
+                        }
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) energy[b] = __fmul_rn(energy[b], __ldg(p.keep + mat * NB + b)); // :174
+                        depth++;                                                                // :175
+                        org = f3(__fmaf_rn(1e-3f, dir.x, pt.x), __fmaf_rn(1e-3f, dir.y, pt.y), __fmaf_rn(1e-3f, dir.z, pt.z)); // :179
+                    }
+                }
+            }
+            if (MODE == 0) deposit_warp<NB>(p, dep, bin, primary, energy);
+
+            // loop guard for the paths that go on (:233-236)
+            if (parked && have && !ended) {
+                float emax = energy[0];
+#pragma unroll
+                for (int b = 1; b < NB; ++b) emax = fmaxf(emax, energy[b]);
+                if (!(dist < p.dist_thr && emax > p.energy_thres && (unsigned)depth < p.max_bounces)) ended = true;
+            }
+            if (parked && have && ended) {
+                if (p.rec_bin) p.rec_bin[ray] = bin;
+                if (p.rec_ear) p.rec_ear[ray] = ear;
+                if (p.rec_nseg) p.rec_nseg[ray] = nseg;
+                if (p.rec_energy) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = ear ? energy[b] : 0.f;
+                }
+                if (MODE == 1) p.pc_nseg[ray] = nseg;
+                segs += (unsigned long long)nseg;
+                have = false;
+            }
+            // refill parked lanes without a path from the warp's chunk (ballot/popc compaction)
+            unsigned need = __ballot_sync(FULL, parked && !have);
+            while (need) {
+                if (chunk_next >= chunk_end) {
+                    unsigned long long b = 0;
+                    if (lane == 0) b = atomicAdd(p.counters, (unsigned long long)kChunk);
+                    b = __shfl_sync(FULL, b, 0);
+                    chunk_next = (long long)b;
+                    chunk_end = min((long long)b + kChunk, p.n_rays);
+                    if (chunk_next >= chunk_end) {
+                        if (parked && !have) exhausted = true;
+                        break;
+                    }
+                }
+                const int avail = (int)min((long long)32, chunk_end - chunk_next);
+                const int rank = __popc(need & ((1u << lane) - 1u));
+                if (((need >> lane) & 1u) && rank < avail) {
+                    ray = chunk_next + rank;
+                    have = true;
+                    org = f3(p.emitter[0], p.emitter[1], p.emitter[2]);          // :210
+                    dir = emit_direction(p.seed, (uint64_t)(p.ray_begin + ray)); // :216-224
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) energy[b] = p.energy0;          // :208
+                    dist = 0.f; depth = 0; nseg = 0;                             // :209,:211
+                    // a fresh path can only fail the guard through its parameters (or a zero direction, :230)
+                    const bool zero_dir = !(dir.x != 0.f || dir.y != 0.f || dir.z != 0.f);
+                    if (zero_dir || !(0.f < p.dist_thr && p.energy0 > p.energy_thres && 0u < p.max_bounces)) {
+                        if (p.rec_bin) p.rec_bin[ray] = -1;
+                        if (p.rec_ear) p.rec_ear[ray] = 0;
+                        if (p.rec_nseg) p.rec_nseg[ray] = 0;
+                        if (p.rec_energy) {
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = 0.f;
+                        }
+                        if (MODE == 1) p.pc_nseg[ray] = 0;
+                        have = false;                                            // picks another ray in the next round
+                    }
+                }
+                chunk_next += min(__popc(need), avail);
+                need = __ballot_sync(FULL, parked && !have && !exhausted);
+            }
+            // start the next segment
+            if (parked && have) {
+                if (MODE == 1) {
+                    const size_t ci = (size_t)nseg * (size_t)p.pc_stride + (size_t)ray;
+                    p.pc_dir_d[ci] = make_float4(dir.x, dir.y, dir.z, dist);
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) p.pc_energy[ci * NB + b] = energy[b];
+                }
+                nseg++;
+                ix = safe_rcp(dir.x); iy = safe_rcp(dir.y); iz = safe_rcp(dir.z);
+                ox = org.x * ix; oy = org.y * iy; oz = org.z * iz;
+                stack[0] = kSentinel; sp = 1;
+                cur = p.root;
+                h.t = 1e20f; h.u = 0.f; h.v = 0.f; h.slot = -1; h.id = INT_MAX;
+                pending = true;
+            }
+        } else if (leaf_m != 0 && (__popc(leaf_m) >= ARV2_TL || inner_m == 0)) {
+            // ======================= phase L: one leaf per lane
+            if (at_leaf) {
+                const int code = ~cur;
+                const int first = code >> 3;
+                const int cnt = (code & 7) + 1;
+                for (int i = 0; i < cnt; ++i) {
+                    const int slot = first + i;
+                    const float4 a = __ldg(tris + slot * 3 + 0);
+                    const float4 b = __ldg(tris + slot * 3 + 1);
+                    const float4 c = __ldg(tris + slot * 3 + 2);
+                    float t, u, v;
+                    if (tri_test(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), org, dir, &t, &u, &v)) {
+                        const int id = __float_as_int(a.w);
+                        if (t < h.t || (t == h.t && id < h.id)) { h.t = t; h.u = u; h.v = v; h.slot = slot; h.id = id; }
+                    }
+                }
+                cur = stack[--sp];
+            }
+        } else {
+            // ======================= phase I: a burst of inner-node steps
+#pragma unroll 1
+            for (int k = 0; k < ARV2_BURST; ++k) {
+                if (cur >= 0) {
+                    const F8 na = ldg256(nodes + cur * 4), nb = ldg256(nodes + cur * 4 + 2);
+                    const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
+                    const float c0lox = fmaf(n0.x, ix, -ox), c0hix = fmaf(n0.y, ix, -ox);
+                    const float c0loy = fmaf(n0.z, iy, -oy), c0hiy = fmaf(n0.w, iy, -oy);
+                    const float c0loz = fmaf(n2.x, iz, -oz), c0hiz = fmaf(n2.y, iz, -oz);
+                    const float c1lox = fmaf(n1.x, ix, -ox), c1hix = fmaf(n1.y, ix, -ox);
+                    const float c1loy = fmaf(n1.z, iy, -oy), c1hiy = fmaf(n1.w, iy, -oy);
+                    const float c1loz = fmaf(n2.z, iz, -oz), c1hiz = fmaf(n2.w, iz, -oz);
+                    const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.f));
+                    const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
+                    const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.f));
+                    const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
+                    const bool go0 = c0min <= c0max, go1 = c1min <= c1max;
+                    const int i0 = __float_as_int(n3.x), i1 = __float_as_int(n3.y);
+                    if (!go0 && !go1) {
+                        cur = stack[--sp];
+                    } else {
+                        cur = go0 ? i0 : i1;
+                        if (go0 && go1) {
+                            int far = i1;
+                            if (c1min < c0min) { cur = i1; far = i0; }
+                            stack[sp++] = far;
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
+    if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+}
+
 // Receiver move: walk each ray's cached receiver-independent segments in order and
 // deposit at the first one the receiver intercepts before the wall (t_recv < t_wall;
 // ties go to the scene because scene triangle ids are lower).  One thread per ray,
@@ -447,13 +681,18 @@ template <int NB, int MODE>
 cudaError_t launch_trace_t(const TraceParams& p, int sm_count, cudaStream_t stream)
 {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel<NB, MODE>, kThreads, 0);
+#ifdef ARV2_TRACE_V1
+    auto kernel = trace_kernel<NB, MODE>;
+#else
+    auto kernel = trace2_kernel<NB, MODE>;
+#endif
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long want = (p.n_rays + kThreads - 1) / kThreads;
     long long grid = (long long)sm_count * per_sm;
     if (want < grid) grid = want < 1 ? 1 : want;
-    trace_kernel<NB, MODE><<<(unsigned)grid, kThreads, 0, stream>>>(p);
+    kernel<<<(unsigned)grid, kThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
