@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <climits>
 #include <string>
 #include <vector>
 
@@ -60,6 +61,27 @@ void build_bvh_sah(const float* tri_verts, int64_t n, HostBvh* out, int n_thread
 void refit_bvh(const float* tri_verts, int64_t n, HostBvh* bvh);
 // Conservative padding applied to every box (relative to the scene extent).
 inline float bvh_pad(float extent) { return extent * 1e-5f + 1e-6f; }
+
+// ---- device layout: 16-bit quantised binary BVH ---------------------------------------------
+// 32 B per node = one 256-bit load (the tracer is bound by L1 wavefronts = load instructions
+// per lane, not bytes): both child boxes quantised to the tree's 65536^3 grid
+//   w0..w2 = child 0: (lo | hi << 16) for x, y, z      w3..w5 = child 1
+//   w6, w7 = child codes: >= 0 inner node index, < 0 leaf ~((first << 3) | (count-1))
+// plane = grid.origin + q * grid.cell, rounded outwards by 2 cells; an absent child is the
+// inverted box (lo = 65535, hi = 0).  The scene and the receiver are two trees with their own
+// grids, walked one after the other (no top node), so a receiver move rewrites ~55 KB.
+// Triangles, 64 B = two 256-bit loads: (P1, id) (P2, material) (P3, Ng.x) (Ng.y, Ng.z, 0, 0),
+// Ng = the unit normal of the arithmetic contract, precomputed once.
+struct QNode { uint32_t w[8]; };
+struct QuantGrid { float origin[3]; float cell[3]; };
+constexpr int kTraversalStack = 64;      // per-lane stack entries of the kernels (trace.cu)
+
+QuantGrid make_quant_grid(const float lo[3], const float hi[3]);
+// Same topology and node numbering as `bvh2`; inner codes + node_offset, leaf slots + slot_offset.
+void quantize_bvh2(const HostBvh& bvh2, const QuantGrid& g, int32_t node_offset, int64_t slot_offset, std::vector<QNode>* out);
+int bvh2_depth(const HostBvh& bvh2);
+// 64 B triangle record (normal precomputed with the contract's operations).
+void make_tri_record(const float* v9, int32_t id, int32_t material, float* out16);
 
 // ---- host front end -------------------------------------------------------------
 int load_obj(const std::string& path, HostScene* out, std::string* err);

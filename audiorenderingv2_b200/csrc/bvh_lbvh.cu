@@ -1,6 +1,7 @@
 // bvh_lbvh.cu -- GPU LBVH builder (K1): Morton codes -> radix sort -> Karras radix tree ->
 // bottom-up refit -> collapse of <=4-triangle subtrees into leaves -> emission in the
-// traversal layout of arv2_internal.h.  All hand-written sm_100a kernels, no CUB/Thrust.
+// binary layout of arv2_internal.h (BvhNode); the host then quantises it like the SAH tree.
+// All hand-written sm_100a kernels, no CUB/Thrust.
 //
 // Replaces optixAccelBuild (OR/AudioRenderer.cpp:95-218) when a fast rebuild matters more
 // than tree quality (desc.bvh_builder = 1); the host binned-SAH builder stays the default
@@ -275,7 +276,7 @@ __global__ void tri_gather_kernel(const float* __restrict__ verts, const int* __
 #define LB(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return e_; } } while (0)
 
 cudaError_t build_bvh_lbvh(const float* d_verts, const int* d_mats, int n, int id_base, float4* d_nodes, float4* d_tris,
-                           int node_offset, int slot_offset, LbvhResult* out, cudaStream_t stream)
+                           int* d_order, int node_offset, int slot_offset, LbvhResult* out, cudaStream_t stream)
 {
     if (n <= kMaxLeafTris) return cudaErrorInvalidValue;    // tiny inputs take the host builder
     unsigned *keys[2] = {nullptr, nullptr}, *counts = nullptr, *flags = nullptr;
@@ -330,7 +331,8 @@ cudaError_t build_bvh_lbvh(const float* d_verts, const int* d_mats, int n, int i
     for (int a = 0; a < 3; ++a) { out->lo[a] -= pad; out->hi[a] += pad; }
     out->n_nodes = (int)h_nodes;
     emit_kernel<<<G, T, 0, stream>>>(n, left, right, first, last, boxes, flags, node_offset, slot_offset, pad, d_nodes);
-    tri_gather_kernel<<<G, T, 0, stream>>>(d_verts, d_mats, vals[cur], n, id_base, slot_offset, d_tris);
+    if (d_tris) tri_gather_kernel<<<G, T, 0, stream>>>(d_verts, d_mats, vals[cur], n, id_base, slot_offset, d_tris);
+    if (d_order) LB(cudaMemcpyAsync(d_order, vals[cur], (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, stream));
     LB(cudaGetLastError());
     LB(cudaStreamSynchronize(stream));
     cleanup();

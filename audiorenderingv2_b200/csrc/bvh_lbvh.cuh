@@ -10,7 +10,8 @@ struct LbvhResult { int n_nodes; float lo[3], hi[3]; };
 // d_verts: float[n][9], d_mats: int[n] (device).  Writes n_nodes 64 B nodes to d_nodes (node 0 =
 // root; inner child indices are stored + node_offset) and n triangles in leaf order to
 // d_tris (slots + slot_offset, global ids id_base + input index).  Needs n > 4.
+// d_tris (48 B records in leaf order) and d_order (leaf-order slot -> input index) are optional.
 cudaError_t build_bvh_lbvh(const float* d_verts, const int* d_mats, int n, int id_base, float4* d_nodes, float4* d_tris,
-                           int node_offset, int slot_offset, LbvhResult* out, cudaStream_t stream);
+                           int* d_order, int node_offset, int slot_offset, LbvhResult* out, cudaStream_t stream);
 
 } // namespace arv2

@@ -53,7 +53,10 @@ struct arv2_ctx {
     HostScene scene;
     HostReceiver receiver;
     bool has_receiver = false;
-    HostBvh scene_bvh, recv_bvh;
+    HostBvh recv_bvh;
+    std::vector<QNode> recv_q;
+    QuantGrid scene_grid{}, recv_grid{};
+    size_t upload_bytes = 0;
     bool recv_bvh_built = false;
     std::vector<float> recv_world;     // [n_recv][3][3]
     int64_t n_scene = 0, n_left = 0, n_right = 0;
@@ -124,50 +127,23 @@ int upload_receiver(arv2_ctx* c)
     } else {
         refit_bvh(c->recv_world.data(), n, &c->recv_bvh);
     }
-    // stage: [top node (4 f4)] [recv nodes] [recv tris]
-    const int32_t nn = (int32_t)c->recv_bvh.nodes.size();
-    const int32_t node_base = 1 + c->n_scene_nodes;
+    // quantise the (re)fitted tree on its own grid and stage [receiver nodes][receiver triangles]
+    const int32_t node_base = c->n_scene_nodes;
     const int64_t tri_base = c->n_scene;
-    float4* st = c->h_stage;
-    // top node: child0 = scene root (node 1), child1 = receiver root
-    {
-        BvhNode top{};
-        const float* slo = c->scene_bvh.lo; const float* shi = c->scene_bvh.hi;
-        const float* rlo = c->recv_bvh.lo; const float* rhi = c->recv_bvh.hi;
-        top.q[0] = slo[0]; top.q[1] = shi[0]; top.q[2] = slo[1]; top.q[3] = shi[1];
-        top.q[4] = rlo[0]; top.q[5] = rhi[0]; top.q[6] = rlo[1]; top.q[7] = rhi[1];
-        top.q[8] = slo[2]; top.q[9] = shi[2]; top.q[10] = rlo[2]; top.q[11] = rhi[2];
-        int32_t ch[4] = {1, node_base, 0, 0};
-        std::memcpy(&top.q[12], ch, sizeof ch);
-        std::memcpy(st, &top, sizeof top);
-    }
-    float4* sn = st + 4;
-    for (int32_t i = 0; i < nn; ++i) {
-        BvhNode d = c->recv_bvh.nodes[i];
-        int32_t ch[4];
-        std::memcpy(ch, &d.q[12], sizeof ch);
-        for (int w = 0; w < 2; ++w) {
-            if (ch[w] >= 0) ch[w] += node_base;
-            else { const int32_t code = ~ch[w]; ch[w] = ~(int32_t)((((int64_t)(code >> kLeafShift) + tri_base) << kLeafShift) | (code & 7)); }
-        }
-        std::memcpy(&d.q[12], ch, sizeof ch);
-        std::memcpy(sn + 4 * i, &d, sizeof d);
-    }
-    float4* stt = sn + 4 * (size_t)c->n_recv_nodes;
+    c->recv_grid = make_quant_grid(c->recv_bvh.lo, c->recv_bvh.hi);
+    quantize_bvh2(c->recv_bvh, c->recv_grid, node_base, tri_base, &c->recv_q);
+    const int32_t nn = (int32_t)c->recv_q.size();
+    if (nn > c->n_recv_nodes || bvh2_depth(c->recv_bvh) + 2 > kTraversalStack) { set_error("receiver BVH exceeds its reservation"); return ARV2_ERR_STATE; }
+    float4* sn = c->h_stage;
+    std::memcpy(sn, c->recv_q.data(), (size_t)nn * sizeof(QNode));
+    float4* stt = sn + 2 * (size_t)c->n_recv_nodes;
     for (int64_t s = 0; s < n; ++s) {
         const int32_t src = c->recv_bvh.order[s];
-        const float* v = c->recv_world.data() + 9 * (size_t)src;
-        const int32_t gid = (int32_t)(tri_base + src);
-        const int32_t mat = src < nl ? -1 : -2;
-        float idf, matf;
-        std::memcpy(&idf, &gid, 4); std::memcpy(&matf, &mat, 4);
-        stt[3 * s + 0] = make_float4(v[0], v[1], v[2], idf);
-        stt[3 * s + 1] = make_float4(v[3], v[4], v[5], matf);
-        stt[3 * s + 2] = make_float4(v[6], v[7], v[8], 0.f);
+        make_tri_record(c->recv_world.data() + 9 * (size_t)src, (int32_t)(tri_base + src), src < nl ? -1 : -2, (float*)(stt + 4 * s));
     }
-    CK(cudaMemcpyAsync(c->d_nodes, st, sizeof(float4) * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_nodes + 4 * (size_t)node_base, sn, sizeof(float4) * 4 * (size_t)nn, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_tris + 3 * (size_t)tri_base, stt, sizeof(float4) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_nodes + 2 * (size_t)node_base, sn, sizeof(QNode) * (size_t)nn, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_tris + 4 * (size_t)tri_base, stt, sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    c->upload_bytes = sizeof(QNode) * (size_t)nn + sizeof(float4) * 4 * (size_t)n;
     c->recv_dirty = false;
     return ARV2_OK;
 }
@@ -197,7 +173,12 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     p->max_bounces = c->max_bounces;
     p->delay = (int)((double)c->desc.sample_rate * 0.00044);   // :125
     p->ir_len = c->ir_len; p->mono = c->mono;
-    p->root = 0; p->recv_root = 1 + c->n_scene_nodes;
+    p->scene_root = 0; p->recv_root = c->n_scene_nodes;
+    p->has_scene = c->n_scene > 0 ? 1 : 0; p->has_recv = c->has_receiver ? 1 : 0;
+    for (int a = 0; a < 3; ++a) {
+        p->sg_origin[a] = c->scene_grid.origin[a]; p->sg_cell[a] = c->scene_grid.cell[a];
+        p->rg_origin[a] = c->recv_grid.origin[a]; p->rg_cell[a] = c->recv_grid.cell[a];
+    }
     p->any_scatter = c->any_scatter;
 }
 
@@ -420,73 +401,64 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
         if (scat[m] > 0.f) c->any_scatter = 1;
     }
 
-    // scene BVH (built once; OR/AudioRenderer.cpp:95-218 rebuilds on every move)
+    // scene BVH (built once; OR/AudioRenderer.cpp:95-218 rebuilds on every move): binary tree
+    // from the host binned-SAH builder or the GPU LBVH builder (K1), then quantised to the
+    // 32 B node the kernels traverse
     const int64_t n_recv = c->n_left + c->n_right;
     c->n_recv_nodes = (int32_t)std::max<int64_t>(1, n_recv);
     const bool gpu_build = desc->bvh_builder == 1 && c->n_scene > kMaxLeafTris;
     const unsigned hc = std::thread::hardware_concurrency();
+    HostBvh scene2;
     if (!gpu_build) {
-        build_bvh_sah(c->scene.tri_verts.data(), c->n_scene, &c->scene_bvh, hc ? (int)hc : 1);
-        c->n_scene_nodes = (int32_t)c->scene_bvh.nodes.size();
+        build_bvh_sah(c->scene.tri_verts.data(), c->n_scene, &scene2, hc ? (int)hc : 1);
+    } else {
+        float* d_v = nullptr; int* d_m = nullptr; float4* d_n2 = nullptr; int* d_order = nullptr;
+        const size_t n = (size_t)c->n_scene;
+        cudaError_t e = cudaMalloc(&d_v, n * 9 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&d_m, n * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&d_n2, n * 4 * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc(&d_order, n * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemcpy(d_v, c->scene.tri_verts.data(), n * 9 * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_m, c->scene.tri_mesh.data(), n * sizeof(int), cudaMemcpyHostToDevice);
+        LbvhResult res{};
+        if (e == cudaSuccess) e = build_bvh_lbvh(d_v, d_m, (int)n, 0, d_n2, nullptr, d_order, 0, 0, &res, c->stream);
+        if (e == cudaSuccess) {
+            scene2.nodes.resize((size_t)res.n_nodes);
+            scene2.order.resize(n);
+            e = cudaMemcpy(scene2.nodes.data(), d_n2, (size_t)res.n_nodes * sizeof(BvhNode), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(scene2.order.data(), d_order, n * sizeof(int), cudaMemcpyDeviceToHost);
+            for (int a = 0; a < 3; ++a) { scene2.lo[a] = res.lo[a]; scene2.hi[a] = res.hi[a]; }
+        }
+        cudaFree(d_v); cudaFree(d_m); cudaFree(d_n2); cudaFree(d_order);
+        if (e != cudaSuccess) { set_error(std::string("build_bvh_lbvh: ") + cudaGetErrorString(e)); return fail(ARV2_ERR_CUDA); }
     }
-    const size_t scene_node_cap = gpu_build ? (size_t)c->n_scene : (size_t)c->n_scene_nodes;
-    const size_t total_nodes = 1 + scene_node_cap + (size_t)c->n_recv_nodes;
+    if (bvh2_depth(scene2) + 2 > kTraversalStack) { set_error("scene BVH too deep for the traversal stack"); return fail(ARV2_ERR_INVALID); }
+    c->n_scene_nodes = (int32_t)scene2.nodes.size();
+    std::vector<QNode> scene_q;
+    if (c->n_scene > 0) {
+        c->scene_grid = make_quant_grid(scene2.lo, scene2.hi);
+        quantize_bvh2(scene2, c->scene_grid, 0, 0, &scene_q);
+    } else {
+        scene_q.assign(scene2.nodes.size(), QNode{});
+    }
+    const size_t total_nodes = (size_t)c->n_scene_nodes + (size_t)c->n_recv_nodes;
     const size_t total_tris = (size_t)std::max<int64_t>(1, c->n_scene + n_recv);
-    CKC(cudaMalloc(&c->d_nodes, total_nodes * 4 * sizeof(float4)));
-    CKC(cudaMalloc(&c->d_tris, total_tris * 3 * sizeof(float4)));
+    CKC(cudaMalloc(&c->d_nodes, total_nodes * sizeof(QNode)));
+    CKC(cudaMalloc(&c->d_tris, total_tris * 4 * sizeof(float4)));
     CKC(cudaMalloc(&c->d_keep, keep.size() * sizeof(float)));
     CKC(cudaMalloc(&c->d_scatter, scat.size() * sizeof(float)));
     CKC(cudaMemcpy(c->d_keep, keep.data(), keep.size() * sizeof(float), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_scatter, scat.data(), scat.size() * sizeof(float), cudaMemcpyHostToDevice));
-    if (gpu_build) {
-        // K1: Morton / radix sort / Karras tree / refit / collapse, all on the device
-        float* d_v = nullptr; int* d_m = nullptr;
-        CKC(cudaMalloc(&d_v, (size_t)c->n_scene * 9 * sizeof(float)));
-        cudaError_t e = cudaMalloc(&d_m, (size_t)c->n_scene * sizeof(int));
-        if (e == cudaSuccess) e = cudaMemcpy(d_v, c->scene.tri_verts.data(), (size_t)c->n_scene * 9 * sizeof(float), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d_m, c->scene.tri_mesh.data(), (size_t)c->n_scene * sizeof(int), cudaMemcpyHostToDevice);
-        LbvhResult res{};
-        if (e == cudaSuccess) e = build_bvh_lbvh(d_v, d_m, (int)c->n_scene, 0, c->d_nodes + 4, c->d_tris, 1, 0, &res, c->stream);
-        cudaFree(d_v); cudaFree(d_m);
-        if (e != cudaSuccess) { set_error(std::string("build_bvh_lbvh: ") + cudaGetErrorString(e)); return fail(ARV2_ERR_CUDA); }
-        c->n_scene_nodes = res.n_nodes;
-        for (int a = 0; a < 3; ++a) { c->scene_bvh.lo[a] = res.lo[a]; c->scene_bvh.hi[a] = res.hi[a]; }
-    }
     {
-        // top node without a receiver: child1 empty
-        BvhNode top{};
-        const float* slo = c->scene_bvh.lo; const float* shi = c->scene_bvh.hi;
-        top.q[0] = slo[0]; top.q[1] = shi[0]; top.q[2] = slo[1]; top.q[3] = shi[1];
-        top.q[4] = top.q[5] = top.q[6] = top.q[7] = kEmptyBox;
-        top.q[8] = slo[2]; top.q[9] = shi[2]; top.q[10] = top.q[11] = kEmptyBox;
-        int32_t ch[4] = {1, ~0, 0, 0};
-        std::memcpy(&top.q[12], ch, sizeof ch);
-        CKC(cudaMemcpy(c->d_nodes, &top, sizeof top, cudaMemcpyHostToDevice));
-    }
-    if (!gpu_build) {
-        // scene nodes at [1, 1+ns), scene tris at [0, n_scene)
-        std::vector<BvhNode> nodes = c->scene_bvh.nodes;
-        for (auto& d : nodes) {
-            int32_t ch[4];
-            std::memcpy(ch, &d.q[12], sizeof ch);
-            for (int w = 0; w < 2; ++w) if (ch[w] >= 0) ch[w] += 1;
-            std::memcpy(&d.q[12], ch, sizeof ch);
-        }
-        CKC(cudaMemcpy(c->d_nodes + 4, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
-        std::vector<float4> tris((size_t)c->n_scene * 3);
+        CKC(cudaMemcpy(c->d_nodes, scene_q.data(), scene_q.size() * sizeof(QNode), cudaMemcpyHostToDevice));
+        std::vector<float> recs((size_t)c->n_scene * 16);
         for (int64_t s = 0; s < c->n_scene; ++s) {
-            const int32_t src = c->scene_bvh.order[s];
-            const float* v = c->scene.tri_verts.data() + 9 * (size_t)src;
-            const int32_t mat = c->scene.tri_mesh[src];
-            float idf, matf;
-            std::memcpy(&idf, &src, 4); std::memcpy(&matf, &mat, 4);
-            tris[3 * s + 0] = make_float4(v[0], v[1], v[2], idf);
-            tris[3 * s + 1] = make_float4(v[3], v[4], v[5], matf);
-            tris[3 * s + 2] = make_float4(v[6], v[7], v[8], 0.f);
+            const int32_t src = scene2.order[s];
+            make_tri_record(c->scene.tri_verts.data() + 9 * (size_t)src, src, c->scene.tri_mesh[src], recs.data() + 16 * (size_t)s);
         }
-        if (c->n_scene) CKC(cudaMemcpy(c->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        if (c->n_scene) CKC(cudaMemcpy(c->d_tris, recs.data(), recs.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    c->stage_f4 = 4 + 4 * (size_t)c->n_recv_nodes + 3 * (size_t)std::max<int64_t>(1, n_recv);
+    c->stage_f4 = 2 * (size_t)c->n_recv_nodes + 4 * (size_t)std::max<int64_t>(1, n_recv);
     CKC(cudaMallocHost(&c->h_stage, c->stage_f4 * sizeof(float4)));
     CKC(cudaMallocHost(&c->h_counters, 16 * sizeof(unsigned long long)));
 
@@ -625,7 +597,6 @@ int arv2_render(arv2_ctx* c, double* ms)
         CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
         TraceParams p;
         fill_params(c, &p, 0, c->n_rays_total);
-        p.root = 1;                                       // scene sub-tree only
         p.rec_bin = nullptr; p.rec_ear = nullptr; p.rec_energy = nullptr; p.rec_nseg = nullptr;
         CK(cudaEventRecord(c->ev0, c->stream));
         CK(launch_trace(p, c->bands, 1, c->sm_count, c->stream));

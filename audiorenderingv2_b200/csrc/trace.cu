@@ -3,17 +3,22 @@
 // Replaces the OptiX pipeline of the reference (B200 has no RT cores):
 //   __raygen__renderFrame     OR/devicePrograms.cu:192-254  -> trace_kernel (path loop)
 //   optixTrace / GAS traversal OR/devicePrograms.cu:240-251 -> closest_hit (software BVH)
-//   __closesthit__radiance    OR/devicePrograms.cu:62-180   -> shade step in trace_kernel
+//   __closesthit__radiance    OR/devicePrograms.cu:62-180   -> shade_segment
 //   __miss__radiance          OR/devicePrograms.cu:186-190  -> "no hit" branch
 //   fillZeros / addIRs        OR/kernels.cu:77-97,519-536   -> cudaMemsetAsync / finalize_kernel
 //
 // Design: persistent CTAs; every warp keeps 32 paths in flight and refills lanes whose
 // path ended from a warp-local chunk of the seeded ray set (ballot + popc compaction),
-// so no ray state ever goes through HBM.  Receiver deposits are aggregated across the
-// warp (match.any) and accumulated in an fp64 histogram with native RED.F64, which
-// makes the result independent of the deposit order to ~1e-16.
+// so no ray state ever goes through HBM.  The r02 profile showed the tracer bound by the
+// L1 data pipe at one wavefront per lane and load instruction (the whole BVH is L2/L1
+// resident, DRAM idles), so the layouts minimise load INSTRUCTIONS: a binary node with
+// 16-bit quantised child boxes is one 256-bit load, a triangle two (arv2_internal.h).
+// Receiver deposits are aggregated across the warp (match.any) and accumulated in an fp64
+// histogram with native RED.F64, which makes the result independent of the deposit order
+// to ~1e-16.
 #include <climits>
 
+#include "arv2_internal.h"
 #include "arv2_model.cuh"
 #include "trace.cuh"
 
@@ -23,7 +28,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kChunk = 128;          // rays a warp claims per global atomic
-constexpr int kStack = 64;
+constexpr int kStack = kTraversalStack;
 #ifndef ARV2_THREADS
 #define ARV2_THREADS 128
 #endif
@@ -31,15 +36,13 @@ constexpr int kStack = 64;
 #define ARV2_MINB 8
 #endif
 constexpr int kThreads = ARV2_THREADS;
-constexpr int kSentinel = INT_MIN;
+constexpr int kSentinel = INT_MIN;   // "nothing (left) to traverse"
 constexpr int kRerenderThreads = 256;
 constexpr int kRerenderBatch = 12;   // lanes that must hold a candidate before the receiver walk
 
 struct Hit { float t, u, v; int slot, id; };
 
-// 256-bit read-only global load (sm_100+: LDG.E.ENL2.256.CONSTANT).  A divergent gather
-// costs the L1 data pipe one wavefront per load instruction and lane, so a 64 B node is
-// fetched with 2 of these instead of 4 x LDG.128 (profiles/micro/gather.cu: 1.34x).
+// 256-bit read-only global load (sm_100+: LDG.E.ENL2.256.CONSTANT).
 struct __align__(32) F8 { float4 lo, hi; };
 __device__ __forceinline__ F8 ldg256(const float4* p)
 {
@@ -56,76 +59,131 @@ __device__ __forceinline__ float safe_rcp(float d)
     return 1.0f / (fabsf(d) > eps ? d : copysignf(eps, d));
 }
 
-// Closest hit = min (t, global triangle id) over all triangles whose exact test
-// accepts; the BVH only prunes (boxes are padded, comparison is <=).
-__device__ __forceinline__ void closest_hit(const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                            int root, F3 org, F3 dir, float tmax, Hit& h)
+// One half of a packed (lo | hi << 16) word -> 2^23 + q as a float: a single PRMT that
+// drops the 16 bits into the mantissa of 0x4B000000.  sel = 0x7610 (lo half) / 0x7632 (hi).
+__device__ __forceinline__ float qhalf(float word, unsigned sel)
 {
-    const float ix = safe_rcp(dir.x), iy = safe_rcp(dir.y), iz = safe_rcp(dir.z);
-    const float ox = org.x * ix, oy = org.y * iy, oz = org.z * iz;
-    int stack[kStack];
-    int sp = 0;
-    stack[sp++] = kSentinel;
-    int cur = root;
-    h.t = tmax; h.u = 0.f; h.v = 0.f; h.slot = -1; h.id = INT_MAX;
-#ifdef ARV2_STATS
-    int n_inner = 0, n_tri = 0, n_leaf = 0;
-#endif
+    return __uint_as_float(__byte_perm(__float_as_uint(word), 0x4B000000u, sel));
+}
 
-    while (cur != kSentinel) {
-        while (cur >= 0) {
-#ifdef ARV2_STATS
-            n_inner++;
-#endif
-            const F8 na = ldg256(nodes + cur * 4), nb = ldg256(nodes + cur * 4 + 2);
-            const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
-            const float c0lox = fmaf(n0.x, ix, -ox), c0hix = fmaf(n0.y, ix, -ox);
-            const float c0loy = fmaf(n0.z, iy, -oy), c0hiy = fmaf(n0.w, iy, -oy);
-            const float c0loz = fmaf(n2.x, iz, -oz), c0hiz = fmaf(n2.y, iz, -oz);
-            const float c1lox = fmaf(n1.x, ix, -ox), c1hix = fmaf(n1.y, ix, -ox);
-            const float c1loy = fmaf(n1.z, iy, -oy), c1hiy = fmaf(n1.w, iy, -oy);
-            const float c1loz = fmaf(n2.z, iz, -oz), c1hiz = fmaf(n2.w, iz, -oz);
-            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.f));
-            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
-            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.f));
-            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
-            const bool go0 = c0min <= c0max, go1 = c1min <= c1max;
-            const int i0 = __float_as_int(n3.x), i1 = __float_as_int(n3.y);
-            if (!go0 && !go1) {
-                cur = stack[--sp];
-            } else {
-                cur = go0 ? i0 : i1;
-                if (go0 && go1) {
-                    int far = i1;
-                    if (c1min < c0min) { cur = i1; far = i0; }
-                    stack[sp++] = far;
-                }
+// Per-segment, per-tree ray constants: t(plane q) = fma(2^23 + q, a, b) with
+//   a = cell / dir,  b = (origin - org) / dir - 2^23 * a;
+// the near / far plane of each axis is picked by the PRMT selector (sign of dir).
+struct RayGrid {
+    float ax, ay, az, bx, by, bz;
+    unsigned nx, ny, nz;     // near selectors; far = near ^ 0x0022
+    __device__ __forceinline__ void setup(const float* origin, const float* cell, F3 org, F3 dir)
+    {
+        const float ix = safe_rcp(dir.x), iy = safe_rcp(dir.y), iz = safe_rcp(dir.z);
+        ax = cell[0] * ix; ay = cell[1] * iy; az = cell[2] * iz;
+        bx = fmaf(-8388608.f, ax, (origin[0] - org.x) * ix);
+        by = fmaf(-8388608.f, ay, (origin[1] - org.y) * iy);
+        bz = fmaf(-8388608.f, az, (origin[2] - org.z) * iz);
+        nx = ix < 0.f ? 0x7632u : 0x7610u;
+        ny = iy < 0.f ? 0x7632u : 0x7610u;
+        nz = iz < 0.f ? 0x7632u : 0x7610u;
+    }
+};
+
+// Traversal of one tree.  Closest hit = min (t, global triangle id) over all triangles
+// whose exact test accepts; the tree only prunes (boxes are padded and quantised outwards,
+// comparisons are <=), so any tree gives the same answer.  The stack is a separate local
+// array on purpose: inside a struct it would drag the scalars into local memory with it.
+struct Traversal {
+    int sp, cur;
+    Hit h;
+
+    __device__ __forceinline__ void reset(float tmax) { h.t = tmax; h.u = 0.f; h.v = 0.f; h.slot = -1; h.id = INT_MAX; cur = kSentinel; sp = 0; }
+    __device__ __forceinline__ void enter(int* stack, int root) { stack[0] = kSentinel; sp = 1; cur = root; }
+    __device__ __forceinline__ bool at_inner() const { return cur >= 0; }
+    __device__ __forceinline__ bool at_leaf() const { return cur < 0 && cur != kSentinel; }
+    __device__ __forceinline__ bool finished() const { return cur == kSentinel; }
+
+    __device__ __forceinline__ void step_inner(int* stack, const float4* __restrict__ nodes, const RayGrid& g)
+    {
+        const F8 N = ldg256(nodes + cur * 2);
+        const unsigned fx = g.nx ^ 0x0022u, fy = g.ny ^ 0x0022u, fz = g.nz ^ 0x0022u;
+        const float n0 = fmaxf(fmaxf(fmaf(qhalf(N.lo.x, g.nx), g.ax, g.bx), fmaf(qhalf(N.lo.y, g.ny), g.ay, g.by)),
+                               fmaxf(fmaf(qhalf(N.lo.z, g.nz), g.az, g.bz), 0.f));
+        const float f0 = fminf(fminf(fmaf(qhalf(N.lo.x, fx), g.ax, g.bx), fmaf(qhalf(N.lo.y, fy), g.ay, g.by)),
+                               fminf(fmaf(qhalf(N.lo.z, fz), g.az, g.bz), h.t));
+        const float n1 = fmaxf(fmaxf(fmaf(qhalf(N.lo.w, g.nx), g.ax, g.bx), fmaf(qhalf(N.hi.x, g.ny), g.ay, g.by)),
+                               fmaxf(fmaf(qhalf(N.hi.y, g.nz), g.az, g.bz), 0.f));
+        const float f1 = fminf(fminf(fmaf(qhalf(N.lo.w, fx), g.ax, g.bx), fmaf(qhalf(N.hi.x, fy), g.ay, g.by)),
+                               fminf(fmaf(qhalf(N.hi.y, fz), g.az, g.bz), h.t));
+        const bool go0 = n0 <= f0, go1 = n1 <= f1;
+        const int i0 = __float_as_int(N.hi.z), i1 = __float_as_int(N.hi.w);
+        if (!go0 && !go1) {
+            cur = stack[--sp];
+        } else {
+            cur = go0 ? i0 : i1;
+            if (go0 && go1) {
+                int far = i1;
+                if (n1 < n0) { cur = i1; far = i0; }
+                stack[sp++] = far;
             }
         }
-        if (cur == kSentinel) break;
-        // leaf
+    }
+
+    // one leaf: exact tests of its <= 4 triangles
+    __device__ __forceinline__ void step_leaf(int* stack, const float4* __restrict__ tris, F3 org, F3 dir)
+    {
         const int code = ~cur;
         const int first = code >> 3;
         const int cnt = (code & 7) + 1;
-#ifdef ARV2_STATS
-        n_leaf++; n_tri += cnt;
-#endif
         for (int i = 0; i < cnt; ++i) {
             const int slot = first + i;
-            const float4 a = __ldg(tris + slot * 3 + 0);
-            const float4 b = __ldg(tris + slot * 3 + 1);
-            const float4 c = __ldg(tris + slot * 3 + 2);
+            const F8 A = ldg256(tris + slot * 4), B = ldg256(tris + slot * 4 + 2);
             float t, u, v;
-            if (tri_test(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), org, dir, &t, &u, &v)) {
-                const int id = __float_as_int(a.w);
+            if (tri_test(f3(A.lo.x, A.lo.y, A.lo.z), f3(A.hi.x, A.hi.y, A.hi.z), f3(B.lo.x, B.lo.y, B.lo.z), org, dir, &t, &u, &v)) {
+                const int id = __float_as_int(A.lo.w);
                 if (t < h.t || (t == h.t && id < h.id)) { h.t = t; h.u = u; h.v = v; h.slot = slot; h.id = id; }
             }
         }
         cur = stack[--sp];
     }
-#ifdef ARV2_STATS
-    h.id = n_inner | (n_leaf << 10) | (n_tri << 20);
-#endif
+
+    __device__ __forceinline__ void walk(int* stack, const float4* __restrict__ nodes, const float4* __restrict__ tris, int root,
+                                         const RayGrid& g, F3 org, F3 dir)
+    {
+        enter(stack, root);
+        while (!finished()) {
+            while (at_inner()) step_inner(stack, nodes, g);
+            if (finished()) break;
+            step_leaf(stack, tris, org, dir);
+        }
+    }
+};
+
+// Does the segment org + t*dir, 0 <= t <= tmax, enter the ball that contains the placed
+// receiver mesh?  Exact-conservative (the radius is padded on the host).
+__device__ __forceinline__ bool enters_receiver_ball(const TraceParams& p, F3 org, F3 dir, float tmax)
+{
+    const float ocx = org.x - p.center[0], ocy = org.y - p.center[1], ocz = org.z - p.center[2];
+    const float b = ocx * dir.x + ocy * dir.y + ocz * dir.z;
+    const float c = ocx * ocx + ocy * ocy + ocz * ocz - p.recv_radius * p.recv_radius;
+    const float d2 = dir.x * dir.x + dir.y * dir.y + dir.z * dir.z;
+    const float disc = b * b - d2 * c;
+    if (!(disc >= 0.f)) return false;
+    const float sq = sqrtf(disc);
+    return (-b + sq) >= 0.f && (-b - sq) <= tmax * d2;
+}
+
+// optixTrace: closest hit over the scene tree, then (full trace only) over the receiver
+// tree when the segment can reach it.
+template <int MODE>
+__device__ __forceinline__ void closest_hit(const TraceParams& p, int* stack, Traversal& tr, F3 org, F3 dir)
+{
+    tr.reset(1e20f);
+    RayGrid g;
+    if (p.has_scene) {
+        g.setup(p.sg_origin, p.sg_cell, org, dir);
+        tr.walk(stack, p.nodes, p.tris, p.scene_root, g, org, dir);
+    }
+    if (MODE == 0 && p.has_recv && enters_receiver_ball(p, org, dir, tr.h.t)) {
+        g.setup(p.rg_origin, p.rg_cell, org, dir);
+        tr.walk(stack, p.nodes, p.tris, p.recv_root, g, org, dir);
+    }
 }
 
 // Warp-aggregated deposit into the fp64 histogram (OR/devicePrograms.cu:128-170).
@@ -186,7 +244,7 @@ __device__ __forceinline__ int receiver_hit(const TraceParams& p, F3 pt, F3 dir,
     return __float2int_rz(roundf(__fmul_rn(elapsed, p.fs)));
 }
 
-// Hit point and path length (OR/devicePrograms.cu:79-83).
+// Hit point (OR/devicePrograms.cu:79-81).
 __device__ __forceinline__ F3 hit_point(F3 p1, F3 p2, F3 p3, float u, float v)
 {
     const float w = __fsub_rn(__fsub_rn(1.0f, u), v);
@@ -195,384 +253,183 @@ __device__ __forceinline__ F3 hit_point(F3 p1, F3 p2, F3 p3, float u, float v)
               __fmaf_rn(v, p3.z, __fmaf_rn(u, p2.z, __fmul_rn(w, p1.z))));
 }
 
+// Per-lane path state (struct PRD, OR/PRD.h:5-14, kept in registers).
+template <int NB>
+struct Path {
+    long long ray;
+    F3 org, dir;
+    float energy[NB];
+    float dist;
+    int depth, nseg;
+};
+
+struct Deposit { bool dep; int bin, ear, primary; };
+
+// __closesthit__radiance / __miss__radiance for a finished segment.  Returns true when the
+// path ends (miss or receiver); a wall hit bounces the path in place.
+template <int NB, int MODE>
+__device__ __forceinline__ bool shade_segment(const TraceParams& p, Path<NB>& s, const Hit& h, Deposit& d)
+{
+    if (MODE == 1) p.pc_org_t[(size_t)(s.nseg - 1) * (size_t)p.pc_stride + (size_t)s.ray] = make_float4(s.org.x, s.org.y, s.org.z, h.t);
+    if (h.slot < 0) return true;                                                     // miss :186-190
+    const F8 A = ldg256(p.tris + h.slot * 4), B = ldg256(p.tris + h.slot * 4 + 2);
+    const F3 p1 = f3(A.lo.x, A.lo.y, A.lo.z), p2 = f3(A.hi.x, A.hi.y, A.hi.z), p3 = f3(B.lo.x, B.lo.y, B.lo.z);
+    const int mat = __float_as_int(A.hi.w);
+    const F3 pt = hit_point(p1, p2, p3, h.u, h.v);
+    const F3 dp = sub3(pt, s.org);
+    s.dist = __fadd_rn(s.dist, __fsqrt_rn(dot3(dp, dp)));                            // :83
+    if (mat < 0) {
+        d.bin = receiver_hit<NB>(p, pt, s.dir, s.dist, s.energy);
+        d.ear = (mat == -1) ? 1 : 2;
+        d.primary = (mat == -1) ? 0 : 1;
+        d.dep = d.bin >= 0 && d.bin < p.ir_len;
+        return true;                                                                  // :147,:169
+    }
+    const F3 ng = f3(B.lo.w, B.hi.x, B.hi.y);                                        // :75-77, precomputed on the host
+    bool diffuse = false;
+    uint32_t r[4];
+    if (p.any_scatter) {
+        const float sc = __ldg(p.scattering + mat);
+        if (sc > 0.f) {
+            philox4x32(p.seed, (uint64_t)(p.ray_begin + s.ray), (uint32_t)s.depth, 1u, r);
+            diffuse = __fmul_rn((float)(r[0] >> 8), 0x1p-24f) < sc;
+        }
+    }
+    if (diffuse) {
+        s.dir = lambert_direction(r, s.dir, ng);
+    } else {
+        const float k = __fmul_rn(2.0f, dot3(s.dir, ng));                            // :173
+        s.dir = f3(__fmaf_rn(-k, ng.x, s.dir.x), __fmaf_rn(-k, ng.y, s.dir.y), __fmaf_rn(-k, ng.z, s.dir.z));
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) s.energy[b] = __fmul_rn(s.energy[b], __ldg(p.keep + mat * NB + b));    // :174
+    s.depth++;                                                                        // :175
+    s.org = f3(__fmaf_rn(1e-3f, s.dir.x, pt.x), __fmaf_rn(1e-3f, s.dir.y, pt.y), __fmaf_rn(1e-3f, s.dir.z, pt.z)); // :179
+    return false;
+}
+
+// loop guard of __raygen__renderFrame (:230, :233-236)
+template <int NB>
+__device__ __forceinline__ bool path_goes_on(const TraceParams& p, const Path<NB>& s)
+{
+    float emax = s.energy[0];
+#pragma unroll
+    for (int b = 1; b < NB; ++b) emax = fmaxf(emax, s.energy[b]);
+    const bool zero_dir = !(s.dir.x != 0.f || s.dir.y != 0.f || s.dir.z != 0.f);
+    return !zero_dir && s.dist < p.dist_thr && emax > p.energy_thres && (unsigned)s.depth < p.max_bounces;
+}
+
+template <int NB, int MODE>
+__device__ __forceinline__ void end_path(const TraceParams& p, const Path<NB>& s, const Deposit& d, unsigned long long& segs)
+{
+    if (p.rec_bin) p.rec_bin[s.ray] = d.bin;
+    if (p.rec_ear) p.rec_ear[s.ray] = d.ear;
+    if (p.rec_nseg) p.rec_nseg[s.ray] = s.nseg;
+    if (p.rec_energy) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) p.rec_energy[s.ray * NB + b] = d.ear ? s.energy[b] : 0.f;
+    }
+    if (MODE == 1) p.pc_nseg[s.ray] = s.nseg;
+    segs += (unsigned long long)s.nseg;
+}
+
+template <int NB>
+__device__ __forceinline__ void new_path(const TraceParams& p, Path<NB>& s, long long ray)
+{
+    s.ray = ray;
+    s.org = f3(p.emitter[0], p.emitter[1], p.emitter[2]);              // :210
+    s.dir = emit_direction(p.seed, (uint64_t)(p.ray_begin + ray));     // :216-224
+#pragma unroll
+    for (int b = 0; b < NB; ++b) s.energy[b] = p.energy0;              // :208
+    s.dist = 0.f; s.depth = 0; s.nseg = 0;                             // :209,:211
+}
+
+template <int NB, int MODE>
+__device__ __forceinline__ void begin_segment(const TraceParams& p, Path<NB>& s)
+{
+    if (MODE == 1) {
+        const size_t ci = (size_t)s.nseg * (size_t)p.pc_stride + (size_t)s.ray;
+        p.pc_dir_d[ci] = make_float4(s.dir.x, s.dir.y, s.dir.z, s.dist);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) p.pc_energy[ci * NB + b] = s.energy[b];
+    }
+    s.nseg++;
+}
+
+// Warp-level refill of the lanes in `want` from the warp's chunk of the ray set
+// (ballot / popc compaction).  Lanes that got a ray return true.
+template <int NB>
+__device__ __forceinline__ bool refill(const TraceParams& p, bool want, long long& chunk_next, long long& chunk_end,
+                                       bool& exhausted, Path<NB>& s)
+{
+    const int lane = threadIdx.x & 31;
+    bool got = false;
+    unsigned need = __ballot_sync(FULL, want && !exhausted);
+    while (need) {
+        if (chunk_next >= chunk_end) {
+            unsigned long long b = 0;
+            if (lane == 0) b = atomicAdd(p.counters, (unsigned long long)kChunk);
+            b = __shfl_sync(FULL, b, 0);
+            chunk_next = (long long)b;
+            chunk_end = min((long long)b + kChunk, p.n_rays);
+            if (chunk_next >= chunk_end) {
+                if (want && !got) exhausted = true;
+                break;
+            }
+        }
+        const int avail = (int)min((long long)32, chunk_end - chunk_next);
+        const int rank = __popc(need & ((1u << lane) - 1u));
+        if (((need >> lane) & 1u) && rank < avail) {
+            new_path<NB>(p, s, chunk_next + rank);
+            got = true;
+        }
+        chunk_next += min(__popc(need), avail);
+        need = __ballot_sync(FULL, want && !got && !exhausted);
+    }
+    return got;
+}
+
+// ---------------------------------------------------------------------------------------
+// trace_kernel: while-while traversal, all lanes of a warp advance segment by segment.
 template <int NB, int MODE>
 __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceParams p)
 {
     const int lane = threadIdx.x & 31;
     long long chunk_next = 0, chunk_end = 0;      // warp-uniform
     bool have = false, exhausted = false;
-    long long ray = 0;
-    F3 org = f3(0, 0, 0), dir = f3(0, 0, 0);
-    float energy[NB];
-    float dist = 0.f;
-    int depth = 0, nseg = 0;
+    Path<NB> s;
+    s.ray = 0; s.org = f3(0, 0, 0); s.dir = f3(0, 0, 0); s.dist = 0.f; s.depth = 0; s.nseg = 0;
     unsigned long long segs = 0;
+    Traversal tr;
+    int stack[kStack];
 
     for (;;) {
-        // ---- refill idle lanes from the warp's chunk (ballot/popc compaction)
-        unsigned need = __ballot_sync(FULL, !have && !exhausted);
-        while (need) {
-            if (chunk_next >= chunk_end) {
-                unsigned long long b = 0;
-                if (lane == 0) b = atomicAdd(p.counters, (unsigned long long)kChunk);
-                b = __shfl_sync(FULL, b, 0);
-                chunk_next = (long long)b;
-                chunk_end = min((long long)b + kChunk, p.n_rays);
-                if (chunk_next >= chunk_end) {
-                    if (!have) exhausted = true;
-                    break;
-                }
-            }
-            const int avail = (int)min((long long)32, chunk_end - chunk_next);
-            const int rank = __popc(need & ((1u << lane) - 1u));
-            if (((need >> lane) & 1u) && rank < avail) {
-                ray = chunk_next + rank;
-                have = true;
-                org = f3(p.emitter[0], p.emitter[1], p.emitter[2]);          // :210
-                dir = emit_direction(p.seed, (uint64_t)(p.ray_begin + ray)); // :216-224
-#pragma unroll
-                for (int b = 0; b < NB; ++b) energy[b] = p.energy0;          // :208
-                dist = 0.f; depth = 0; nseg = 0;                             // :209,:211
-            }
-            chunk_next += min(__popc(need), avail);
-            need = __ballot_sync(FULL, !have && !exhausted);
-        }
+        if (refill<NB>(p, !have, chunk_next, chunk_end, exhausted, s)) have = true;
         if (!__any_sync(FULL, have)) break;
 
-        bool ended = false, dep = false;
-        int bin = -1, ear = 0, primary = 0;
+        bool ended = false;
+        Deposit d; d.dep = false; d.bin = -1; d.ear = 0; d.primary = 0;
         if (have) {
-            float emax = energy[0];
-#pragma unroll
-            for (int b = 1; b < NB; ++b) emax = fmaxf(emax, energy[b]);
-            const bool zero_dir = !(dir.x != 0.f || dir.y != 0.f || dir.z != 0.f);            // :230
-            if (zero_dir || !(dist < p.dist_thr && emax > p.energy_thres && (unsigned)depth < p.max_bounces)) {
-                ended = true;                                                                   // :233-236
+            if (!path_goes_on<NB>(p, s)) {
+                ended = true;                                                         // :233-236
             } else {
-                const size_t ci = (size_t)nseg * (size_t)p.pc_stride + (size_t)ray;
-                if (MODE == 1) {
-                    p.pc_dir_d[ci] = make_float4(dir.x, dir.y, dir.z, dist);
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) p.pc_energy[ci * NB + b] = energy[b];
-                }
-                nseg++;
-                Hit h;
-                closest_hit(p.nodes, p.tris, p.root, org, dir, 1e20f, h);
-                if (MODE == 1) p.pc_org_t[ci] = make_float4(org.x, org.y, org.z, h.t);
-#ifdef ARV2_STATS
-                {
-                    // counters[2..]: sum inner, sum warp-max inner * lanes, sum leaf, sum max leaf, sum tri, sum max tri, segments, warp-rounds*32
-                    const unsigned am = __activemask();
-                    const int ni = h.id & 1023, nl = (h.id >> 10) & 1023, nt = (h.id >> 20) & 1023;
-                    const int mi = __reduce_max_sync(am, ni), ml = __reduce_max_sync(am, nl), mt = __reduce_max_sync(am, nt);
-                    const int si = __reduce_add_sync(am, ni), sl = __reduce_add_sync(am, nl), st = __reduce_add_sync(am, nt);
-                    if ((threadIdx.x & 31) == __ffs(am) - 1) {
-                        atomicAdd(p.counters + 2, (unsigned long long)si); atomicAdd(p.counters + 3, (unsigned long long)mi * 32);
-                        atomicAdd(p.counters + 4, (unsigned long long)sl); atomicAdd(p.counters + 5, (unsigned long long)ml * 32);
-                        atomicAdd(p.counters + 6, (unsigned long long)st); atomicAdd(p.counters + 7, (unsigned long long)mt * 32);
-                        atomicAdd(p.counters + 8, (unsigned long long)__popc(am)); atomicAdd(p.counters + 9, 32ull);
-                    }
-                }
-#endif
-                if (h.slot < 0) {
-                    ended = true;                                                               // miss :186-190
-                } else {
-                    const float4 a = __ldg(p.tris + h.slot * 3 + 0);
-                    const float4 b4 = __ldg(p.tris + h.slot * 3 + 1);
-                    const float4 c4 = __ldg(p.tris + h.slot * 3 + 2);
-                    const F3 p1 = f3(a.x, a.y, a.z), p2 = f3(b4.x, b4.y, b4.z), p3 = f3(c4.x, c4.y, c4.z);
-                    const int mat = __float_as_int(b4.w);
-                    const F3 pt = hit_point(p1, p2, p3, h.u, h.v);
-                    const F3 dp = sub3(pt, org);
-                    dist = __fadd_rn(dist, __fsqrt_rn(dot3(dp, dp)));                           // :83
-                    if (mat < 0) {
-                        bin = receiver_hit<NB>(p, pt, dir, dist, energy);
-                        ear = (mat == -1) ? 1 : 2;
-                        primary = (mat == -1) ? 0 : 1;
-                        dep = bin >= 0 && bin < p.ir_len;
-                        ended = true;                                                           // :147,:169
-                    } else {
-                        // :75-77  Ng = normalize(cross(P2-P1, P3-P1))
-                        const F3 nc = cross3(sub3(p2, p1), sub3(p3, p1));
-                        const float ninv = __fdiv_rn(1.0f, __fsqrt_rn(dot3(nc, nc)));
-                        const F3 ng = f3(__fmul_rn(nc.x, ninv), __fmul_rn(nc.y, ninv), __fmul_rn(nc.z, ninv));
-                        bool diffuse = false;
-                        uint32_t r[4];
-                        if (p.any_scatter) {
-                            const float sc = __ldg(p.scattering + mat);
-                            if (sc > 0.f) {
-                                philox4x32(p.seed, (uint64_t)(p.ray_begin + ray), (uint32_t)depth, 1u, r);
-                                diffuse = __fmul_rn((float)(r[0] >> 8), 0x1p-24f) < sc;
-                            }
-                        }
-                        if (diffuse) {
-                            dir = lambert_direction(r, dir, ng);
-                        } else {
-                            const float k = __fmul_rn(2.0f, dot3(dir, ng));                     // :173
-                            dir = f3(__fmaf_rn(-k, ng.x, dir.x), __fmaf_rn(-k, ng.y, dir.y), __fmaf_rn(-k, ng.z, dir.z));
-                        }
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) energy[b] = __fmul_rn(energy[b], __ldg(p.keep + mat * NB + b)); // :174
-                        depth++;                                                                // :175
-                        org = f3(__fmaf_rn(1e-3f, dir.x, pt.x), __fmaf_rn(1e-3f, dir.y, pt.y), __fmaf_rn(1e-3f, dir.z, pt.z)); // :179
-                    }
-                }
+                begin_segment<NB, MODE>(p, s);
+                closest_hit<MODE>(p, stack, tr, s.org, s.dir);
+                ended = shade_segment<NB, MODE>(p, s, tr.h, d);
             }
         }
-        if (MODE == 0) deposit_warp<NB>(p, dep, bin, primary, energy);
+        if (MODE == 0) deposit_warp<NB>(p, d.dep, d.bin, d.primary, s.energy);
         if (ended) {
-            if (p.rec_bin) p.rec_bin[ray] = bin;
-            if (p.rec_ear) p.rec_ear[ray] = ear;
-            if (p.rec_nseg) p.rec_nseg[ray] = nseg;
-            if (p.rec_energy) {
-#pragma unroll
-                for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = ear ? energy[b] : 0.f;
-            }
-            if (MODE == 1) p.pc_nseg[ray] = nseg;
-            segs += (unsigned long long)nseg;
+            end_path<NB, MODE>(p, s, d, segs);
             have = false;
         }
     }
-    // one atomic per warp for the segment counter
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
     if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
 }
 
 // ---------------------------------------------------------------------------------------
-// trace2_kernel: the same path tracer as trace_kernel with the lanes of a warp decoupled.
-// r01/r02 profiles: per-segment node-visit counts vary so much inside a warp (sum / (32 x max)
-// = 49 %) that the inner loop of trace_kernel runs at 12 of 32 lanes.  Here a lane that has
-// finished its segment parks (cur == kSentinel) while the others keep traversing; three
-// warp-uniform phases are scheduled by ballots:
-//   A  shade + deposit + refill + start the next segment -- when >= kTA lanes are parked
-//   L  one leaf (<= 4 triangle tests) per lane           -- when >= kTL lanes stand at a leaf
-//   I  up to kBurst inner-node steps                      -- otherwise
-// so every phase runs with many lanes and nobody waits for the slowest traversal.
-#ifndef ARV2_TA
-#define ARV2_TA 12
-#endif
-#ifndef ARV2_TL
-#define ARV2_TL 8
-#endif
-#ifndef ARV2_BURST
-#define ARV2_BURST 4
-#endif
-template <int NB, int MODE>
-__global__ void __launch_bounds__(kThreads, ARV2_MINB) trace2_kernel(const TraceParams p)
-{
-    const int lane = threadIdx.x & 31;
-    long long chunk_next = 0, chunk_end = 0;      // warp-uniform
-    bool have = false, exhausted = false, pending = false;
-    long long ray = 0;
-    F3 org = f3(0, 0, 0), dir = f3(0, 0, 0);
-    float energy[NB];
-    float dist = 0.f;
-    int depth = 0, nseg = 0;
-    unsigned long long segs = 0;
-    // traversal state of the segment in flight
-    int stack[kStack];
-    int sp = 0, cur = kSentinel;
-    float ix = 0.f, iy = 0.f, iz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
-    Hit h;
-    h.t = 1e20f; h.u = 0.f; h.v = 0.f; h.slot = -1; h.id = INT_MAX;
-    const float4* __restrict__ nodes = p.nodes;
-    const float4* __restrict__ tris = p.tris;
-
-    for (;;) {
-        const bool at_inner = cur >= 0;
-        const bool at_leaf = cur < 0 && cur != kSentinel;
-        const bool parked = cur == kSentinel && !exhausted;
-        const unsigned inner_m = __ballot_sync(FULL, at_inner);
-        const unsigned leaf_m = __ballot_sync(FULL, at_leaf);
-        const unsigned park_m = __ballot_sync(FULL, parked);
-        if ((inner_m | leaf_m | park_m) == 0) break;
-
-        if (park_m != 0 && (__popc(park_m) >= ARV2_TA || (inner_m | leaf_m) == 0)) {
-            // ======================= phase A: shade, deposit, refill, start next segment
-            bool ended = false, dep = false;
-            int bin = -1, ear = 0, primary = 0;
-            if (parked && have && pending) {
-                pending = false;
-                if (MODE == 1) p.pc_org_t[(size_t)(nseg - 1) * (size_t)p.pc_stride + (size_t)ray] = make_float4(org.x, org.y, org.z, h.t);
-                if (h.slot < 0) {
-                    ended = true;                                                               // miss :186-190
-                } else {
-                    const float4 a = __ldg(tris + h.slot * 3 + 0);
-                    const float4 b4 = __ldg(tris + h.slot * 3 + 1);
-                    const float4 c4 = __ldg(tris + h.slot * 3 + 2);
-                    const F3 p1 = f3(a.x, a.y, a.z), p2 = f3(b4.x, b4.y, b4.z), p3 = f3(c4.x, c4.y, c4.z);
-                    const int mat = __float_as_int(b4.w);
-                    const F3 pt = hit_point(p1, p2, p3, h.u, h.v);
-                    const F3 dp = sub3(pt, org);
-                    dist = __fadd_rn(dist, __fsqrt_rn(dot3(dp, dp)));                           // :83
-                    if (mat < 0) {
-                        bin = receiver_hit<NB>(p, pt, dir, dist, energy);
-                        ear = (mat == -1) ? 1 : 2;
-                        primary = (mat == -1) ? 0 : 1;
-                        dep = bin >= 0 && bin < p.ir_len;
-                        ended = true;                                                           // :147,:169
-                    } else {
-                        const F3 nc = cross3(sub3(p2, p1), sub3(p3, p1));                       // :75-77
-                        const float ninv = __fdiv_rn(1.0f, __fsqrt_rn(dot3(nc, nc)));
-                        const F3 ng = f3(__fmul_rn(nc.x, ninv), __fmul_rn(nc.y, ninv), __fmul_rn(nc.z, ninv));
-                        bool diffuse = false;
-                        uint32_t r[4];
-                        if (p.any_scatter) {
-                            const float sc = __ldg(p.scattering + mat);
-                            if (sc > 0.f) {
-                                philox4x32(p.seed, (uint64_t)(p.ray_begin + ray), (uint32_t)depth, 1u, r);
-                                diffuse = __fmul_rn((float)(r[0] >> 8), 0x1p-24f) < sc;
-                            }
-                        }
-                        if (diffuse) {
-                            dir = lambert_direction(r, dir, ng);
-                        } else {
-                            const float k = __fmul_rn(2.0f, dot3(dir, ng));                     // :173
-                            dir = f3(__fmaf_rn(-k, ng.x, dir.x), __fmaf_rn(-k, ng.y, dir.y), __fmaf_rn(-k, ng.z, dir.z));
-                        }
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) energy[b] = __fmul_rn(energy[b], __ldg(p.keep + mat * NB + b)); // :174
-                        depth++;                                                                // :175
-                        org = f3(__fmaf_rn(1e-3f, dir.x, pt.x), __fmaf_rn(1e-3f, dir.y, pt.y), __fmaf_rn(1e-3f, dir.z, pt.z)); // :179
-                    }
-                }
-            }
-            if (MODE == 0) deposit_warp<NB>(p, dep, bin, primary, energy);
-
-            // loop guard for the paths that go on (:233-236)
-            if (parked && have && !ended) {
-                float emax = energy[0];
-#pragma unroll
-                for (int b = 1; b < NB; ++b) emax = fmaxf(emax, energy[b]);
-                if (!(dist < p.dist_thr && emax > p.energy_thres && (unsigned)depth < p.max_bounces)) ended = true;
-            }
-            if (parked && have && ended) {
-                if (p.rec_bin) p.rec_bin[ray] = bin;
-                if (p.rec_ear) p.rec_ear[ray] = ear;
-                if (p.rec_nseg) p.rec_nseg[ray] = nseg;
-                if (p.rec_energy) {
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = ear ? energy[b] : 0.f;
-                }
-                if (MODE == 1) p.pc_nseg[ray] = nseg;
-                segs += (unsigned long long)nseg;
-                have = false;
-            }
-            // refill parked lanes without a path from the warp's chunk (ballot/popc compaction)
-            unsigned need = __ballot_sync(FULL, parked && !have);
-            while (need) {
-                if (chunk_next >= chunk_end) {
-                    unsigned long long b = 0;
-                    if (lane == 0) b = atomicAdd(p.counters, (unsigned long long)kChunk);
-                    b = __shfl_sync(FULL, b, 0);
-                    chunk_next = (long long)b;
-                    chunk_end = min((long long)b + kChunk, p.n_rays);
-                    if (chunk_next >= chunk_end) {
-                        if (parked && !have) exhausted = true;
-                        break;
-                    }
-                }
-                const int avail = (int)min((long long)32, chunk_end - chunk_next);
-                const int rank = __popc(need & ((1u << lane) - 1u));
-                if (((need >> lane) & 1u) && rank < avail) {
-                    ray = chunk_next + rank;
-                    have = true;
-                    org = f3(p.emitter[0], p.emitter[1], p.emitter[2]);          // :210
-                    dir = emit_direction(p.seed, (uint64_t)(p.ray_begin + ray)); // :216-224
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) energy[b] = p.energy0;          // :208
-                    dist = 0.f; depth = 0; nseg = 0;                             // :209,:211
-                    // a fresh path can only fail the guard through its parameters (or a zero direction, :230)
-                    const bool zero_dir = !(dir.x != 0.f || dir.y != 0.f || dir.z != 0.f);
-                    if (zero_dir || !(0.f < p.dist_thr && p.energy0 > p.energy_thres && 0u < p.max_bounces)) {
-                        if (p.rec_bin) p.rec_bin[ray] = -1;
-                        if (p.rec_ear) p.rec_ear[ray] = 0;
-                        if (p.rec_nseg) p.rec_nseg[ray] = 0;
-                        if (p.rec_energy) {
-#pragma unroll
-                            for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = 0.f;
-                        }
-                        if (MODE == 1) p.pc_nseg[ray] = 0;
-                        have = false;                                            // picks another ray in the next round
-                    }
-                }
-                chunk_next += min(__popc(need), avail);
-                need = __ballot_sync(FULL, parked && !have && !exhausted);
-            }
-            // start the next segment
-            if (parked && have) {
-                if (MODE == 1) {
-                    const size_t ci = (size_t)nseg * (size_t)p.pc_stride + (size_t)ray;
-                    p.pc_dir_d[ci] = make_float4(dir.x, dir.y, dir.z, dist);
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) p.pc_energy[ci * NB + b] = energy[b];
-                }
-                nseg++;
-                ix = safe_rcp(dir.x); iy = safe_rcp(dir.y); iz = safe_rcp(dir.z);
-                ox = org.x * ix; oy = org.y * iy; oz = org.z * iz;
-                stack[0] = kSentinel; sp = 1;
-                cur = p.root;
-                h.t = 1e20f; h.u = 0.f; h.v = 0.f; h.slot = -1; h.id = INT_MAX;
-                pending = true;
-            }
-        } else if (leaf_m != 0 && (__popc(leaf_m) >= ARV2_TL || inner_m == 0)) {
-            // ======================= phase L: one leaf per lane
-            if (at_leaf) {
-                const int code = ~cur;
-                const int first = code >> 3;
-                const int cnt = (code & 7) + 1;
-                for (int i = 0; i < cnt; ++i) {
-                    const int slot = first + i;
-                    const float4 a = __ldg(tris + slot * 3 + 0);
-                    const float4 b = __ldg(tris + slot * 3 + 1);
-                    const float4 c = __ldg(tris + slot * 3 + 2);
-                    float t, u, v;
-                    if (tri_test(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), org, dir, &t, &u, &v)) {
-                        const int id = __float_as_int(a.w);
-                        if (t < h.t || (t == h.t && id < h.id)) { h.t = t; h.u = u; h.v = v; h.slot = slot; h.id = id; }
-                    }
-                }
-                cur = stack[--sp];
-            }
-        } else {
-            // ======================= phase I: a burst of inner-node steps
-#pragma unroll 1
-            for (int k = 0; k < ARV2_BURST; ++k) {
-                if (cur >= 0) {
-                    const F8 na = ldg256(nodes + cur * 4), nb = ldg256(nodes + cur * 4 + 2);
-                    const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
-                    const float c0lox = fmaf(n0.x, ix, -ox), c0hix = fmaf(n0.y, ix, -ox);
-                    const float c0loy = fmaf(n0.z, iy, -oy), c0hiy = fmaf(n0.w, iy, -oy);
-                    const float c0loz = fmaf(n2.x, iz, -oz), c0hiz = fmaf(n2.y, iz, -oz);
-                    const float c1lox = fmaf(n1.x, ix, -ox), c1hix = fmaf(n1.y, ix, -ox);
-                    const float c1loy = fmaf(n1.z, iy, -oy), c1hiy = fmaf(n1.w, iy, -oy);
-                    const float c1loz = fmaf(n2.z, iz, -oz), c1hiz = fmaf(n2.w, iz, -oz);
-                    const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.f));
-                    const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
-                    const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.f));
-                    const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
-                    const bool go0 = c0min <= c0max, go1 = c1min <= c1max;
-                    const int i0 = __float_as_int(n3.x), i1 = __float_as_int(n3.y);
-                    if (!go0 && !go1) {
-                        cur = stack[--sp];
-                    } else {
-                        cur = go0 ? i0 : i1;
-                        if (go0 && go1) {
-                            int far = i1;
-                            if (c1min < c0min) { cur = i1; far = i0; }
-                            stack[sp++] = far;
-                        }
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
-    if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
-}
-
 // Receiver move: walk each ray's cached receiver-independent segments in order and
 // deposit at the first one the receiver intercepts before the wall (t_recv < t_wall;
 // ties go to the scene because scene triangle ids are lower).  One thread per ray,
@@ -580,15 +437,13 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace2_kernel(const Trace
 // A segment is first tested against the receiver's bounding ball (a few FMAs, exact-
 // conservative); lanes whose segment passes park it and keep waiting until enough lanes of
 // the warp hold a candidate (or nobody is scanning), then those lanes walk the receiver
-// sub-tree together -- the r01 profile had this traversal running at 2.9 of 32 lanes.
+// tree together -- the r01 profile had this traversal running at 2.9 of 32 lanes.
 template <int NB>
 __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceParams p)
 {
     const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = ray < p.n_rays;
     const int n = valid ? p.pc_nseg[ray] : 0;
-    const F3 ctr = f3(p.center[0], p.center[1], p.center[2]);
-    const float r2 = p.recv_radius * p.recv_radius;
     int k = 0;
     bool done = n == 0, cand = false;
     float4 ot = make_float4(0, 0, 0, 0), dd = make_float4(0, 0, 0, 0);
@@ -596,6 +451,8 @@ __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceP
     float energy[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) energy[b] = 0.f;
+    Traversal tr;
+    int stack[kStack];
     for (;;) {
         // ---- scan: advance to the next segment that enters the bounding ball
         if (!done && !cand) {
@@ -604,18 +461,7 @@ __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceP
                 const size_t ci = (size_t)k * (size_t)p.pc_stride + (size_t)ray;
                 ot = __ldcs(p.pc_org_t + ci);
                 dd = __ldcs(p.pc_dir_d + ci);
-                const float ocx = ot.x - ctr.x, ocy = ot.y - ctr.y, ocz = ot.z - ctr.z;
-                const float b = ocx * dd.x + ocy * dd.y + ocz * dd.z;
-                const float c = ocx * ocx + ocy * ocy + ocz * ocz - r2;
-                const float d2 = dd.x * dd.x + dd.y * dd.y + dd.z * dd.z;
-                const float disc = b * b - d2 * c;
-                // enters the ball at t0 = (-b - sqrt(disc))/d2, leaves at t1; needs t1 >= 0 and t0 <= t_wall
-                bool pass = false;
-                if (disc >= 0.f) {
-                    const float sq = sqrtf(disc);
-                    pass = (-b + sq) >= 0.f && (-b - sq) <= ot.w * d2;
-                }
-                if (pass) cand = true;
+                if (enters_receiver_ball(p, f3(ot.x, ot.y, ot.z), f3(dd.x, dd.y, dd.z), ot.w)) cand = true;
                 else if (++k >= n) done = true;
             }
         }
@@ -627,14 +473,15 @@ __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceP
             int bin = -1, primary = 0;
             if (cand) {
                 const F3 org = f3(ot.x, ot.y, ot.z), dir = f3(dd.x, dd.y, dd.z);
-                Hit h;
-                closest_hit(p.nodes, p.tris, p.recv_root, org, dir, ot.w, h);
+                RayGrid g;
+                g.setup(p.rg_origin, p.rg_cell, org, dir);
+                tr.reset(ot.w);
+                tr.walk(stack, p.nodes, p.tris, p.recv_root, g, org, dir);
+                const Hit& h = tr.h;
                 if (h.slot >= 0 && h.t < ot.w) {
-                    const float4 a = __ldg(p.tris + h.slot * 3 + 0);
-                    const float4 b4 = __ldg(p.tris + h.slot * 3 + 1);
-                    const float4 c4 = __ldg(p.tris + h.slot * 3 + 2);
-                    const int mat = __float_as_int(b4.w);
-                    const F3 pt = hit_point(f3(a.x, a.y, a.z), f3(b4.x, b4.y, b4.z), f3(c4.x, c4.y, c4.z), h.u, h.v);
+                    const F8 A = ldg256(p.tris + h.slot * 4), B = ldg256(p.tris + h.slot * 4 + 2);
+                    const int mat = __float_as_int(A.hi.w);
+                    const F3 pt = hit_point(f3(A.lo.x, A.lo.y, A.lo.z), f3(A.hi.x, A.hi.y, A.hi.z), f3(B.lo.x, B.lo.y, B.lo.z), h.u, h.v);
                     const F3 dp = sub3(pt, org);
                     const float dist = __fadd_rn(dd.w, __fsqrt_rn(dot3(dp, dp)));
                     const size_t ci = (size_t)k * (size_t)p.pc_stride + (size_t)ray;
@@ -680,12 +527,8 @@ __global__ void finalize_kernel(const double* __restrict__ hist, int n, int mono
 template <int NB, int MODE>
 cudaError_t launch_trace_t(const TraceParams& p, int sm_count, cudaStream_t stream)
 {
-    int per_sm = 0;
-#ifdef ARV2_TRACE_V1
     auto kernel = trace_kernel<NB, MODE>;
-#else
-    auto kernel = trace2_kernel<NB, MODE>;
-#endif
+    int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
