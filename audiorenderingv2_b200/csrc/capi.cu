@@ -53,9 +53,11 @@ struct arv2_ctx {
     HostScene scene;
     HostReceiver receiver;
     bool has_receiver = false;
-    HostBvh recv_bvh;
+    HostBvh scene_bvh, recv_bvh;     // binary trees (the scene's is kept for re-quantisation)
     std::vector<QNode> recv_q;
-    QuantGrid scene_grid{}, recv_grid{};
+    QuantGrid grid{};
+    float grid_lo[3] = {0, 0, 0}, grid_hi[3] = {0, 0, 0};
+    bool grid_set = false;
     size_t upload_bytes = 0;
     bool recv_bvh_built = false;
     std::vector<float> recv_world;     // [n_recv][3][3]
@@ -104,6 +106,66 @@ struct arv2_stream {
 
 namespace {
 
+// two-level top node: child 0 = scene tree (node 1), child 1 = receiver tree
+QNode make_top_node(const arv2_ctx* c, bool with_receiver)
+{
+    HostBvh t;
+    t.nodes.resize(1);
+    BvhNode& n = t.nodes[0];
+    for (int i = 0; i < 12; ++i) n.q[i] = kEmptyBox;
+    int32_t ch[4] = {~0, ~0, 0, 0};
+    if (c->n_scene > 0) {
+        n.q[0] = c->scene_bvh.lo[0]; n.q[1] = c->scene_bvh.hi[0]; n.q[2] = c->scene_bvh.lo[1]; n.q[3] = c->scene_bvh.hi[1];
+        n.q[8] = c->scene_bvh.lo[2]; n.q[9] = c->scene_bvh.hi[2];
+        ch[0] = 1;
+    }
+    if (with_receiver) {
+        n.q[4] = c->recv_bvh.lo[0]; n.q[5] = c->recv_bvh.hi[0]; n.q[6] = c->recv_bvh.lo[1]; n.q[7] = c->recv_bvh.hi[1];
+        n.q[10] = c->recv_bvh.lo[2]; n.q[11] = c->recv_bvh.hi[2];
+        ch[1] = 1 + c->n_scene_nodes;
+    }
+    std::memcpy(&n.q[12], ch, sizeof ch);
+    std::vector<QNode> q;
+    quantize_bvh2(t, c->grid, 0, 0, &q);
+    // quantize_bvh2 offsets inner codes by node_offset = 0: the codes above are already absolute
+    return q[0];
+}
+
+// (Re)build the quantisation grid so that it contains the scene and the placed receiver
+// with a wide margin, then quantise and upload the scene nodes.
+int ensure_grid(arv2_ctx* c)
+{
+    float lo[3], hi[3];
+    bool any = false;
+    for (int a = 0; a < 3; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+    if (c->n_scene > 0) { for (int a = 0; a < 3; ++a) { lo[a] = c->scene_bvh.lo[a]; hi[a] = c->scene_bvh.hi[a]; } any = true; }
+    bool inside = c->grid_set;
+    if (c->has_receiver && c->recv_bvh_built) {
+        for (int a = 0; a < 3; ++a) {
+            if (c->recv_bvh.lo[a] < c->grid_lo[a] || c->recv_bvh.hi[a] > c->grid_hi[a]) inside = false;
+            lo[a] = std::fmin(lo[a], c->recv_bvh.lo[a]); hi[a] = std::fmax(hi[a], c->recv_bvh.hi[a]);
+        }
+        any = true;
+    }
+    if (inside) return ARV2_OK;
+    if (!any) for (int a = 0; a < 3; ++a) { lo[a] = -1.f; hi[a] = 1.f; }
+    float ext = 0.f;
+    for (int a = 0; a < 3; ++a) ext = std::fmax(ext, hi[a] - lo[a]);
+    const float margin = std::fmax(2.0f, 0.25f * ext);     // the receiver may roam this far outside
+    for (int a = 0; a < 3; ++a) { c->grid_lo[a] = lo[a] - margin; c->grid_hi[a] = hi[a] + margin; }
+    c->grid = make_quant_grid(c->grid_lo, c->grid_hi);
+    c->grid_set = true;
+    std::vector<QNode> q;
+    if (c->n_scene > 0) {
+        quantize_bvh2(c->scene_bvh, c->grid, 1, 0, &q);
+        CK(cudaMemcpy(c->d_nodes + 2, q.data(), q.size() * sizeof(QNode), cudaMemcpyHostToDevice));
+    }
+    const QNode top = make_top_node(c, false);
+    CK(cudaMemcpy(c->d_nodes, &top, sizeof top, cudaMemcpyHostToDevice));
+    c->cache_valid = c->cache_valid;   // paths do not depend on the grid (exact tests decide)
+    return ARV2_OK;
+}
+
 int upload_receiver(arv2_ctx* c)
 {
     if (!c->has_receiver || !c->recv_dirty) return ARV2_OK;
@@ -127,23 +189,30 @@ int upload_receiver(arv2_ctx* c)
     } else {
         refit_bvh(c->recv_world.data(), n, &c->recv_bvh);
     }
-    // quantise the (re)fitted tree on its own grid and stage [receiver nodes][receiver triangles]
-    const int32_t node_base = c->n_scene_nodes;
+    // the grid must contain the receiver; if it moved out (or this is the first placement)
+    // re-grid and re-quantise the scene nodes too (rare: the grid carries a wide margin)
+    int rc = ensure_grid(c);
+    if (rc != ARV2_OK) return rc;
+    // stage [top node][receiver nodes][receiver triangles]
+    const int32_t node_base = 1 + c->n_scene_nodes;
     const int64_t tri_base = c->n_scene;
-    c->recv_grid = make_quant_grid(c->recv_bvh.lo, c->recv_bvh.hi);
-    quantize_bvh2(c->recv_bvh, c->recv_grid, node_base, tri_base, &c->recv_q);
+    quantize_bvh2(c->recv_bvh, c->grid, node_base, tri_base, &c->recv_q);
     const int32_t nn = (int32_t)c->recv_q.size();
-    if (nn > c->n_recv_nodes || bvh2_depth(c->recv_bvh) + 2 > kTraversalStack) { set_error("receiver BVH exceeds its reservation"); return ARV2_ERR_STATE; }
-    float4* sn = c->h_stage;
+    if (nn > c->n_recv_nodes || bvh2_depth(c->recv_bvh) + 3 > kTraversalStack) { set_error("receiver BVH exceeds its reservation"); return ARV2_ERR_STATE; }
+    float4* st = c->h_stage;
+    const QNode top = make_top_node(c, true);
+    std::memcpy(st, &top, sizeof top);
+    float4* sn = st + 2;
     std::memcpy(sn, c->recv_q.data(), (size_t)nn * sizeof(QNode));
     float4* stt = sn + 2 * (size_t)c->n_recv_nodes;
     for (int64_t s = 0; s < n; ++s) {
         const int32_t src = c->recv_bvh.order[s];
         make_tri_record(c->recv_world.data() + 9 * (size_t)src, (int32_t)(tri_base + src), src < nl ? -1 : -2, (float*)(stt + 4 * s));
     }
+    CK(cudaMemcpyAsync(c->d_nodes, st, sizeof(QNode), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_nodes + 2 * (size_t)node_base, sn, sizeof(QNode) * (size_t)nn, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_tris + 4 * (size_t)tri_base, stt, sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    c->upload_bytes = sizeof(QNode) * (size_t)nn + sizeof(float4) * 4 * (size_t)n;
+    c->upload_bytes = sizeof(QNode) * (size_t)(nn + 1) + sizeof(float4) * 4 * (size_t)n;
     c->recv_dirty = false;
     return ARV2_OK;
 }
@@ -173,12 +242,10 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     p->max_bounces = c->max_bounces;
     p->delay = (int)((double)c->desc.sample_rate * 0.00044);   // :125
     p->ir_len = c->ir_len; p->mono = c->mono;
-    p->scene_root = 0; p->recv_root = c->n_scene_nodes;
-    p->has_scene = c->n_scene > 0 ? 1 : 0; p->has_recv = c->has_receiver ? 1 : 0;
-    for (int a = 0; a < 3; ++a) {
-        p->sg_origin[a] = c->scene_grid.origin[a]; p->sg_cell[a] = c->scene_grid.cell[a];
-        p->rg_origin[a] = c->recv_grid.origin[a]; p->rg_cell[a] = c->recv_grid.cell[a];
-    }
+    p->root = 0;
+    p->scene_root = c->n_scene > 0 ? 1 : -1;
+    p->recv_root = c->has_receiver ? 1 + c->n_scene_nodes : -1;
+    for (int a = 0; a < 3; ++a) { p->g_origin[a] = c->grid.origin[a]; p->g_cell[a] = c->grid.cell[a]; }
     p->any_scatter = c->any_scatter;
 }
 
@@ -408,7 +475,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     c->n_recv_nodes = (int32_t)std::max<int64_t>(1, n_recv);
     const bool gpu_build = desc->bvh_builder == 1 && c->n_scene > kMaxLeafTris;
     const unsigned hc = std::thread::hardware_concurrency();
-    HostBvh scene2;
+    HostBvh& scene2 = c->scene_bvh;
     if (!gpu_build) {
         build_bvh_sah(c->scene.tri_verts.data(), c->n_scene, &scene2, hc ? (int)hc : 1);
     } else {
@@ -432,16 +499,9 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
         cudaFree(d_v); cudaFree(d_m); cudaFree(d_n2); cudaFree(d_order);
         if (e != cudaSuccess) { set_error(std::string("build_bvh_lbvh: ") + cudaGetErrorString(e)); return fail(ARV2_ERR_CUDA); }
     }
-    if (bvh2_depth(scene2) + 2 > kTraversalStack) { set_error("scene BVH too deep for the traversal stack"); return fail(ARV2_ERR_INVALID); }
+    if (bvh2_depth(scene2) + 3 > kTraversalStack) { set_error("scene BVH too deep for the traversal stack"); return fail(ARV2_ERR_INVALID); }
     c->n_scene_nodes = (int32_t)scene2.nodes.size();
-    std::vector<QNode> scene_q;
-    if (c->n_scene > 0) {
-        c->scene_grid = make_quant_grid(scene2.lo, scene2.hi);
-        quantize_bvh2(scene2, c->scene_grid, 0, 0, &scene_q);
-    } else {
-        scene_q.assign(scene2.nodes.size(), QNode{});
-    }
-    const size_t total_nodes = (size_t)c->n_scene_nodes + (size_t)c->n_recv_nodes;
+    const size_t total_nodes = 1 + (size_t)c->n_scene_nodes + (size_t)c->n_recv_nodes;
     const size_t total_tris = (size_t)std::max<int64_t>(1, c->n_scene + n_recv);
     CKC(cudaMalloc(&c->d_nodes, total_nodes * sizeof(QNode)));
     CKC(cudaMalloc(&c->d_tris, total_tris * 4 * sizeof(float4)));
@@ -450,7 +510,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     CKC(cudaMemcpy(c->d_keep, keep.data(), keep.size() * sizeof(float), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_scatter, scat.data(), scat.size() * sizeof(float), cudaMemcpyHostToDevice));
     {
-        CKC(cudaMemcpy(c->d_nodes, scene_q.data(), scene_q.size() * sizeof(QNode), cudaMemcpyHostToDevice));
+        if (ensure_grid(c) != ARV2_OK) return fail(ARV2_ERR_CUDA);      // quantises + uploads the scene nodes and the top node
         std::vector<float> recs((size_t)c->n_scene * 16);
         for (int64_t s = 0; s < c->n_scene; ++s) {
             const int32_t src = scene2.order[s];
@@ -458,7 +518,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
         }
         if (c->n_scene) CKC(cudaMemcpy(c->d_tris, recs.data(), recs.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    c->stage_f4 = 2 * (size_t)c->n_recv_nodes + 4 * (size_t)std::max<int64_t>(1, n_recv);
+    c->stage_f4 = 2 + 2 * (size_t)c->n_recv_nodes + 4 * (size_t)std::max<int64_t>(1, n_recv);
     CKC(cudaMallocHost(&c->h_stage, c->stage_f4 * sizeof(float4)));
     CKC(cudaMallocHost(&c->h_counters, 16 * sizeof(unsigned long long)));
 

@@ -169,21 +169,15 @@ __device__ __forceinline__ bool enters_receiver_ball(const TraceParams& p, F3 or
     return (-b + sq) >= 0.f && (-b - sq) <= tmax * d2;
 }
 
-// optixTrace: closest hit over the scene tree, then (full trace only) over the receiver
-// tree when the segment can reach it.
-template <int MODE>
-__device__ __forceinline__ void closest_hit(const TraceParams& p, int* stack, Traversal& tr, F3 org, F3 dir)
+// optixTrace: closest hit below `root` (the two-level top node for a full trace, the scene
+// root while filling the path cache, the receiver root for a re-render).
+__device__ __forceinline__ void closest_hit(const TraceParams& p, int* stack, Traversal& tr, int root, F3 org, F3 dir, float tmax)
 {
-    tr.reset(1e20f);
+    tr.reset(tmax);
+    if (root < 0) return;
     RayGrid g;
-    if (p.has_scene) {
-        g.setup(p.sg_origin, p.sg_cell, org, dir);
-        tr.walk(stack, p.nodes, p.tris, p.scene_root, g, org, dir);
-    }
-    if (MODE == 0 && p.has_recv && enters_receiver_ball(p, org, dir, tr.h.t)) {
-        g.setup(p.rg_origin, p.rg_cell, org, dir);
-        tr.walk(stack, p.nodes, p.tris, p.recv_root, g, org, dir);
-    }
+    g.setup(p.g_origin, p.g_cell, org, dir);
+    tr.walk(stack, p.nodes, p.tris, root, g, org, dir);
 }
 
 // Warp-aggregated deposit into the fp64 histogram (OR/devicePrograms.cu:128-170).
@@ -414,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceP
                 ended = true;                                                         // :233-236
             } else {
                 begin_segment<NB, MODE>(p, s);
-                closest_hit<MODE>(p, stack, tr, s.org, s.dir);
+                closest_hit(p, stack, tr, MODE == 0 ? p.root : p.scene_root, s.org, s.dir, 1e20f);
                 ended = shade_segment<NB, MODE>(p, s, tr.h, d);
             }
         }
@@ -422,6 +416,91 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceP
         if (ended) {
             end_path<NB, MODE>(p, s, d, segs);
             have = false;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
+    if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+}
+
+// ---------------------------------------------------------------------------------------
+// trace2_kernel: the same path tracer with the lanes of a warp decoupled.  Per-segment
+// node-visit counts vary so much inside a warp (sum / (32 x max) = 49 % on the conference
+// scene) that lanes of trace_kernel idle most of the time (9.5 of 32 lanes per instruction,
+// r03b profile) and the kernel ends up latency-bound with too few loads in flight.  Here a
+// lane that has finished its segment parks while the others keep traversing; three
+// warp-uniform phases are scheduled by ballots:
+//   A  shade + deposit + refill + start the next segment -- when >= ARV2_TA lanes are parked
+//   L  one leaf (<= 4 triangle tests) per lane           -- when >= ARV2_TL lanes stand at a leaf
+//   I  up to ARV2_BURST inner-node steps                  -- otherwise
+#ifndef ARV2_TA
+#define ARV2_TA 12
+#endif
+#ifndef ARV2_TL
+#define ARV2_TL 8
+#endif
+#ifndef ARV2_BURST
+#define ARV2_BURST 4
+#endif
+template <int NB, int MODE>
+__global__ void __launch_bounds__(kThreads, ARV2_MINB) trace2_kernel(const TraceParams p)
+{
+    const int lane = threadIdx.x & 31;
+    long long chunk_next = 0, chunk_end = 0;      // warp-uniform
+    bool have = false, exhausted = false, pending = false;
+    Path<NB> s;
+    s.ray = 0; s.org = f3(0, 0, 0); s.dir = f3(0, 0, 0); s.dist = 0.f; s.depth = 0; s.nseg = 0;
+    unsigned long long segs = 0;
+    Traversal tr;
+    tr.reset(1e20f);
+    RayGrid g;
+    g.ax = g.ay = g.az = g.bx = g.by = g.bz = 0.f; g.nx = g.ny = g.nz = 0x7610u;
+    int stack[kStack];
+
+    for (;;) {
+        const bool parked = tr.finished() && !exhausted;
+        const unsigned inner_m = __ballot_sync(FULL, tr.at_inner());
+        const unsigned leaf_m = __ballot_sync(FULL, tr.at_leaf());
+        const unsigned park_m = __ballot_sync(FULL, parked);
+        if ((inner_m | leaf_m | park_m) == 0) break;
+
+        if (park_m != 0 && (__popc(park_m) >= ARV2_TA || (inner_m | leaf_m) == 0)) {
+            // ---- phase A
+            bool ended = false;
+            Deposit d; d.dep = false; d.bin = -1; d.ear = 0; d.primary = 0;
+            if (parked && have && pending) {
+                pending = false;
+                ended = shade_segment<NB, MODE>(p, s, tr.h, d);
+            }
+            if (MODE == 0) deposit_warp<NB>(p, d.dep, d.bin, d.primary, s.energy);
+            if (parked && have && !ended && !path_goes_on<NB>(p, s)) ended = true;
+            if (parked && have && ended) { end_path<NB, MODE>(p, s, d, segs); have = false; }
+            if (refill<NB>(p, parked && !have, chunk_next, chunk_end, exhausted, s)) {
+                have = true;
+                if (!path_goes_on<NB>(p, s)) {      // only through its parameters (or a zero direction)
+                    Deposit none; none.dep = false; none.bin = -1; none.ear = 0; none.primary = 0;
+                    end_path<NB, MODE>(p, s, none, segs);
+                    have = false;
+                }
+            }
+            if (parked && have) {
+                begin_segment<NB, MODE>(p, s);
+                tr.reset(1e20f);
+                pending = true;
+                const int root = MODE == 0 ? p.root : p.scene_root;
+                if (root >= 0) {
+                    g.setup(p.g_origin, p.g_cell, s.org, s.dir);
+                    tr.enter(stack, root);
+                }
+            }
+        } else if (leaf_m != 0 && (__popc(leaf_m) >= ARV2_TL || inner_m == 0)) {
+            // ---- phase L
+            if (tr.at_leaf()) tr.step_leaf(stack, p.tris, s.org, s.dir);
+        } else {
+            // ---- phase I
+#pragma unroll 1
+            for (int k = 0; k < ARV2_BURST; ++k)
+                if (tr.at_inner()) tr.step_inner(stack, p.nodes, g);
         }
     }
 #pragma unroll
@@ -473,10 +552,7 @@ __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceP
             int bin = -1, primary = 0;
             if (cand) {
                 const F3 org = f3(ot.x, ot.y, ot.z), dir = f3(dd.x, dd.y, dd.z);
-                RayGrid g;
-                g.setup(p.rg_origin, p.rg_cell, org, dir);
-                tr.reset(ot.w);
-                tr.walk(stack, p.nodes, p.tris, p.recv_root, g, org, dir);
+                closest_hit(p, stack, tr, p.recv_root, org, dir, ot.w);
                 const Hit& h = tr.h;
                 if (h.slot >= 0 && h.t < ot.w) {
                     const F8 A = ldg256(p.tris + h.slot * 4), B = ldg256(p.tris + h.slot * 4 + 2);
@@ -527,7 +603,11 @@ __global__ void finalize_kernel(const double* __restrict__ hist, int n, int mono
 template <int NB, int MODE>
 cudaError_t launch_trace_t(const TraceParams& p, int sm_count, cudaStream_t stream)
 {
+#ifdef ARV2_TRACE_V2
+    auto kernel = trace2_kernel<NB, MODE>;
+#else
     auto kernel = trace_kernel<NB, MODE>;
+#endif
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
     if (e != cudaSuccess) return e;
