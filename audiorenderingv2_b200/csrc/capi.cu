@@ -109,26 +109,20 @@ namespace {
 // two-level top node: child 0 = scene tree (node 1), child 1 = receiver tree
 QNode make_top_node(const arv2_ctx* c, bool with_receiver)
 {
-    HostBvh t;
-    t.nodes.resize(1);
-    BvhNode& n = t.nodes[0];
-    for (int i = 0; i < 12; ++i) n.q[i] = kEmptyBox;
-    int32_t ch[4] = {~0, ~0, 0, 0};
+    float lo[2][3], hi[2][3];
+    int32_t codes[2];
+    int n = 0;
     if (c->n_scene > 0) {
-        n.q[0] = c->scene_bvh.lo[0]; n.q[1] = c->scene_bvh.hi[0]; n.q[2] = c->scene_bvh.lo[1]; n.q[3] = c->scene_bvh.hi[1];
-        n.q[8] = c->scene_bvh.lo[2]; n.q[9] = c->scene_bvh.hi[2];
-        ch[0] = 1;
+        for (int a = 0; a < 3; ++a) { lo[n][a] = c->scene_bvh.lo[a]; hi[n][a] = c->scene_bvh.hi[a]; }
+        codes[n++] = 1;
     }
     if (with_receiver) {
-        n.q[4] = c->recv_bvh.lo[0]; n.q[5] = c->recv_bvh.hi[0]; n.q[6] = c->recv_bvh.lo[1]; n.q[7] = c->recv_bvh.hi[1];
-        n.q[10] = c->recv_bvh.lo[2]; n.q[11] = c->recv_bvh.hi[2];
-        ch[1] = 1 + c->n_scene_nodes;
+        for (int a = 0; a < 3; ++a) { lo[n][a] = c->recv_bvh.lo[a]; hi[n][a] = c->recv_bvh.hi[a]; }
+        codes[n++] = 1 + c->n_scene_nodes;
     }
-    std::memcpy(&n.q[12], ch, sizeof ch);
-    std::vector<QNode> q;
-    quantize_bvh2(t, c->grid, 0, 0, &q);
-    // quantize_bvh2 offsets inner codes by node_offset = 0: the codes above are already absolute
-    return q[0];
+    QNode q;
+    make_qnode(c->grid, lo, hi, codes, n, &q);
+    return q;
 }
 
 // (Re)build the quantisation grid so that it contains the scene and the placed receiver
@@ -157,8 +151,9 @@ int ensure_grid(arv2_ctx* c)
     c->grid_set = true;
     std::vector<QNode> q;
     if (c->n_scene > 0) {
-        quantize_bvh2(c->scene_bvh, c->grid, 1, 0, &q);
-        CK(cudaMemcpy(c->d_nodes + 2, q.data(), q.size() * sizeof(QNode), cudaMemcpyHostToDevice));
+        collapse_bvh4(c->scene_bvh, c->grid, 1, 0, &q);
+        if ((int32_t)q.size() > c->n_scene_nodes || bvh4_stack_need(q, 1) > kTraversalStack) { set_error("scene BVH too deep for the traversal stack"); return ARV2_ERR_INVALID; }
+        CK(cudaMemcpy(c->d_nodes + 4, q.data(), q.size() * sizeof(QNode), cudaMemcpyHostToDevice));
     }
     const QNode top = make_top_node(c, false);
     CK(cudaMemcpy(c->d_nodes, &top, sizeof top, cudaMemcpyHostToDevice));
@@ -196,21 +191,21 @@ int upload_receiver(arv2_ctx* c)
     // stage [top node][receiver nodes][receiver triangles]
     const int32_t node_base = 1 + c->n_scene_nodes;
     const int64_t tri_base = c->n_scene;
-    quantize_bvh2(c->recv_bvh, c->grid, node_base, tri_base, &c->recv_q);
+    collapse_bvh4(c->recv_bvh, c->grid, node_base, tri_base, &c->recv_q);
     const int32_t nn = (int32_t)c->recv_q.size();
-    if (nn > c->n_recv_nodes || bvh2_depth(c->recv_bvh) + 3 > kTraversalStack) { set_error("receiver BVH exceeds its reservation"); return ARV2_ERR_STATE; }
+    if (nn > c->n_recv_nodes || bvh4_stack_need(c->recv_q, node_base) > kTraversalStack) { set_error("receiver BVH exceeds its reservation"); return ARV2_ERR_STATE; }
     float4* st = c->h_stage;
     const QNode top = make_top_node(c, true);
     std::memcpy(st, &top, sizeof top);
-    float4* sn = st + 2;
+    float4* sn = st + 4;
     std::memcpy(sn, c->recv_q.data(), (size_t)nn * sizeof(QNode));
-    float4* stt = sn + 2 * (size_t)c->n_recv_nodes;
+    float4* stt = sn + 4 * (size_t)c->n_recv_nodes;
     for (int64_t s = 0; s < n; ++s) {
         const int32_t src = c->recv_bvh.order[s];
         make_tri_record(c->recv_world.data() + 9 * (size_t)src, (int32_t)(tri_base + src), src < nl ? -1 : -2, (float*)(stt + 4 * s));
     }
     CK(cudaMemcpyAsync(c->d_nodes, st, sizeof(QNode), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_nodes + 2 * (size_t)node_base, sn, sizeof(QNode) * (size_t)nn, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_nodes + 4 * (size_t)node_base, sn, sizeof(QNode) * (size_t)nn, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_tris + 4 * (size_t)tri_base, stt, sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     c->upload_bytes = sizeof(QNode) * (size_t)(nn + 1) + sizeof(float4) * 4 * (size_t)n;
     c->recv_dirty = false;
@@ -499,7 +494,6 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
         cudaFree(d_v); cudaFree(d_m); cudaFree(d_n2); cudaFree(d_order);
         if (e != cudaSuccess) { set_error(std::string("build_bvh_lbvh: ") + cudaGetErrorString(e)); return fail(ARV2_ERR_CUDA); }
     }
-    if (bvh2_depth(scene2) + 3 > kTraversalStack) { set_error("scene BVH too deep for the traversal stack"); return fail(ARV2_ERR_INVALID); }
     c->n_scene_nodes = (int32_t)scene2.nodes.size();
     const size_t total_nodes = 1 + (size_t)c->n_scene_nodes + (size_t)c->n_recv_nodes;
     const size_t total_tris = (size_t)std::max<int64_t>(1, c->n_scene + n_recv);
@@ -510,7 +504,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     CKC(cudaMemcpy(c->d_keep, keep.data(), keep.size() * sizeof(float), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_scatter, scat.data(), scat.size() * sizeof(float), cudaMemcpyHostToDevice));
     {
-        if (ensure_grid(c) != ARV2_OK) return fail(ARV2_ERR_CUDA);      // quantises + uploads the scene nodes and the top node
+        { const int grc = ensure_grid(c); if (grc != ARV2_OK) return fail(grc); }      // quantises + uploads the scene nodes and the top node
         std::vector<float> recs((size_t)c->n_scene * 16);
         for (int64_t s = 0; s < c->n_scene; ++s) {
             const int32_t src = scene2.order[s];
@@ -518,7 +512,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
         }
         if (c->n_scene) CKC(cudaMemcpy(c->d_tris, recs.data(), recs.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    c->stage_f4 = 2 + 2 * (size_t)c->n_recv_nodes + 4 * (size_t)std::max<int64_t>(1, n_recv);
+    c->stage_f4 = 4 + 4 * (size_t)c->n_recv_nodes + 4 * (size_t)std::max<int64_t>(1, n_recv);
     CKC(cudaMallocHost(&c->h_stage, c->stage_f4 * sizeof(float4)));
     CKC(cudaMallocHost(&c->h_counters, 16 * sizeof(unsigned long long)));
 

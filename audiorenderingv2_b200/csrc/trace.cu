@@ -11,8 +11,9 @@
 // path ended from a warp-local chunk of the seeded ray set (ballot + popc compaction),
 // so no ray state ever goes through HBM.  The r02 profile showed the tracer bound by the
 // L1 data pipe at one wavefront per lane and load instruction (the whole BVH is L2/L1
-// resident, DRAM idles), so the layouts minimise load INSTRUCTIONS: a binary node with
-// 16-bit quantised child boxes is one 256-bit load, a triangle two (arv2_internal.h).
+// resident, DRAM idles) and then latency-bound on the dependent node chain, so the layout
+// minimises load INSTRUCTIONS and dependent steps: a 4-wide node with 16-bit child boxes on
+// one global grid is two 256-bit loads, a triangle two (arv2_internal.h).
 // Receiver deposits are aggregated across the warp (match.any) and accumulated in an fp64
 // histogram with native RED.F64, which makes the result independent of the deposit order
 // to ~1e-16.
@@ -40,7 +41,17 @@ constexpr int kSentinel = INT_MIN;   // "nothing (left) to traverse"
 constexpr int kRerenderThreads = 256;
 constexpr int kRerenderBatch = 12;   // lanes that must hold a candidate before the receiver walk
 
+#define ARV2_INF __int_as_float(0x7f800000)
+
 struct Hit { float t, u, v; int slot, id; };
+
+__device__ __forceinline__ void cswap(float& ta, int& ea, float& tb, int& eb)
+{
+    const bool s = tb < ta;
+    const float t0 = s ? tb : ta, t1 = s ? ta : tb;
+    const int e0 = s ? eb : ea, e1 = s ? ea : eb;
+    ta = t0; tb = t1; ea = e0; eb = e1;
+}
 
 // 256-bit read-only global load (sm_100+: LDG.E.ENL2.256.CONSTANT).
 struct __align__(32) F8 { float4 lo, hi; };
@@ -99,30 +110,32 @@ struct Traversal {
     __device__ __forceinline__ bool at_leaf() const { return cur < 0 && cur != kSentinel; }
     __device__ __forceinline__ bool finished() const { return cur == kSentinel; }
 
+    // one 4-wide node (two 256-bit loads): slab test of the four quantised child boxes,
+    // descend into the nearest hit child, push the others far-to-near
     __device__ __forceinline__ void step_inner(int* stack, const float4* __restrict__ nodes, const RayGrid& g)
     {
-        const F8 N = ldg256(nodes + cur * 2);
+        const F8 A = ldg256(nodes + cur * 4), B = ldg256(nodes + cur * 4 + 2);
         const unsigned fx = g.nx ^ 0x0022u, fy = g.ny ^ 0x0022u, fz = g.nz ^ 0x0022u;
-        const float n0 = fmaxf(fmaxf(fmaf(qhalf(N.lo.x, g.nx), g.ax, g.bx), fmaf(qhalf(N.lo.y, g.ny), g.ay, g.by)),
-                               fmaxf(fmaf(qhalf(N.lo.z, g.nz), g.az, g.bz), 0.f));
-        const float f0 = fminf(fminf(fmaf(qhalf(N.lo.x, fx), g.ax, g.bx), fmaf(qhalf(N.lo.y, fy), g.ay, g.by)),
-                               fminf(fmaf(qhalf(N.lo.z, fz), g.az, g.bz), h.t));
-        const float n1 = fmaxf(fmaxf(fmaf(qhalf(N.lo.w, g.nx), g.ax, g.bx), fmaf(qhalf(N.hi.x, g.ny), g.ay, g.by)),
-                               fmaxf(fmaf(qhalf(N.hi.y, g.nz), g.az, g.bz), 0.f));
-        const float f1 = fminf(fminf(fmaf(qhalf(N.lo.w, fx), g.ax, g.bx), fmaf(qhalf(N.hi.x, fy), g.ay, g.by)),
-                               fminf(fmaf(qhalf(N.hi.y, fz), g.az, g.bz), h.t));
-        const bool go0 = n0 <= f0, go1 = n1 <= f1;
-        const int i0 = __float_as_int(N.hi.z), i1 = __float_as_int(N.hi.w);
-        if (!go0 && !go1) {
-            cur = stack[--sp];
-        } else {
-            cur = go0 ? i0 : i1;
-            if (go0 && go1) {
-                int far = i1;
-                if (n1 < n0) { cur = i1; far = i0; }
-                stack[sp++] = far;
-            }
-        }
+        float t0 = interval(A.lo.x, A.lo.y, A.lo.z, g, fx, fy, fz);
+        float t1 = interval(A.lo.w, A.hi.x, A.hi.y, g, fx, fy, fz);
+        float t2 = interval(A.hi.z, A.hi.w, B.lo.x, g, fx, fy, fz);
+        float t3 = interval(B.lo.y, B.lo.z, B.lo.w, g, fx, fy, fz);
+        int e0 = __float_as_int(B.hi.x), e1 = __float_as_int(B.hi.y), e2 = __float_as_int(B.hi.z), e3 = __float_as_int(B.hi.w);
+        cswap(t0, e0, t1, e1); cswap(t2, e2, t3, e3); cswap(t0, e0, t2, e2); cswap(t1, e1, t3, e3); cswap(t1, e1, t2, e2);
+        if (t3 < ARV2_INF) stack[sp++] = e3;
+        if (t2 < ARV2_INF) stack[sp++] = e2;
+        if (t1 < ARV2_INF) stack[sp++] = e1;
+        cur = t0 < ARV2_INF ? e0 : stack[--sp];
+    }
+
+    // entry distance of the ray into one quantised child box, +inf when it misses
+    __device__ __forceinline__ float interval(float wx, float wy, float wz, const RayGrid& g, unsigned fx, unsigned fy, unsigned fz) const
+    {
+        const float tn = fmaxf(fmaxf(fmaf(qhalf(wx, g.nx), g.ax, g.bx), fmaf(qhalf(wy, g.ny), g.ay, g.by)),
+                               fmaxf(fmaf(qhalf(wz, g.nz), g.az, g.bz), 0.f));
+        const float tf = fminf(fminf(fmaf(qhalf(wx, fx), g.ax, g.bx), fmaf(qhalf(wy, fy), g.ay, g.by)),
+                               fminf(fmaf(qhalf(wz, fz), g.az, g.bz), h.t));
+        return tn <= tf ? tn : ARV2_INF;
     }
 
     // one leaf: exact tests of its <= 4 triangles
@@ -408,7 +421,11 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceP
                 ended = true;                                                         // :233-236
             } else {
                 begin_segment<NB, MODE>(p, s);
-                closest_hit(p, stack, tr, MODE == 0 ? p.root : p.scene_root, s.org, s.dir, 1e20f);
+                // only segments whose line meets the receiver's bounding ball start at the two-level
+                // top node; the others go straight into the scene tree (the top node's AABB of
+                // the ball would let 3x as many lanes into the receiver tree)
+                const bool to_recv = MODE == 0 && p.recv_root >= 0 && enters_receiver_ball(p, s.org, s.dir, 1e20f);
+                closest_hit(p, stack, tr, to_recv ? p.root : p.scene_root, s.org, s.dir, 1e20f);
                 ended = shade_segment<NB, MODE>(p, s, tr.h, d);
             }
         }
@@ -487,7 +504,8 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace2_kernel(const Trace
                 begin_segment<NB, MODE>(p, s);
                 tr.reset(1e20f);
                 pending = true;
-                const int root = MODE == 0 ? p.root : p.scene_root;
+                const bool to_recv = MODE == 0 && p.recv_root >= 0 && enters_receiver_ball(p, s.org, s.dir, 1e20f);
+                const int root = to_recv ? p.root : p.scene_root;
                 if (root >= 0) {
                     g.setup(p.g_origin, p.g_cell, s.org, s.dir);
                     tr.enter(stack, root);
