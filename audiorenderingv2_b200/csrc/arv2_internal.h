@@ -38,10 +38,6 @@ struct HostReceiver {
 //   q2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
 //   q3 = (int c0, int c1, -, -)   c >= 0: inner node index
 //                                 c <  0: leaf, ~c = (first_tri << 3) | (count - 1)
-// Triangles, 48 B each (3 x float4), stored in leaf order:
-//   t0 = (P1.xyz, bits(global triangle id))
-//   t1 = (P2.xyz, bits(material: >=0 wall material, -1 / -2 receiver ear))
-//   t2 = (P3.xyz, 0)
 struct BvhNode { float q[16]; };
 constexpr int kMaxLeafTris = 4;
 constexpr int kLeafShift = 3;
@@ -62,34 +58,15 @@ void refit_bvh(const float* tri_verts, int64_t n, HostBvh* bvh);
 // Conservative padding applied to every box (relative to the scene extent).
 inline float bvh_pad(float extent) { return extent * 1e-5f + 1e-6f; }
 
-// ---- device layout: 4-wide BVH, 16-bit boxes on one global grid ----------------------------
-// The tracer is latency-bound on the chain load node -> test boxes -> load next node
-// (r03b profile: 5 of 6.7 warps per scheduler wait on the L1/L2 round trip), so the layout
-// minimises dependent steps and load instructions: a node holds FOUR children, their boxes
-// quantised to a 65536^3 grid shared by the whole context, i.e. all dequantisation constants
-// belong to the ray, none to the node:  plane = grid.origin + q * grid.cell,
-// t(q) = q * (cell / dir) + (origin - org) / dir.   64 B per node = two 256-bit loads:
-//   w[3*i + a] = child i, axis a: (lo | hi << 16), rounded outwards by 2 cells
-//   w[12 + i]  = child code: >= 0 inner node index, < 0 leaf ~((first << 3) | (count-1)),
-//                kEmptyEntry with an inverted box (lo = 65535, hi = 0) for an absent child
-// Node 0 is the two-level top node (scene tree, receiver tree): a receiver move rewrites only
-// the receiver's ~55 KB.  Triangles, 64 B = two 256-bit loads:
-// (P1, id) (P2, material) (P3, Ng.x) (Ng.y, Ng.z, 0, 0), Ng = the unit normal of the
-// arithmetic contract, precomputed once.
-struct QNode { uint32_t w[16]; };
-struct QuantGrid { float origin[3]; float cell[3]; };
-constexpr int32_t kEmptyEntry = INT32_MIN;
-constexpr int kTraversalStack = 96;      // per-lane stack entries of the kernels (trace.cu)
-
-QuantGrid make_quant_grid(const float lo[3], const float hi[3]);
-// Collapse a binary tree into 4-wide quantised nodes (node 0 = root).  Inner codes are
-// written + node_offset, leaf slots + slot_offset; the triangle order of `bvh2` is kept.
-void collapse_bvh4(const HostBvh& bvh2, const QuantGrid& g, int32_t node_offset, int64_t slot_offset, std::vector<QNode>* out);
-// One node over up to four (box, code) children.
-void make_qnode(const QuantGrid& g, const float (*lo)[3], const float (*hi)[3], const int32_t* codes, int n, QNode* out);
-// Worst-case traversal stack entries of a collapsed tree (3 pushes per level + slack).
-int bvh4_stack_need(const std::vector<QNode>& nodes, int32_t node_offset);
-// 64 B triangle record (normal precomputed with the contract's operations).
+// ---- device layout -------------------------------------------------------------------------
+// Nodes: BvhNode as above, [0] = two-level top node (child 0 = scene tree at node 1, child 1 =
+// receiver tree), so a receiver move rewrites only the receiver's ~85 KB.
+// Triangles, 64 B = two 256-bit loads, in leaf order:
+//   (P1, id) (P2, material) (P3, Ng.x) (Ng.y, Ng.z, 0, 0)
+// material >= 0 = mesh index into keep[mesh][band], -1 / -2 = receiver ears; Ng = the unit
+// normal of the arithmetic contract, precomputed once on the host.
+constexpr int kTraversalStack = 64;      // per-lane stack entries of the kernels (trace.cu)
+int bvh2_depth(const HostBvh& bvh2);
 void make_tri_record(const float* v9, int32_t id, int32_t material, float* out16);
 
 // ---- host front end -------------------------------------------------------------

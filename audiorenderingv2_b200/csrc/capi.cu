@@ -53,11 +53,7 @@ struct arv2_ctx {
     HostScene scene;
     HostReceiver receiver;
     bool has_receiver = false;
-    HostBvh scene_bvh, recv_bvh;     // binary trees (the scene's is kept for re-quantisation)
-    std::vector<QNode> recv_q;
-    QuantGrid grid{};
-    float grid_lo[3] = {0, 0, 0}, grid_hi[3] = {0, 0, 0};
-    bool grid_set = false;
+    HostBvh scene_bvh, recv_bvh;     // binary trees (host copies)
     size_t upload_bytes = 0;
     bool recv_bvh_built = false;
     std::vector<float> recv_world;     // [n_recv][3][3]
@@ -106,59 +102,40 @@ struct arv2_stream {
 
 namespace {
 
-// two-level top node: child 0 = scene tree (node 1), child 1 = receiver tree
-QNode make_top_node(const arv2_ctx* c, bool with_receiver)
+// Binary nodes with their child links moved into the combined index space.
+void offset_nodes(const HostBvh& b, int32_t node_offset, int64_t slot_offset, BvhNode* out)
 {
-    float lo[2][3], hi[2][3];
-    int32_t codes[2];
-    int n = 0;
-    if (c->n_scene > 0) {
-        for (int a = 0; a < 3; ++a) { lo[n][a] = c->scene_bvh.lo[a]; hi[n][a] = c->scene_bvh.hi[a]; }
-        codes[n++] = 1;
+    for (size_t i = 0; i < b.nodes.size(); ++i) {
+        BvhNode d = b.nodes[i];
+        int32_t ch[4];
+        std::memcpy(ch, &d.q[12], sizeof ch);
+        for (int w = 0; w < 2; ++w) {
+            if (ch[w] >= 0) ch[w] += node_offset;
+            else { const int32_t code = ~ch[w]; ch[w] = ~(int32_t)((((int64_t)(code >> kLeafShift) + slot_offset) << kLeafShift) | (code & 7)); }
+        }
+        std::memcpy(&d.q[12], ch, sizeof ch);
+        out[i] = d;
     }
-    if (with_receiver) {
-        for (int a = 0; a < 3; ++a) { lo[n][a] = c->recv_bvh.lo[a]; hi[n][a] = c->recv_bvh.hi[a]; }
-        codes[n++] = 1 + c->n_scene_nodes;
-    }
-    QNode q;
-    make_qnode(c->grid, lo, hi, codes, n, &q);
-    return q;
 }
 
-// (Re)build the quantisation grid so that it contains the scene and the placed receiver
-// with a wide margin, then quantise and upload the scene nodes.
-int ensure_grid(arv2_ctx* c)
+// two-level top node: child 0 = scene tree (node 1), child 1 = receiver tree
+BvhNode make_top_node(const arv2_ctx* c, bool with_receiver)
 {
-    float lo[3], hi[3];
-    bool any = false;
-    for (int a = 0; a < 3; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
-    if (c->n_scene > 0) { for (int a = 0; a < 3; ++a) { lo[a] = c->scene_bvh.lo[a]; hi[a] = c->scene_bvh.hi[a]; } any = true; }
-    bool inside = c->grid_set;
-    if (c->has_receiver && c->recv_bvh_built) {
-        for (int a = 0; a < 3; ++a) {
-            if (c->recv_bvh.lo[a] < c->grid_lo[a] || c->recv_bvh.hi[a] > c->grid_hi[a]) inside = false;
-            lo[a] = std::fmin(lo[a], c->recv_bvh.lo[a]); hi[a] = std::fmax(hi[a], c->recv_bvh.hi[a]);
-        }
-        any = true;
-    }
-    if (inside) return ARV2_OK;
-    if (!any) for (int a = 0; a < 3; ++a) { lo[a] = -1.f; hi[a] = 1.f; }
-    float ext = 0.f;
-    for (int a = 0; a < 3; ++a) ext = std::fmax(ext, hi[a] - lo[a]);
-    const float margin = std::fmax(2.0f, 0.25f * ext);     // the receiver may roam this far outside
-    for (int a = 0; a < 3; ++a) { c->grid_lo[a] = lo[a] - margin; c->grid_hi[a] = hi[a] + margin; }
-    c->grid = make_quant_grid(c->grid_lo, c->grid_hi);
-    c->grid_set = true;
-    std::vector<QNode> q;
+    BvhNode n{};
+    for (int i = 0; i < 12; ++i) n.q[i] = kEmptyBox;
+    int32_t ch[4] = {~0, ~0, 0, 0};
     if (c->n_scene > 0) {
-        collapse_bvh4(c->scene_bvh, c->grid, 1, 0, &q);
-        if ((int32_t)q.size() > c->n_scene_nodes || bvh4_stack_need(q, 1) > kTraversalStack) { set_error("scene BVH too deep for the traversal stack"); return ARV2_ERR_INVALID; }
-        CK(cudaMemcpy(c->d_nodes + 4, q.data(), q.size() * sizeof(QNode), cudaMemcpyHostToDevice));
+        n.q[0] = c->scene_bvh.lo[0]; n.q[1] = c->scene_bvh.hi[0]; n.q[2] = c->scene_bvh.lo[1]; n.q[3] = c->scene_bvh.hi[1];
+        n.q[8] = c->scene_bvh.lo[2]; n.q[9] = c->scene_bvh.hi[2];
+        ch[0] = 1;
     }
-    const QNode top = make_top_node(c, false);
-    CK(cudaMemcpy(c->d_nodes, &top, sizeof top, cudaMemcpyHostToDevice));
-    c->cache_valid = c->cache_valid;   // paths do not depend on the grid (exact tests decide)
-    return ARV2_OK;
+    if (with_receiver) {
+        n.q[4] = c->recv_bvh.lo[0]; n.q[5] = c->recv_bvh.hi[0]; n.q[6] = c->recv_bvh.lo[1]; n.q[7] = c->recv_bvh.hi[1];
+        n.q[10] = c->recv_bvh.lo[2]; n.q[11] = c->recv_bvh.hi[2];
+        ch[1] = 1 + c->n_scene_nodes;
+    }
+    std::memcpy(&n.q[12], ch, sizeof ch);
+    return n;
 }
 
 int upload_receiver(arv2_ctx* c)
@@ -184,30 +161,25 @@ int upload_receiver(arv2_ctx* c)
     } else {
         refit_bvh(c->recv_world.data(), n, &c->recv_bvh);
     }
-    // the grid must contain the receiver; if it moved out (or this is the first placement)
-    // re-grid and re-quantise the scene nodes too (rare: the grid carries a wide margin)
-    int rc = ensure_grid(c);
-    if (rc != ARV2_OK) return rc;
     // stage [top node][receiver nodes][receiver triangles]
     const int32_t node_base = 1 + c->n_scene_nodes;
     const int64_t tri_base = c->n_scene;
-    collapse_bvh4(c->recv_bvh, c->grid, node_base, tri_base, &c->recv_q);
-    const int32_t nn = (int32_t)c->recv_q.size();
-    if (nn > c->n_recv_nodes || bvh4_stack_need(c->recv_q, node_base) > kTraversalStack) { set_error("receiver BVH exceeds its reservation"); return ARV2_ERR_STATE; }
+    const int32_t nn = (int32_t)c->recv_bvh.nodes.size();
+    if (nn > c->n_recv_nodes || bvh2_depth(c->recv_bvh) + 3 > kTraversalStack) { set_error("receiver BVH exceeds its reservation"); return ARV2_ERR_STATE; }
     float4* st = c->h_stage;
-    const QNode top = make_top_node(c, true);
+    const BvhNode top = make_top_node(c, true);
     std::memcpy(st, &top, sizeof top);
     float4* sn = st + 4;
-    std::memcpy(sn, c->recv_q.data(), (size_t)nn * sizeof(QNode));
+    offset_nodes(c->recv_bvh, node_base, tri_base, (BvhNode*)sn);
     float4* stt = sn + 4 * (size_t)c->n_recv_nodes;
     for (int64_t s = 0; s < n; ++s) {
         const int32_t src = c->recv_bvh.order[s];
         make_tri_record(c->recv_world.data() + 9 * (size_t)src, (int32_t)(tri_base + src), src < nl ? -1 : -2, (float*)(stt + 4 * s));
     }
-    CK(cudaMemcpyAsync(c->d_nodes, st, sizeof(QNode), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_nodes + 4 * (size_t)node_base, sn, sizeof(QNode) * (size_t)nn, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_nodes, st, sizeof(BvhNode), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_nodes + 4 * (size_t)node_base, sn, sizeof(BvhNode) * (size_t)nn, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_tris + 4 * (size_t)tri_base, stt, sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    c->upload_bytes = sizeof(QNode) * (size_t)(nn + 1) + sizeof(float4) * 4 * (size_t)n;
+    c->upload_bytes = sizeof(BvhNode) * (size_t)(nn + 1) + sizeof(float4) * 4 * (size_t)n;
     c->recv_dirty = false;
     return ARV2_OK;
 }
@@ -240,7 +212,6 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     p->root = 0;
     p->scene_root = c->n_scene > 0 ? 1 : -1;
     p->recv_root = c->has_receiver ? 1 + c->n_scene_nodes : -1;
-    for (int a = 0; a < 3; ++a) { p->g_origin[a] = c->grid.origin[a]; p->g_cell[a] = c->grid.cell[a]; }
     p->any_scatter = c->any_scatter;
 }
 
@@ -497,14 +468,19 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     c->n_scene_nodes = (int32_t)scene2.nodes.size();
     const size_t total_nodes = 1 + (size_t)c->n_scene_nodes + (size_t)c->n_recv_nodes;
     const size_t total_tris = (size_t)std::max<int64_t>(1, c->n_scene + n_recv);
-    CKC(cudaMalloc(&c->d_nodes, total_nodes * sizeof(QNode)));
+    CKC(cudaMalloc(&c->d_nodes, total_nodes * sizeof(BvhNode)));
     CKC(cudaMalloc(&c->d_tris, total_tris * 4 * sizeof(float4)));
     CKC(cudaMalloc(&c->d_keep, keep.size() * sizeof(float)));
     CKC(cudaMalloc(&c->d_scatter, scat.size() * sizeof(float)));
     CKC(cudaMemcpy(c->d_keep, keep.data(), keep.size() * sizeof(float), cudaMemcpyHostToDevice));
     CKC(cudaMemcpy(c->d_scatter, scat.data(), scat.size() * sizeof(float), cudaMemcpyHostToDevice));
     {
-        { const int grc = ensure_grid(c); if (grc != ARV2_OK) return fail(grc); }      // quantises + uploads the scene nodes and the top node
+        if (bvh2_depth(scene2) + 3 > kTraversalStack) { set_error("scene BVH too deep for the traversal stack"); return fail(ARV2_ERR_INVALID); }
+        std::vector<BvhNode> nodes(scene2.nodes.size());
+        offset_nodes(scene2, 1, 0, nodes.data());
+        const BvhNode top = make_top_node(c, false);
+        CKC(cudaMemcpy(c->d_nodes, &top, sizeof top, cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(c->d_nodes + 4, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));      // quantises + uploads the scene nodes and the top node
         std::vector<float> recs((size_t)c->n_scene * 16);
         for (int64_t s = 0; s < c->n_scene; ++s) {
             const int32_t src = scene2.order[s];

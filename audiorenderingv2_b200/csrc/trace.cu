@@ -11,9 +11,11 @@
 // path ended from a warp-local chunk of the seeded ray set (ballot + popc compaction),
 // so no ray state ever goes through HBM.  The r02 profile showed the tracer bound by the
 // L1 data pipe at one wavefront per lane and load instruction (the whole BVH is L2/L1
-// resident, DRAM idles) and then latency-bound on the dependent node chain, so the layout
-// minimises load INSTRUCTIONS and dependent steps: a 4-wide node with 16-bit child boxes on
-// one global grid is two 256-bit loads, a triangle two (arv2_internal.h).
+// resident, DRAM idles), so every 64 B record (binary node with both child boxes, triangle
+// with its precomputed normal) is fetched with two 256-bit loads (arv2_internal.h).
+// Quantised 32 B binary nodes and 4-wide nodes (8- and 16-bit boxes) were built and measured:
+// all slower or equal, the kernel is bound by the latency of the dependent node chain
+// (profiles/r03_trace_layout_experiments.md).
 // Receiver deposits are aggregated across the warp (match.any) and accumulated in an fp64
 // histogram with native RED.F64, which makes the result independent of the deposit order
 // to ~1e-16.
@@ -41,17 +43,7 @@ constexpr int kSentinel = INT_MIN;   // "nothing (left) to traverse"
 constexpr int kRerenderThreads = 256;
 constexpr int kRerenderBatch = 12;   // lanes that must hold a candidate before the receiver walk
 
-#define ARV2_INF __int_as_float(0x7f800000)
-
 struct Hit { float t, u, v; int slot, id; };
-
-__device__ __forceinline__ void cswap(float& ta, int& ea, float& tb, int& eb)
-{
-    const bool s = tb < ta;
-    const float t0 = s ? tb : ta, t1 = s ? ta : tb;
-    const int e0 = s ? eb : ea, e1 = s ? ea : eb;
-    ta = t0; tb = t1; ea = e0; eb = e1;
-}
 
 // 256-bit read-only global load (sm_100+: LDG.E.ENL2.256.CONSTANT).
 struct __align__(32) F8 { float4 lo, hi; };
@@ -70,29 +62,13 @@ __device__ __forceinline__ float safe_rcp(float d)
     return 1.0f / (fabsf(d) > eps ? d : copysignf(eps, d));
 }
 
-// One half of a packed (lo | hi << 16) word -> 2^23 + q as a float: a single PRMT that
-// drops the 16 bits into the mantissa of 0x4B000000.  sel = 0x7610 (lo half) / 0x7632 (hi).
-__device__ __forceinline__ float qhalf(float word, unsigned sel)
-{
-    return __uint_as_float(__byte_perm(__float_as_uint(word), 0x4B000000u, sel));
-}
-
-// Per-segment, per-tree ray constants: t(plane q) = fma(2^23 + q, a, b) with
-//   a = cell / dir,  b = (origin - org) / dir - 2^23 * a;
-// the near / far plane of each axis is picked by the PRMT selector (sign of dir).
+// Per-segment ray constants of the slab test: t(plane) = plane * (1/dir) - org/dir.
 struct RayGrid {
-    float ax, ay, az, bx, by, bz;
-    unsigned nx, ny, nz;     // near selectors; far = near ^ 0x0022
-    __device__ __forceinline__ void setup(const float* origin, const float* cell, F3 org, F3 dir)
+    float ix, iy, iz, ox, oy, oz;
+    __device__ __forceinline__ void setup(F3 org, F3 dir)
     {
-        const float ix = safe_rcp(dir.x), iy = safe_rcp(dir.y), iz = safe_rcp(dir.z);
-        ax = cell[0] * ix; ay = cell[1] * iy; az = cell[2] * iz;
-        bx = fmaf(-8388608.f, ax, (origin[0] - org.x) * ix);
-        by = fmaf(-8388608.f, ay, (origin[1] - org.y) * iy);
-        bz = fmaf(-8388608.f, az, (origin[2] - org.z) * iz);
-        nx = ix < 0.f ? 0x7632u : 0x7610u;
-        ny = iy < 0.f ? 0x7632u : 0x7610u;
-        nz = iz < 0.f ? 0x7632u : 0x7610u;
+        ix = safe_rcp(dir.x); iy = safe_rcp(dir.y); iz = safe_rcp(dir.z);
+        ox = org.x * ix; oy = org.y * iy; oz = org.z * iz;
     }
 };
 
@@ -110,32 +86,34 @@ struct Traversal {
     __device__ __forceinline__ bool at_leaf() const { return cur < 0 && cur != kSentinel; }
     __device__ __forceinline__ bool finished() const { return cur == kSentinel; }
 
-    // one 4-wide node (two 256-bit loads): slab test of the four quantised child boxes,
-    // descend into the nearest hit child, push the others far-to-near
+    // one binary node (64 B = two 256-bit loads, both child boxes in the parent): slab tests,
+    // descend into the nearer hit child, push the other
     __device__ __forceinline__ void step_inner(int* stack, const float4* __restrict__ nodes, const RayGrid& g)
     {
-        const F8 A = ldg256(nodes + cur * 4), B = ldg256(nodes + cur * 4 + 2);
-        const unsigned fx = g.nx ^ 0x0022u, fy = g.ny ^ 0x0022u, fz = g.nz ^ 0x0022u;
-        float t0 = interval(A.lo.x, A.lo.y, A.lo.z, g, fx, fy, fz);
-        float t1 = interval(A.lo.w, A.hi.x, A.hi.y, g, fx, fy, fz);
-        float t2 = interval(A.hi.z, A.hi.w, B.lo.x, g, fx, fy, fz);
-        float t3 = interval(B.lo.y, B.lo.z, B.lo.w, g, fx, fy, fz);
-        int e0 = __float_as_int(B.hi.x), e1 = __float_as_int(B.hi.y), e2 = __float_as_int(B.hi.z), e3 = __float_as_int(B.hi.w);
-        cswap(t0, e0, t1, e1); cswap(t2, e2, t3, e3); cswap(t0, e0, t2, e2); cswap(t1, e1, t3, e3); cswap(t1, e1, t2, e2);
-        if (t3 < ARV2_INF) stack[sp++] = e3;
-        if (t2 < ARV2_INF) stack[sp++] = e2;
-        if (t1 < ARV2_INF) stack[sp++] = e1;
-        cur = t0 < ARV2_INF ? e0 : stack[--sp];
-    }
-
-    // entry distance of the ray into one quantised child box, +inf when it misses
-    __device__ __forceinline__ float interval(float wx, float wy, float wz, const RayGrid& g, unsigned fx, unsigned fy, unsigned fz) const
-    {
-        const float tn = fmaxf(fmaxf(fmaf(qhalf(wx, g.nx), g.ax, g.bx), fmaf(qhalf(wy, g.ny), g.ay, g.by)),
-                               fmaxf(fmaf(qhalf(wz, g.nz), g.az, g.bz), 0.f));
-        const float tf = fminf(fminf(fmaf(qhalf(wx, fx), g.ax, g.bx), fmaf(qhalf(wy, fy), g.ay, g.by)),
-                               fminf(fmaf(qhalf(wz, fz), g.az, g.bz), h.t));
-        return tn <= tf ? tn : ARV2_INF;
+        const F8 na = ldg256(nodes + cur * 4), nb = ldg256(nodes + cur * 4 + 2);
+        const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
+        const float c0lox = fmaf(n0.x, g.ix, -g.ox), c0hix = fmaf(n0.y, g.ix, -g.ox);
+        const float c0loy = fmaf(n0.z, g.iy, -g.oy), c0hiy = fmaf(n0.w, g.iy, -g.oy);
+        const float c0loz = fmaf(n2.x, g.iz, -g.oz), c0hiz = fmaf(n2.y, g.iz, -g.oz);
+        const float c1lox = fmaf(n1.x, g.ix, -g.ox), c1hix = fmaf(n1.y, g.ix, -g.ox);
+        const float c1loy = fmaf(n1.z, g.iy, -g.oy), c1hiy = fmaf(n1.w, g.iy, -g.oy);
+        const float c1loz = fmaf(n2.z, g.iz, -g.oz), c1hiz = fmaf(n2.w, g.iz, -g.oz);
+        const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.f));
+        const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
+        const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.f));
+        const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
+        const bool go0 = c0min <= c0max, go1 = c1min <= c1max;
+        const int i0 = __float_as_int(n3.x), i1 = __float_as_int(n3.y);
+        if (!go0 && !go1) {
+            cur = stack[--sp];
+        } else {
+            cur = go0 ? i0 : i1;
+            if (go0 && go1) {
+                int far = i1;
+                if (c1min < c0min) { cur = i1; far = i0; }
+                stack[sp++] = far;
+            }
+        }
     }
 
     // one leaf: exact tests of its <= 4 triangles
@@ -189,7 +167,7 @@ __device__ __forceinline__ void closest_hit(const TraceParams& p, int* stack, Tr
     tr.reset(tmax);
     if (root < 0) return;
     RayGrid g;
-    g.setup(p.g_origin, p.g_cell, org, dir);
+    g.setup(org, dir);
     tr.walk(stack, p.nodes, p.tris, root, g, org, dir);
 }
 
@@ -471,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace2_kernel(const Trace
     Traversal tr;
     tr.reset(1e20f);
     RayGrid g;
-    g.ax = g.ay = g.az = g.bx = g.by = g.bz = 0.f; g.nx = g.ny = g.nz = 0x7610u;
+    g.ix = g.iy = g.iz = g.ox = g.oy = g.oz = 0.f;
     int stack[kStack];
 
     for (;;) {
@@ -507,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace2_kernel(const Trace
                 const bool to_recv = MODE == 0 && p.recv_root >= 0 && enters_receiver_ball(p, s.org, s.dir, 1e20f);
                 const int root = to_recv ? p.root : p.scene_root;
                 if (root >= 0) {
-                    g.setup(p.g_origin, p.g_cell, s.org, s.dir);
+                    g.setup(s.org, s.dir);
                     tr.enter(stack, root);
                 }
             }

@@ -9,7 +9,7 @@ namespace arv2 {
 // Everything one render needs, passed by value as the kernel parameter
 // (the role of LaunchParams, OR/LaunchParams.h:20-43).
 struct TraceParams {
-    const float4* nodes;        // 32 B quantised nodes: [top][scene tree][receiver tree] (arv2_internal.h)
+    const float4* nodes;        // 64 B binary nodes: [top][scene tree][receiver tree] (arv2_internal.h)
     const float4* tris;         // 64 B triangle records, leaf order
     const float* keep;          // [n_mats][bands]  1 - mat_absorption
     const float* scattering;    // [n_mats]
@@ -31,7 +31,6 @@ struct TraceParams {
     int delay, ir_len, mono;
     int root;                   // node the full trace starts at (0 = two-level top node)
     int scene_root, recv_root;  // roots of the two sub-trees (-1: absent)
-    float g_origin[3], g_cell[3];     // quantisation grid shared by all nodes
     int any_scatter;            // 0: skip the diffuse-bounce RNG entirely
 };
 
