@@ -102,6 +102,7 @@ SYMBOLS = {
     "arv2_ir_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "arv2_hist_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "arv2_last_segments": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "arv2_last_upload_bytes": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "arv2_get_records": (C.c_int, [_vp, _ip, _ip, _fp, _ip]),
     "arv2_write_ir_text": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
     "arv2_convolve_file": (C.c_int, [_vp, _fp, C.c_size_t, _fp, _fp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -368,6 +369,11 @@ class AudioRenderer:
         s = C.c_int64()
         _check(lib().arv2_last_segments(self._h, C.byref(s)))
         return s.value
+
+    def last_upload_bytes(self):
+        b = C.c_int64()
+        _check(lib().arv2_last_upload_bytes(self._h, C.byref(b)))
+        return b.value
 
     def records(self, n_rays=None):
         n = self.n_rays if n_rays is None else n_rays

@@ -687,6 +687,13 @@ int arv2_hist_device(arv2_ctx* c, double** h, int64_t* count)
     return ARV2_OK;
 }
 
+int arv2_last_upload_bytes(arv2_ctx* c, int64_t* bytes)
+{
+    REQUIRE(c && bytes, "null argument");
+    *bytes = (int64_t)c->upload_bytes;
+    return ARV2_OK;
+}
+
 int arv2_last_segments(arv2_ctx* c, int64_t* segs)
 {
     REQUIRE(c && segs, "null argument");

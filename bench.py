@@ -35,7 +35,23 @@ EMITTER = (2.0, 1.5, 2.0)
 RECEIVER = (9.0, 1.4, 5.5)
 YAW = 30.0
 SEED = 7
+BANDS = 1
 BYTES_PER_SEGMENT = 17 * 64 + 4 * 36 + 64      # 1296 B for T ~ 332k
+WORKLOAD = "c2"
+
+
+def select_workload(name):
+    """c2 = BASELINE configs[1] (the default and the only driver-facing line);
+    c4 = configs[3]: synthetic 1M-triangle hall, 8 frequency bands, 10M rays per GPU."""
+    global RAYS, EMITTER, RECEIVER, SEED, BANDS, BYTES_PER_SEGMENT, WORKLOAD
+    WORKLOAD = name
+    if name == "c4":
+        RAYS = (1000, 100, 100)
+        EMITTER = (8.0, 1.6, 15.0)
+        RECEIVER = (30.0, 1.6, 15.0)
+        SEED = 11
+        BANDS = 8
+        BYTES_PER_SEGMENT = 19 * 64 + 4 * 36 + 64 + 56      # 1480 B
 
 
 def log(*a):
@@ -92,6 +108,9 @@ class ClockSampler:
 
 def scene_case():
     from audiorenderingv2_b200 import scenes
+    if WORKLOAD == "c4":
+        tv, tm, names = scenes.atrium()
+        return tv, tm, names, scenes.materials(bands=8)
     tv, tm, names = scenes.conference_room()
     return tv, tm, names, scenes.materials()
 
@@ -100,7 +119,11 @@ def oracle_flat(tv, tm, names, mats, recv):
     import oracle  # noqa: F401  (cpu_baseline / --impl reference only)
     from oracle import scene as osc
     model = osc.Model(meshes=[osc.Mesh(names[i], np.ascontiguousarray(tv[tm == i])) for i in range(len(names))])
-    flat = osc.flatten(model, osc.ReceiverTemplate(*recv), RECEIVER, YAW, [(m[0], m[1]) for m in mats])
+    flat = osc.flatten(model, osc.ReceiverTemplate(*recv), RECEIVER, YAW, [], bands=BANDS)
+    lut = {m[0]: m[1] for m in mats}
+    for i, n in enumerate(names):
+        a = lut[n]
+        flat.absorption[i, :] = np.array(a if isinstance(a, (list, tuple)) else [a] * BANDS, np.float32)
     return flat
 
 
@@ -110,9 +133,9 @@ def cpu_port_rate(n_total_rays, budget_s, chunk):
     import oracle
     tv, tm, names, mats = scene_case()
     flat = oracle_flat(tv, tm, names, mats, load_receiver())
-    prep = oracle.PreparedScene(flat)            # BVH build untimed (as on the GPU side)
+    prep = oracle.PreparedScene(flat, bands=BANDS)            # BVH build untimed (as on the GPU side)
     p = oracle.make_params(rays=(n_total_rays, 1, 1), emitter=EMITTER, sphere_center=RECEIVER, base_power=100.0,
-                           max_bounces=MAX_BOUNCES, hrtf=0.9, sample_rate=FS, ir_length=IR_SECONDS * FS, seed=SEED)
+                           max_bounces=MAX_BOUNCES, hrtf=0.9, sample_rate=FS, ir_length=IR_SECONDS * FS, bands=BANDS, seed=SEED)
     cores = os.cpu_count() or 1
     segs, rays, t = 0, 0, 0.0
     while t < budget_s and rays + chunk <= n_total_rays:
@@ -134,9 +157,9 @@ def run_reference(args):
     import oracle
     tv, tm, names, mats = scene_case()
     flat = oracle_flat(tv, tm, names, mats, load_receiver())
-    prep = oracle.PreparedScene(flat)
+    prep = oracle.PreparedScene(flat, bands=BANDS)
     p = oracle.make_params(rays=(n_total, 1, 1), emitter=EMITTER, sphere_center=RECEIVER, base_power=100.0,
-                           max_bounces=MAX_BOUNCES, hrtf=0.9, sample_rate=FS, ir_length=IR_SECONDS * FS, seed=SEED)
+                           max_bounces=MAX_BOUNCES, hrtf=0.9, sample_rate=FS, ir_length=IR_SECONDS * FS, bands=BANDS, seed=SEED)
     cores = os.cpu_count() or 1
     for i in range(args.warmup):
         prep.trace(p, 0, 20_000, n_threads=cores)
@@ -160,10 +183,14 @@ def run_reference(args):
 
 
 def workload_config(n_gpus):
-    return {"workload": "configs[1]: conference-scale room (procedural stand-in, 331004 triangles + 1020 receiver), "
-                        "1M rays per GPU, 50 bounces, 2 s IR @48 kHz",
+    desc = ("configs[1]: conference-scale room (procedural stand-in, 331004 triangles + 1020 receiver), "
+            "1M rays per GPU, 50 bounces, 2 s IR @48 kHz")
+    if WORKLOAD == "c4":
+        desc = ("configs[3]: synthetic 1M-triangle hall (1048584 triangles + 1020 receiver), 8 frequency bands, "
+                "10M rays per GPU, 50 bounces, 2 s IR @48 kHz")
+    return {"workload": desc,
             "rays_per_gpu": RAYS[0] * RAYS[1] * RAYS[2], "total_rays": RAYS[0] * RAYS[1] * RAYS[2] * n_gpus,
-            "max_bounces": MAX_BOUNCES, "sample_rate": FS, "ir_seconds": IR_SECONDS, "bands": 1,
+            "max_bounces": MAX_BOUNCES, "sample_rate": FS, "ir_seconds": IR_SECONDS, "bands": BANDS,
             "parallelism": f"ray-range sharding x{n_gpus}, NCCL all-reduce of the fp64 IR histogram",
             "l2": "flushed between timed steps (512 MiB write)"}
 
@@ -176,7 +203,9 @@ def main():
     ap.add_argument("--impl", default="arv2", choices=["arv2", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-extras", action="store_true", help="skip the re-render and convolution sub-metrics")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2 = BASELINE configs[1] (default), c4 = configs[3]")
     args = ap.parse_args()
+    select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "arv2" else args.warmup
 
     if args.impl == "reference":
@@ -204,7 +233,7 @@ def main():
     receiver = arv.Receiver.from_triangles(*recv)
     t_build = time.perf_counter()
     # the seeded ray set has total_rays rays; this rank traces [rank*per_gpu, (rank+1)*per_gpu)
-    r = arv.AudioRenderer(scene, IR_SECONDS, FS, mats, (total_rays, 1, 1), receiver=receiver, device=local)
+    r = arv.AudioRenderer(scene, IR_SECONDS, FS, mats, (total_rays, 1, 1), receiver=receiver, device=local, bands=BANDS)
     t_build = time.perf_counter() - t_build
     r.setBasePower(100.0); r.setThresholds(0.0, MAX_BOUNCES); r.set_hrtf_absorption_rate(0.9)
     r.setEmitterPosInOptix(EMITTER); r.setSphereCenterInOptix(RECEIVER, YAW); r.set_seed(SEED)
@@ -263,7 +292,7 @@ def main():
         # ---- e2e: the call a user of the reference makes (full_render_cycle minus the
         # convolution): move the receiver (host -> device upload of its sub-tree), render,
         # read both IRs back to host memory.
-        ir_bytes = 2 * r.ir_length * 4
+        ir_bytes = 2 * BANDS * r.ir_length * 4
         e2e_ms, e2e_segs = [], 0
         for k in range(args.steps):
             flush.fill_(1)
@@ -292,7 +321,7 @@ def main():
         pass
 
     extras = {}
-    if not args.skip_extras:
+    if not args.skip_extras and WORKLOAD == "c2":
         extras.update(bench_rerender(arv, torch, dev, local, scene, receiver, mats, args))
         extras.update(bench_conv(arv, torch, dist, dev, local, rank, world, args))
         extras.update(bench_lbvh(arv, scene, receiver, mats, local))
@@ -303,11 +332,11 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "segments_per_step": total_segs / args.steps, "paths_per_s": total_rays * args.steps / (total_ms * 1e-3),
         "bvh_build_s": t_build,
-        "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": 16 * (4 + 4 * 1020 + 3 * 1020),
+        "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": r.last_upload_bytes(),
                 "d2h_bytes_per_step": ir_bytes + 16, "ms_per_step": float(t_e2e.sum().item()) / args.steps},
         "gpu_launches": 2 * args.steps,
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "trace_kernel<1,0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": f"trace_kernel<{BANDS},0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "bytes_per_segment": BYTES_PER_SEGMENT, "kernel_ms": kernel_ms},
     }

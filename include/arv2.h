@@ -183,6 +183,8 @@ int arv2_set_ir(arv2_ctx* ctx, const float* ir_left, const float* ir_right);/* H
 int arv2_ir_device(arv2_ctx* ctx, float** d_left, float** d_right);
 /* fp64 accumulation histogram double[2][bands][ir_length] (device pointer). */
 int arv2_hist_device(arv2_ctx* ctx, double** d_hist, int64_t* count);
+/* Host->device bytes of the last receiver placement (top node + receiver tree + triangles). */
+int arv2_last_upload_bytes(arv2_ctx* ctx, int64_t* bytes);
 /* Segments (closest-hit queries) traced by the last render on this context. */
 int arv2_last_segments(arv2_ctx* ctx, int64_t* segments);
 /* Per-ray records of the last render (desc.record_rays): arrays of n_rays entries
