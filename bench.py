@@ -64,46 +64,59 @@ def load_receiver():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), sampled
+    through NVML every few ms from a thread (nvidia-smi -lms cannot start fast enough for a
+    50 ms region); falls back to one nvidia-smi query when NVML is unavailable."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.rows = []
-        self.proc = None
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.index = index
+        self.sm, self.bits = [], 0
+        self.stop_flag = False
+        self.h = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._run, daemon=True)
             self.th.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.bits |= int(fn(self.h))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.h is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1.0)
+            if self.sm:
+                return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max,
+                        "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b), "samples": len(self.sm)}
         try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]),
+                    "reasons": [n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")],
+                    "samples": 1, "note": "single nvidia-smi query right after the timed region"}
+        except Exception as e:       # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"clock query unavailable: {e}"], "samples": 0}
 
 
 def scene_case():
