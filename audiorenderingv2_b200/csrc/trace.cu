@@ -20,6 +20,7 @@
 // histogram with native RED.F64, which makes the result independent of the deposit order
 // to ~1e-16.
 #include <climits>
+#include <cstdlib>
 
 #include "arv2_internal.h"
 #include "arv2_model.cuh"
@@ -36,7 +37,7 @@ constexpr int kStack = kTraversalStack;
 #define ARV2_THREADS 128
 #endif
 #ifndef ARV2_MINB
-#define ARV2_MINB 8
+#define ARV2_MINB 6
 #endif
 constexpr int kThreads = ARV2_THREADS;
 constexpr int kSentinel = INT_MIN;   // "nothing (left) to traverse"
@@ -608,6 +609,7 @@ cudaError_t launch_trace_t(const TraceParams& p, int sm_count, cudaStream_t stre
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    if (const char* cap = getenv("ARV2_CTAS_PER_SM")) { const int v = atoi(cap); if (v > 0 && v < per_sm) per_sm = v; }   // tuning aid
     long long want = (p.n_rays + kThreads - 1) / kThreads;
     long long grid = (long long)sm_count * per_sm;
     if (want < grid) grid = want < 1 ? 1 : want;
