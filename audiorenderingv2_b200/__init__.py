@@ -113,6 +113,16 @@ SYMBOLS = {
     "arv2_stream_process_device": (C.c_int, [_vp, _vp, _vp, _vp]),
     "arv2_stream_reset": (C.c_int, [_vp]),
     "arv2_stream_close": (None, [_vp]),
+    "arv2_global_angle": (C.c_float, [C.c_float, C.c_float]),
+    "arv2_policy_create": (C.c_int, [C.c_float, C.c_float, _fp, C.c_float, C.POINTER(_vp)]),
+    "arv2_policy_update": (C.c_int, [_vp, _fp, C.c_float, C.c_double, C.c_int32]),
+    "arv2_policy_destroy": (None, [_vp]),
+    "arv2_playback_fill": (C.c_int64, [C.POINTER(C.c_double), C.c_uint32, C.c_double, C.c_int32, _fp, _fp, C.c_size_t, C.c_size_t, C.c_float]),
+    "arv2_ring_create": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "arv2_ring_add": (C.c_int, [_vp, C.POINTER(C.c_double), C.c_size_t]),
+    "arv2_ring_get_and_reset": (C.c_int, [_vp, C.POINTER(C.c_double), C.c_size_t]),
+    "arv2_ring_destroy": (None, [_vp]),
+    "arv2_live_callback": (C.c_int, [_vp, C.POINTER(C.c_double), C.c_size_t, _vp]),
     "arv2_wav_read": (C.c_int, [C.c_char_p, C.POINTER(_fp), C.POINTER(C.c_size_t), _ip, _ip]),
     "arv2_wav_write_stereo_normalized": (C.c_int, [C.c_char_p, _fp, _fp, C.c_size_t, C.c_int32]),
     "arv2_free": (None, [_vp]),
@@ -436,6 +446,66 @@ class ConvStream:
             self._h = None
 
     __del__ = close
+
+
+def global_angle(orientation_x, orientation_z):
+    """Camera::calculate_global_angle (OR/Camera.cpp:31-41)."""
+    return lib().arv2_global_angle(float(orientation_x), float(orientation_z))
+
+
+class RerenderPolicy:
+    """Re-render trigger of the GL loop (OR/main.cpp:470-498)."""
+
+    def __init__(self, distance_threshold, angle_threshold_deg, start_pos, start_angle_deg):
+        self._h = _vp()
+        p = np.ascontiguousarray(start_pos, dtype=np.float32)
+        _check(lib().arv2_policy_create(float(distance_threshold), float(angle_threshold_deg), _f(p), float(start_angle_deg), C.byref(self._h)))
+
+    def update(self, pos, angle_deg, now_s, is_rendering=False):
+        p = np.ascontiguousarray(pos, dtype=np.float32)
+        return bool(lib().arv2_policy_update(self._h, _f(p), float(angle_deg), float(now_s), 1 if is_rendering else 0))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.arv2_policy_destroy(self._h)
+            self._h = None
+
+
+def playback_fill(n_frames, stream_time, sample_rate, left, right, output_buffer_len, volume=1.0):
+    """audioHandler (OR/main.cpp:69-97): one interleaved RTAUDIO_FLOAT64 callback buffer."""
+    l = np.ascontiguousarray(left, dtype=np.float32); r = np.ascontiguousarray(right, dtype=np.float32)
+    out = np.zeros(2 * n_frames, np.float64)
+    n = lib().arv2_playback_fill(out.ctypes.data_as(C.POINTER(C.c_double)), int(n_frames), float(stream_time), int(sample_rate),
+                                 _f(l), _f(r), l.size, int(output_buffer_len), float(volume))
+    return out, int(n)
+
+
+class Ring:
+    """CircularBuffer<double> (OR/CircularBuffer.h)."""
+
+    def __init__(self, size):
+        self._h = _vp()
+        _check(lib().arv2_ring_create(int(size), C.byref(self._h)))
+
+    def add(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        _check(lib().arv2_ring_add(self._h, v.ctypes.data_as(C.POINTER(C.c_double)), v.size))
+
+    def get_and_reset(self, n):
+        out = np.empty(n, np.float64)
+        _check(lib().arv2_ring_get_and_reset(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), int(n)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.arv2_ring_destroy(self._h)
+            self._h = None
+
+
+def live_callback(stream: "ConvStream", samples, ring: Ring):
+    """audioHandlerWithMic + convoluteLiveInput for one block of mic samples."""
+    x = np.ascontiguousarray(samples, dtype=np.float64)
+    _check(lib().arv2_live_callback(stream._h, x.ctypes.data_as(C.POINTER(C.c_double)), x.size, ring._h))
 
 
 def wav_read(path):

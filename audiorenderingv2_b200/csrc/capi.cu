@@ -912,6 +912,26 @@ void arv2_stream_close(arv2_stream* s)
     delete s;
 }
 
+// audioHandlerWithMic + convoluteLiveInput (OR/main.cpp:99-135, OR/AudioRenderer.cpp:593-661)
+int arv2_live_callback(arv2_stream* s, const double* in, size_t n_in, arv2_ring* ring)
+{
+    REQUIRE(s && in && ring, "arv2_live_callback: null argument");
+    REQUIRE(s->n_src == 1, "arv2_live_callback needs a 1-source stream");
+    REQUIRE(n_in % (size_t)s->block == 0, "n_in must be a multiple of the stream block");
+    std::vector<float> x((size_t)s->block), y((size_t)2 * s->block);
+    std::vector<double> zipped(2 * n_in);
+    for (size_t b = 0; b < n_in / (size_t)s->block; ++b) {
+        for (int i = 0; i < s->block; ++i) x[i] = (float)in[b * s->block + i];
+        const int rc = arv2_stream_process(s, x.data(), y.data());
+        if (rc != ARV2_OK) return rc;
+        for (int i = 0; i < s->block; ++i) {                     // gain 1/(ir_len/2) of the reference = 2x, then d_zipArrays
+            zipped[2 * (b * s->block + i)] = 2.0 * (double)y[i];
+            zipped[2 * (b * s->block + i) + 1] = 2.0 * (double)y[s->block + i];
+        }
+    }
+    return arv2_ring_add(ring, zipped.data(), zipped.size());
+}
+
 /* ------------------------------------------------------------------ audio -- */
 int arv2_wav_read(const char* path, float** samples, size_t* n, int32_t* sample_rate, int32_t* channels)
 {

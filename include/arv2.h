@@ -229,6 +229,46 @@ int arv2_stream_process_device(arv2_stream* s, const float* d_in, float* d_out, 
 int arv2_stream_reset(arv2_stream* s);
 void arv2_stream_close(arv2_stream* s);
 
+/* ------------------------------------------------- playback / re-render policy -- */
+/* Camera::calculate_global_angle (OR/Camera.cpp:31-41): degrees(atan2(o.z, o.x)) in
+ * [0, 360); the receiver is rotated by -angle about +Y (OR/OptixModel.cpp:178-181). */
+float arv2_global_angle(float orientation_x, float orientation_z);
+
+/* Re-render trigger of the GL loop (OR/main.cpp:470-498): a re-render starts when the
+ * receiver moved more than distance_threshold since the last render, or turned more than
+ * angle_threshold degrees (shortest arc), or more than 1 s (whole seconds, like time())
+ * passed since the first movement after the last render -- and none is in flight. */
+typedef struct arv2_rerender_policy arv2_rerender_policy;
+int arv2_policy_create(float distance_threshold, float angle_threshold_deg, const float start_pos[3],
+                       float start_angle_deg, arv2_rerender_policy** out);
+/* Returns 1 when a re-render must be started now (and records pos / angle as its origin),
+ * 0 otherwise.  now_s = wall clock in seconds; is_rendering = a render is still in flight. */
+int arv2_policy_update(arv2_rerender_policy* p, const float pos[3], float angle_deg, double now_s, int32_t is_rendering);
+void arv2_policy_destroy(arv2_rerender_policy* p);
+
+/* audioHandler (OR/main.cpp:69-97): fill one RtAudio callback (RTAUDIO_FLOAT64, interleaved
+ * LRLR, n_frames frames) from the convolved file buffers.  Reproduces the reference's
+ * indexing: position = (int)(stream_time * sample_rate) % n_samples, then for i in
+ * [0, 2*n_frames): out[i] = (i even ? left : right)[i + position] * 100 * volume, stopping
+ * at output_buffer_len (which the reference sets in BYTES, OR/main.cpp:51,85).
+ * Returns the number of doubles written. */
+int64_t arv2_playback_fill(double* out, uint32_t n_frames, double stream_time, int32_t sample_rate,
+                           const float* left, const float* right, size_t n_samples,
+                           size_t output_buffer_len, float volume);
+
+/* CircularBuffer<double> of the live path (OR/CircularBuffer.h): add() overlap-adds at the
+ * read position without advancing, get_and_reset() pops n values, zeroing them. */
+typedef struct arv2_ring arv2_ring;
+int arv2_ring_create(size_t size, arv2_ring** out);
+int arv2_ring_add(arv2_ring* r, const double* values, size_t n);
+int arv2_ring_get_and_reset(arv2_ring* r, double* out, size_t n);   /* ARV2_ERR_INVALID if n > size */
+void arv2_ring_destroy(arv2_ring* r);
+/* One mic callback (audioHandlerWithMic + convoluteLiveInput, OR/main.cpp:99-135,
+ * OR/AudioRenderer.cpp:593-661) on a 1-source stream convolver: n_in samples (a multiple of
+ * the stream's block) are convolved block by block, scaled by the reference's gain 2,
+ * interleaved LRLR and overlap-added into the ring. */
+int arv2_live_callback(arv2_stream* s, const double* in, size_t n_in, arv2_ring* ring);
+
 /* ------------------------------------------------------------------ audio -- */
 /* AudioFile<float>::load as used by Context.cpp:198-213: channel 0 only, int16 ->
  * x/32768, float32 passthrough.  *samples is malloc'd; free with arv2_free. */

@@ -142,3 +142,20 @@ def test_live_reference_semantics():
     out = np.concatenate([st.process(xin[k * 512:(k + 1) * 512]) for k in range(nb)], axis=2)
     assert rel_l2(2.0 * out[0, 0], ref[0:2 * nb * 512:2]) <= TOL
     assert rel_l2(2.0 * out[0, 1], ref[1:2 * nb * 512:2]) <= TOL
+
+
+def test_live_callback_fills_ring_like_the_reference():
+    """audioHandlerWithMic -> convoluteLiveInput -> CircularBuffer (OR/main.cpp:99-135): after one
+    4096-sample callback the ring holds the interleaved, 2x-gain convolution of the block; popping
+    nFrames*2 values gives what the reference would hand to RtAudio (no wrap: 4096 + support <= ir_len)."""
+    fs, ir_len = 44100, 44100
+    hl = np.zeros(ir_len, np.float32); hl[:3000] = decaying_ir(3000, 5, 0.02, fs)
+    hr = np.zeros(ir_len, np.float32); hr[:2000] = decaying_ir(2000, 6, 0.02, fs)
+    x = np.random.default_rng(8).standard_normal(4096)
+    st = arv.ConvStream(1, 512, ir_len)
+    st.set_ir(0, hl, hr)
+    ring = arv.Ring(2 * ir_len)
+    arv.live_callback(st, x, ring)
+    got = ring.get_and_reset(2 * 4096)
+    ref = oracle.reference_live_conv(x, hl, hr)[: 2 * 4096]
+    assert rel_l2(got, ref) <= TOL

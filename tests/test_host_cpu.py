@@ -185,3 +185,57 @@ def test_ray_range_partition():
                 assert b0 + c0 == b1
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
     assert sharding.sources_of(1, 8, 16) == [1, 9] and sum(len(sharding.sources_of(r, 3, 16)) for r in range(3)) == 16
+
+
+# ----------------------------------------------------- callers either side of the path (8f rows 3-4)
+def test_global_angle_convention():
+    """Camera::calculate_global_angle: degrees(atan2(z, x)) in [0, 360) (OR/Camera.cpp:31-41)."""
+    assert arv.global_angle(1, 0) == 0.0
+    assert arv.global_angle(0, 1) == pytest.approx(90.0)
+    assert arv.global_angle(-1, 0) == pytest.approx(180.0)
+    assert arv.global_angle(0, -1) == pytest.approx(270.0)
+    assert 0.0 <= arv.global_angle(0.3, -0.0001) < 360.0
+
+
+def test_rerender_policy_matches_main_loop():
+    """OR/main.cpp:470-498: distance > threshold, shortest-arc angle > threshold, or > 1 s
+    (whole seconds) after the first movement; never while a render is in flight."""
+    p = arv.RerenderPolicy(2.0, 5.0, (0, 0, 0), 350.0)
+    assert not p.update((0, 0, 0), 350.0, 100.0)                 # nothing moved
+    assert not p.update((1.9, 0, 0), 350.0, 100.2)               # below the distance threshold, timer starts
+    assert not p.update((1.9, 0, 0), 350.0, 101.9)               # difftime(101, 100) = 1, not > 1
+    assert p.update((1.9, 0, 0), 350.0, 102.0)                   # 2 whole seconds later
+    assert not p.update((1.9, 0, 0), 350.0, 102.1)               # origin moved to the last render
+    assert p.update((1.9, 0, 2.1), 350.0, 102.2)                 # distance
+    assert not p.update((1.9, 0, 2.1), 354.0, 102.3)             # 4 degrees
+    assert p.update((1.9, 0, 2.1), 2.0, 102.4)                   # 350 -> 2 = 12 degrees over the wrap
+    assert not p.update((1.9, 0, 2.1), 10.0, 102.5, is_rendering=True)   # 8 degrees, but a render is in flight
+    assert p.update((1.9, 0, 2.1), 10.0, 102.6)
+
+
+def test_playback_callback_contract():
+    """audioHandler (OR/main.cpp:69-97): interleaved LRLR doubles, x100 x volume, position from
+    streamTime modulo the file length, the reference's i + position indexing."""
+    n = 1000
+    l = np.arange(n, dtype=np.float32); r = -np.arange(n, dtype=np.float32)
+    out, w = arv.playback_fill(4, 0.0105, 16000, l, r, output_buffer_len=4 * n, volume=0.5)
+    pos = int(0.0105 * 16000) % n
+    assert w == 8
+    exp = [(l if i % 2 == 0 else r)[i + pos] * 100 * 0.5 for i in range(8)]
+    assert np.allclose(out, exp)
+    out, w = arv.playback_fill(256, 0.0, 16000, l, r, output_buffer_len=100, volume=1.0)   # stops at output_buffer_len
+    assert w == 100
+    out, w = arv.playback_fill(4, (n + 3.5) / 16000.0, 16000, l, r, output_buffer_len=4 * n)  # wraps modulo the length
+    assert out[0] == l[3] * 100
+
+
+def test_ring_is_the_reference_circular_buffer():
+    """OR/CircularBuffer.h: add() overlap-adds without advancing, get_and_reset() pops + zeroes."""
+    ring = arv.Ring(8)
+    ring.add([1, 2, 3, 4, 5])
+    ring.add([10, 20])
+    assert list(ring.get_and_reset(3)) == [11, 22, 3]
+    ring.add([1, 1, 1, 1, 1, 1, 1])                 # wraps around the end
+    assert list(ring.get_and_reset(8)) == [5, 6, 1, 1, 1, 1, 1, 0]
+    with pytest.raises(arv.Arv2Error):
+        ring.get_and_reset(9)
