@@ -138,55 +138,87 @@ inline void consider(Hit& best, float t, float u, float v, int64_t id)
 }
 
 /* ---------------------------------------------------------------- BVH ---- */
-/* The oracle's own accelerator: median-split binary BVH over triangle
- * centroids, leaves of <= 4, boxes padded so that the float slab test never
- * rejects a box whose triangle the exact test would accept. Independent of the
- * product's builders; it cannot change results, only speed. */
-struct Node { float lo[3], hi[3]; int32_t left, right, first, count; };
+/* The oracle's own accelerator: binned-SAH binary BVH over triangle centroids, leaves of
+ * <= 4, front-to-back descent by the sign of the ray on the split axis, boxes padded so that
+ * the float slab test never rejects a box whose triangle the exact test would accept.
+ * Written independently of the product's builders; it cannot change results, only speed. */
+struct Node { float lo[3], hi[3]; int32_t left, right, first, count, axis; };
 
 struct Bvh {
     std::vector<Node> nodes;
     std::vector<int64_t> order;
 };
 
-void build_rec(Bvh& b, const std::vector<Tri>& tris, std::vector<V3>& cen, int node, int64_t first, int64_t count)
+struct TriBox { float lo[3], hi[3], c[3]; };
+
+void build_rec(Bvh& b, const std::vector<TriBox>& tb, float pad, int node, int64_t first, int64_t count)
 {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int64_t i = first; i < first + count; ++i) {
-        const Tri& t = tris[b.order[i]];
-        const float vx[3][3] = {{t.p1.x, t.p1.y, t.p1.z},
-                                {t.p1.x + t.e1.x, t.p1.y + t.e1.y, t.p1.z + t.e1.z},
-                                {t.p1.x + t.e2.x, t.p1.y + t.e2.y, t.p1.z + t.e2.z}};
-        for (int k = 0; k < 3; ++k)
-            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], vx[k][a]); hi[a] = std::max(hi[a], vx[k][a]); }
-        const V3 c = cen[b.order[i]];
-        const float ca[3] = {c.x, c.y, c.z};
-        for (int a = 0; a < 3; ++a) { clo[a] = std::min(clo[a], ca[a]); chi[a] = std::max(chi[a], ca[a]); }
+        const TriBox& t = tb[b.order[i]];
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], t.lo[a]); hi[a] = std::max(hi[a], t.hi[a]);
+            clo[a] = std::min(clo[a], t.c[a]); chi[a] = std::max(chi[a], t.c[a]);
+        }
     }
-    float ext = 0.f;
-    for (int a = 0; a < 3; ++a) ext = std::max(ext, std::max(std::fabs(lo[a]), std::fabs(hi[a])));
-    const float pad = ext * 1e-5f + 1e-6f;
     Node n;
     for (int a = 0; a < 3; ++a) { n.lo[a] = lo[a] - pad; n.hi[a] = hi[a] + pad; }
-    n.left = n.right = -1; n.first = (int32_t)first; n.count = (int32_t)count;
-    if (count > 4) {
-        int axis = 0;
-        if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
-        if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
-        const int64_t mid = first + count / 2;
-        auto key = [&](int64_t id) { const V3 c = cen[id]; return axis == 0 ? c.x : axis == 1 ? c.y : c.z; };
-        std::nth_element(b.order.begin() + first, b.order.begin() + mid, b.order.begin() + first + count,
-                         [&](int64_t a, int64_t c) { return key(a) < key(c); });
-        n.count = 0;
-        n.left = (int32_t)b.nodes.size(); b.nodes.emplace_back();
-        n.right = (int32_t)b.nodes.size(); b.nodes.emplace_back();
-        b.nodes[node] = n;
-        build_rec(b, tris, cen, n.left, first, mid - first);
-        build_rec(b, tris, cen, n.right, mid, first + count - mid);
-        return;
+    n.left = n.right = -1; n.first = (int32_t)first; n.count = (int32_t)count; n.axis = 0;
+    if (count <= 4) { b.nodes[node] = n; return; }
+
+    /* binned surface-area heuristic, 12 bins per axis */
+    const int NB = 12;
+    float best = INFINITY; int best_axis = -1, best_bin = -1;
+    auto half_area = [](const float* l, const float* h) {
+        const float x = h[0] - l[0], y = h[1] - l[1], z = h[2] - l[2];
+        return (x >= 0 && y >= 0 && z >= 0) ? x * y + y * z + z * x : 0.f;
+    };
+    for (int a = 0; a < 3; ++a) {
+        const float ext = chi[a] - clo[a];
+        if (!(ext > 0.f)) continue;
+        float blo[NB][3], bhi[NB][3]; int cnt[NB];
+        for (int k = 0; k < NB; ++k) { cnt[k] = 0; for (int d = 0; d < 3; ++d) { blo[k][d] = INFINITY; bhi[k][d] = -INFINITY; } }
+        for (int64_t i = first; i < first + count; ++i) {
+            const TriBox& t = tb[b.order[i]];
+            int k = std::min(NB - 1, std::max(0, (int)((t.c[a] - clo[a]) / ext * NB)));
+            cnt[k]++;
+            for (int d = 0; d < 3; ++d) { blo[k][d] = std::min(blo[k][d], t.lo[d]); bhi[k][d] = std::max(bhi[k][d], t.hi[d]); }
+        }
+        float rarea[NB]; int rcnt[NB];
+        float al[3] = {INFINITY, INFINITY, INFINITY}, ah[3] = {-INFINITY, -INFINITY, -INFINITY}; int c = 0;
+        for (int k = NB - 1; k > 0; --k) {
+            for (int d = 0; d < 3; ++d) { al[d] = std::min(al[d], blo[k][d]); ah[d] = std::max(ah[d], bhi[k][d]); }
+            c += cnt[k]; rarea[k] = half_area(al, ah); rcnt[k] = c;
+        }
+        for (int d = 0; d < 3; ++d) { al[d] = INFINITY; ah[d] = -INFINITY; }
+        c = 0;
+        for (int k = 0; k < NB - 1; ++k) {
+            for (int d = 0; d < 3; ++d) { al[d] = std::min(al[d], blo[k][d]); ah[d] = std::max(ah[d], bhi[k][d]); }
+            c += cnt[k];
+            if (c == 0 || rcnt[k + 1] == 0) continue;
+            const float cost = half_area(al, ah) * c + rarea[k + 1] * rcnt[k + 1];
+            if (cost < best) { best = cost; best_axis = a; best_bin = k; }
+        }
     }
+    int64_t mid;
+    if (best_axis >= 0) {
+        const int a = best_axis; const float ext = chi[a] - clo[a], base = clo[a];
+        auto it = std::partition(b.order.begin() + first, b.order.begin() + first + count, [&](int64_t id) {
+            return std::min(NB - 1, std::max(0, (int)((tb[id].c[a] - base) / ext * NB))) <= best_bin;
+        });
+        mid = it - b.order.begin();
+        n.axis = a;
+    } else {
+        mid = first + count / 2;
+    }
+    if (mid == first || mid == first + count) mid = first + count / 2;
+    n.count = 0;
+    n.left = (int32_t)b.nodes.size(); b.nodes.emplace_back();
+    n.right = (int32_t)b.nodes.size(); b.nodes.emplace_back();
     b.nodes[node] = n;
+    build_rec(b, tb, pad, n.left, first, mid - first);
+    build_rec(b, tb, pad, n.right, mid, first + count - mid);
 }
 
 Bvh build_bvh(const std::vector<Tri>& tris)
@@ -194,16 +226,27 @@ Bvh build_bvh(const std::vector<Tri>& tris)
     Bvh b;
     const int64_t T = (int64_t)tris.size();
     b.order.resize(T);
-    std::vector<V3> cen(T);
+    std::vector<TriBox> tb(T);
+    float ext = 0.f;
     for (int64_t i = 0; i < T; ++i) {
         b.order[i] = i;
         const Tri& t = tris[i];
-        cen[i] = {t.p1.x + (t.e1.x + t.e2.x) * (1.f / 3.f), t.p1.y + (t.e1.y + t.e2.y) * (1.f / 3.f),
-                  t.p1.z + (t.e1.z + t.e2.z) * (1.f / 3.f)};
+        const float v[3][3] = {{t.p1.x, t.p1.y, t.p1.z},
+                               {t.p1.x + t.e1.x, t.p1.y + t.e1.y, t.p1.z + t.e1.z},
+                               {t.p1.x + t.e2.x, t.p1.y + t.e2.y, t.p1.z + t.e2.z}};
+        for (int a = 0; a < 3; ++a) {
+            /* P1 + e is not exactly P2/P3 in float: widen by the rounding of the sum */
+            const float m = std::max(std::fabs(v[0][a]), std::max(std::fabs(v[1][a]), std::fabs(v[2][a]))) * 2e-7f;
+            tb[i].lo[a] = std::min(v[0][a], std::min(v[1][a], v[2][a])) - m;
+            tb[i].hi[a] = std::max(v[0][a], std::max(v[1][a], v[2][a])) + m;
+            tb[i].c[a] = 0.5f * (tb[i].lo[a] + tb[i].hi[a]);
+            ext = std::max(ext, std::max(std::fabs(tb[i].lo[a]), std::fabs(tb[i].hi[a])));
+        }
     }
-    b.nodes.reserve(2 * (T / 2 + 1));
+    const float pad = ext * 1e-5f + 1e-6f;
+    b.nodes.reserve((size_t)T + 2);
     b.nodes.emplace_back();
-    if (T > 0) build_rec(b, tris, cen, 0, 0, T);
+    if (T > 0) build_rec(b, tb, pad, 0, 0, T);
     return b;
 }
 
@@ -226,7 +269,8 @@ Hit closest_bvh(const Bvh& b, const std::vector<Tri>& tris, V3 org, V3 dir)
     Hit best{1e20f, 0.f, 0.f, -1};
     if (tris.empty()) return best;
     const V3 inv = {1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z};
-    int stack[128];
+    const float dd[3] = {dir.x, dir.y, dir.z};
+    int stack[256];
     int sp = 0;
     stack[sp++] = 0;
     while (sp) {
@@ -238,9 +282,10 @@ Hit closest_bvh(const Bvh& b, const std::vector<Tri>& tris, V3 org, V3 dir)
                 float t, u, v;
                 if (tri_test(tris[id], org, dir, &t, &u, &v)) consider(best, t, u, v, id);
             }
-        } else {
-            stack[sp++] = n.left;
-            stack[sp++] = n.right;
+        } else if (sp + 2 <= 256) {
+            /* near child first: the split ordered `left` below `right` on n.axis */
+            if (dd[n.axis] >= 0.f) { stack[sp++] = n.right; stack[sp++] = n.left; }
+            else { stack[sp++] = n.left; stack[sp++] = n.right; }
         }
     }
     return best;
