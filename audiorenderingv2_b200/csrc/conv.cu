@@ -112,17 +112,52 @@ __global__ void __launch_bounds__(kConvThreads) block_spectra_kernel(const float
                   [&](int k, float2 v) { dst[k] = v; });
 }
 
-// acc[e][k] += X[k] * H_e[p][k] over this CTA's partitions, bins k = tid + i*256.
+// ---- TMA (cp.async.bulk) staging --------------------------------------------------------
+// One CTA streams ~300 KB of spectra per step with only 8 warps, far too few loads in flight
+// for plain LDGs (r01 profile: 18.5 us per step, long_scoreboard 20 warps/issue).  The rows
+// of a partition (X, H_left, H_right: block*8 B each) are instead pulled into a 4-stage
+// shared-memory ring by bulk async copies that complete on an mbarrier; the threads only
+// read shared memory.
+constexpr int kStages = 4;
+constexpr int kFftCostInPartitions = 8;   // forward FFT of one block ~ streaming 8 partitions (clock64-measured)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// acc += X[k] * H_e[k] for this thread's bins k = tid*BPT + i (contiguous, so that a
+// thread's BPT bins are one 8*BPT-byte shared-memory access); bin 0 holds (DC, Nyquist).
 template <int BPT>
-__device__ __forceinline__ void mac_partition(const float2* __restrict__ X, const float2* __restrict__ HL,
-                                              const float2* __restrict__ HR, int block, float2 accL[BPT], float2 accR[BPT])
+__device__ __forceinline__ void mac_rows(const float2* X, const float2* HL, const float2* HR, int block, float2 accL[BPT], float2 accR[BPT])
 {
 #pragma unroll
     for (int i = 0; i < BPT; ++i) {
-        const int k = threadIdx.x + i * kConvThreads;
+        const int k = threadIdx.x * BPT + i;
         if (k < block) {
-            const float2 xv = X[k];
-            const float2 hl = __ldg(HL + k), hr = __ldg(HR + k);
+            const float2 xv = X[k], hl = HL[k], hr = HR[k];
             if (k == 0) {   // packed (DC, Nyquist): two real products
                 accL[i].x = fmaf(xv.x, hl.x, accL[i].x); accL[i].y = fmaf(xv.y, hl.y, accL[i].y);
                 accR[i].x = fmaf(xv.x, hr.x, accR[i].x); accR[i].y = fmaf(xv.y, hr.y, accR[i].y);
@@ -131,6 +166,34 @@ __device__ __forceinline__ void mac_partition(const float2* __restrict__ X, cons
                 accR[i].x = fmaf(xv.x, hr.x, fmaf(-xv.y, hr.y, accR[i].x)); accR[i].y = fmaf(xv.x, hr.y, fmaf(xv.y, hr.x, accR[i].y));
             }
         }
+    }
+}
+
+// Multiply-accumulate `n` partitions through the TMA ring.  rows(i, &X, &HL, &HR) yields the
+// global rows of this CTA's i-th partition.  ring: float2[kStages][3][block]; all threads call.
+template <int BPT, class Rows>
+__device__ __forceinline__ void mac_pipeline(float2* ring, unsigned long long* full, int n, int block, Rows rows,
+                                             float2 accL[BPT], float2 accR[BPT])
+{
+    const unsigned row_bytes = (unsigned)block * sizeof(float2);
+    auto issue = [&](int i, int s) {
+        const float2 *X, *HL, *HR;
+        rows(i, &X, &HL, &HR);
+        float2* dst = ring + (size_t)s * 3 * block;
+        mbar_expect_tx(&full[s], 3 * row_bytes);
+        bulk_g2s(dst, X, row_bytes, &full[s]);
+        bulk_g2s(dst + block, HL, row_bytes, &full[s]);
+        bulk_g2s(dst + 2 * block, HR, row_bytes, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < kStages && s < n; ++s) issue(s, s);
+    for (int i = 0; i < n; ++i) {
+        const int s = i % kStages;
+        mbar_wait(&full[s], (unsigned)((i / kStages) & 1));
+        const float2* src = ring + (size_t)s * 3 * block;
+        mac_rows<BPT>(src, src + block, src + 2 * block, block, accL, accR);
+        __syncthreads();                                   // everyone is done with stage s
+        if (threadIdx.x == 0 && i + kStages < n) issue(i + kStages, s);
     }
 }
 
@@ -145,7 +208,7 @@ __device__ float2* reduce_and_inverse(cg::cluster_group& cluster, float2* part, 
     const unsigned C = cluster.num_blocks();
 #pragma unroll
     for (int i = 0; i < BPT; ++i) {
-        const int k = threadIdx.x + i * kConvThreads;
+        const int k = threadIdx.x * BPT + i;
         if (k < block) { part[k] = accL[i]; part[block + k] = accR[i]; }
     }
     cluster.sync();
@@ -186,29 +249,52 @@ __device__ float2* reduce_and_inverse(cg::cluster_group& cluster, float2* part, 
 template <int BPT>
 __global__ void __launch_bounds__(kConvThreads) stream_step_kernel(const ConvStreamArgs a)
 {
-    extern __shared__ float2 smem[];
+    extern __shared__ __align__(128) float2 smem[];
+    __shared__ unsigned long long full[kStages];
     const int block = a.block, N = 2 * block;
-    float2* bufa = smem; float2* bufb = bufa + N; float2* part = bufb + N; float2* yacc = part + N;
+    float2* bufa = smem; float2* bufb = bufa + N; float2* part = bufb + N; float2* yacc = part + N; float2* ring = yacc + N;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     const unsigned C = cluster.num_blocks();
     const int src = blockIdx.x / C;
     float2* fdl = a.fdl + (size_t)src * a.P * block;
     const float2* H = a.H[src];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
+    float2 accL[BPT], accR[BPT];
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) { accL[i] = make_float2(0.f, 0.f); accR[i] = make_float2(0.f, 0.f); }
+    // Partition 0 is the block being transformed right now; rank 0 runs that forward FFT
+    // (~8 partitions' worth of time, measured with clock64) and therefore takes a shorter
+    // contiguous range of the older partitions 1..P-1; the rest is split evenly over ranks 1..C-1.
+    const int T = a.P - 1;
+    int n0 = C > 1 ? (T - kFftCostInPartitions * ((int)C - 1)) / (int)C : T;
+    n0 = max(0, min(T, n0));
+    int first, n;
+    if (rank == 0) { first = 1; n = n0; }
+    else {
+        const int rest = T - n0, per = rest / ((int)C - 1), extra = rest % ((int)C - 1), r1 = (int)rank - 1;
+        first = 1 + n0 + r1 * per + min(r1, extra);
+        n = per + (r1 < extra ? 1 : 0);
+    }
     if (rank == 0) {
         // newest block: forward FFT, publish into the frequency-domain delay line
         const float* in = a.in + (size_t)src * block;
         float2* slot = fdl + (size_t)a.slot * block;
         forward_block(bufa, bufb, block, a.tw, [&](int t) { return in[t]; }, [&](int k, float2 v) { slot[k] = v; });
+        mac_rows<BPT>(slot, H, H + (size_t)a.P * block, block, accL, accR);
     }
-    float2 accL[BPT], accR[BPT];
-#pragma unroll
-    for (int i = 0; i < BPT; ++i) { accL[i] = make_float2(0.f, 0.f); accR[i] = make_float2(0.f, 0.f); }
-    for (int p = (int)rank; p < a.P; p += (int)C) {
-        int s = a.slot - p; if (s < 0) s += a.P;
-        mac_partition<BPT>(fdl + (size_t)s * block, H + (size_t)p * block, H + ((size_t)a.P + p) * block, block, accL, accR);
-    }
+    mac_pipeline<BPT>(ring, full, n, block,
+                      [&](int i, const float2** X, const float2** HL, const float2** HR) {
+                          const int p = first + i;
+                          int s = a.slot - p; if (s < 0) s += a.P;
+                          *X = fdl + (size_t)s * block; *HL = H + (size_t)p * block; *HR = H + ((size_t)a.P + p) * block;
+                      },
+                      accL, accR);
     float2* y = reduce_and_inverse<BPT>(cluster, part, yacc, bufa, bufb, block, a.tw, accL, accR);
     if (!y) return;
     const float sc = 1.0f / (float)N;
@@ -226,22 +312,34 @@ __global__ void __launch_bounds__(kConvThreads) stream_step_kernel(const ConvStr
 template <int BPT>
 __global__ void __launch_bounds__(kConvThreads) file_kernel(const ConvFileArgs a, int out_blocks_per_seg)
 {
-    extern __shared__ float2 smem[];
+    extern __shared__ __align__(128) float2 smem[];
+    __shared__ unsigned long long full[kStages];
     const int block = a.block, N = 2 * block;
-    float2* bufa = smem; float2* bufb = bufa + N; float2* part = bufb + N; float2* yacc = part + N;
+    float2* bufa = smem; float2* bufb = bufa + N; float2* part = bufb + N; float2* yacc = part + N; float2* ring = yacc + N;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     const unsigned C = cluster.num_blocks();
     const int cid = blockIdx.x / C;
     const int seg = cid / out_blocks_per_seg, j = cid % out_blocks_per_seg;
     const float2* X = a.X + (size_t)seg * a.blocks_per_seg * block;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     float2 accL[BPT], accR[BPT];
 #pragma unroll
     for (int i = 0; i < BPT; ++i) { accL[i] = make_float2(0.f, 0.f); accR[i] = make_float2(0.f, 0.f); }
     const int p_lo = max(0, j - (a.blocks_per_seg - 1)), p_hi = min(a.P - 1, j);
-    for (int p = p_lo + (int)rank; p <= p_hi; p += (int)C)
-        mac_partition<BPT>(X + (size_t)(j - p) * block, a.H + (size_t)p * block, a.H + ((size_t)a.P + p) * block, block, accL, accR);
+    const int first = p_lo + (int)rank;
+    const int n = first <= p_hi ? (p_hi - first) / (int)C + 1 : 0;
+    mac_pipeline<BPT>(ring, full, n, block,
+                      [&](int i, const float2** Xr, const float2** HL, const float2** HR) {
+                          const int p = first + i * (int)C;
+                          *Xr = X + (size_t)(j - p) * block; *HL = a.H + (size_t)p * block; *HR = a.H + ((size_t)a.P + p) * block;
+                      },
+                      accL, accR);
     float2* y = reduce_and_inverse<BPT>(cluster, part, yacc, bufa, bufb, block, a.tw, accL, accR);
     if (!y) return;
     const float sc = a.gain / (float)N;
@@ -258,7 +356,7 @@ __global__ void __launch_bounds__(kConvThreads) file_kernel(const ConvFileArgs a
 }
 
 size_t fft_smem_bytes(int block) { return (size_t)4 * block * sizeof(float2); }
-size_t step_smem_bytes(int block) { return (size_t)8 * block * sizeof(float2); }
+size_t step_smem_bytes(int block) { return (size_t)(8 + 3 * kStages) * block * sizeof(float2); }
 
 template <class K>
 cudaError_t launch_cluster(K kernel, unsigned grid, size_t smem, cudaStream_t stream, void** args)
