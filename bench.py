@@ -333,6 +333,12 @@ def main():
     except (OSError, KeyError, ValueError):
         pass
 
+    traffic = None
+    try:      # per-launch DRAM bytes of the trace kernel from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["trace"]["dram_bytes_per_launch"] if WORKLOAD == "c2" else None
+    except (OSError, KeyError, ValueError):
+        pass
+
     extras = {}
     if not args.skip_extras and WORKLOAD == "c2":
         extras.update(bench_rerender(arv, torch, dev, local, scene, receiver, mats, args))
@@ -350,7 +356,8 @@ def main():
         "gpu_launches": 2 * args.steps,
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": f"trace_kernel<{BANDS},0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": segs_per_launch * BYTES_PER_SEGMENT,
                      "bytes_per_segment": BYTES_PER_SEGMENT, "kernel_ms": kernel_ms},
     }
     line.update(extras)

@@ -49,4 +49,19 @@ if os.path.exists(lc):
     with open(os.path.join(ROOT, "profiles", f"{tag}_launches.csv"), "w") as fh:
         fh.write(txt)
 open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w").write("\n".join(out) + "\n")
+# per-launch DRAM traffic of the captured kernels, read by bench.py for roofline.traffic
+import json, re
+traffic = {}
+for name in ("trace", "rerender", "conv"):
+    rep = os.path.join(G, f"{name}_{tag}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    d = dict(zip(rows[0], rows[2])); u = dict(zip(rows[0], rows[1]))
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = sum(float(d[k].replace(",", "")) * scale.get(u[k], 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in d)
+    traffic[name] = {"kernel": d.get("Kernel Name"), "dram_bytes_per_launch": tot, "tag": tag}
+if traffic:
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print("\n".join(out))
