@@ -77,7 +77,7 @@ struct arv2_ctx {
     unsigned long long* d_counters = nullptr;
     int* d_rec_bin = nullptr; int* d_rec_ear = nullptr; int* d_rec_nseg = nullptr; float* d_rec_energy = nullptr;
     long long rec_capacity = 0, last_range_rays = 0;
-    float4* d_pc_org = nullptr; float4* d_pc_dir = nullptr; float* d_pc_energy = nullptr; int* d_pc_nseg = nullptr;
+    float4* d_pc_seg = nullptr; float* d_pc_energy = nullptr; int* d_pc_nseg = nullptr;
     long long pc_rays = 0; unsigned pc_bounces = 0;
     // pinned staging for the receiver sub-tree
     float4* h_stage = nullptr; size_t stage_f4 = 0;
@@ -192,7 +192,7 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     if (c->desc.record_rays && n_rays <= c->rec_capacity) {
         p->rec_bin = c->d_rec_bin; p->rec_ear = c->d_rec_ear; p->rec_energy = c->d_rec_energy; p->rec_nseg = c->d_rec_nseg;
     }
-    p->pc_org_t = c->d_pc_org; p->pc_dir_d = c->d_pc_dir; p->pc_energy = c->d_pc_energy; p->pc_nseg = c->d_pc_nseg;
+    p->pc_seg = c->d_pc_seg; p->pc_energy = c->d_pc_energy; p->pc_nseg = c->d_pc_nseg;
     p->pc_stride = c->pc_rays;
     p->seed = c->seed; p->ray_begin = ray_begin; p->n_rays = n_rays;
     for (int a = 0; a < 3; ++a) { p->emitter[a] = c->emitter[a]; p->center[a] = c->center[a]; }
@@ -218,12 +218,11 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
 int ensure_cache(arv2_ctx* c)
 {
     const long long n = c->n_rays_total;
-    if (c->d_pc_org && c->pc_rays == n && c->pc_bounces >= c->max_bounces) return ARV2_OK;
-    cudaFree(c->d_pc_org); cudaFree(c->d_pc_dir); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg);
-    c->d_pc_org = c->d_pc_dir = nullptr; c->d_pc_energy = nullptr; c->d_pc_nseg = nullptr;
+    if (c->d_pc_seg && c->pc_rays == n && c->pc_bounces >= c->max_bounces) return ARV2_OK;
+    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg);
+    c->d_pc_seg = nullptr; c->d_pc_energy = nullptr; c->d_pc_nseg = nullptr;
     const size_t segs = (size_t)n * c->max_bounces;
-    CK(cudaMalloc(&c->d_pc_org, segs * sizeof(float4)));
-    CK(cudaMalloc(&c->d_pc_dir, segs * sizeof(float4)));
+    CK(cudaMalloc(&c->d_pc_seg, segs * 2 * sizeof(float4)));
     CK(cudaMalloc(&c->d_pc_energy, segs * sizeof(float) * c->bands));
     CK(cudaMalloc(&c->d_pc_nseg, (size_t)n * sizeof(int)));
     c->pc_rays = n; c->pc_bounces = c->max_bounces; c->cache_valid = false;
@@ -521,7 +520,7 @@ void arv2_destroy(arv2_ctx* c)
     cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_keep); cudaFree(c->d_scatter);
     cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_ir_r); cudaFree(c->d_counters);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
-    cudaFree(c->d_pc_org); cudaFree(c->d_pc_dir); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg);
+    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg);
     cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_counters) cudaFreeHost(c->h_counters);

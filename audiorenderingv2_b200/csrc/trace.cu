@@ -256,7 +256,7 @@ struct Deposit { bool dep; int bin, ear, primary; };
 template <int NB, int MODE>
 __device__ __forceinline__ bool shade_segment(const TraceParams& p, Path<NB>& s, const Hit& h, Deposit& d)
 {
-    if (MODE == 1) p.pc_org_t[(size_t)(s.nseg - 1) * (size_t)p.pc_stride + (size_t)s.ray] = make_float4(s.org.x, s.org.y, s.org.z, h.t);
+    if (MODE == 1) p.pc_seg[2 * ((size_t)(s.nseg - 1) * (size_t)p.pc_stride + (size_t)s.ray)] = make_float4(s.org.x, s.org.y, s.org.z, h.t);
     if (h.slot < 0) return true;                                                     // miss :186-190
     const F8 A = ldg256(p.tris + h.slot * 4), B = ldg256(p.tris + h.slot * 4 + 2);
     const F3 p1 = f3(A.lo.x, A.lo.y, A.lo.z), p2 = f3(A.hi.x, A.hi.y, A.hi.z), p3 = f3(B.lo.x, B.lo.y, B.lo.z);
@@ -335,7 +335,7 @@ __device__ __forceinline__ void begin_segment(const TraceParams& p, Path<NB>& s)
 {
     if (MODE == 1) {
         const size_t ci = (size_t)s.nseg * (size_t)p.pc_stride + (size_t)s.ray;
-        p.pc_dir_d[ci] = make_float4(s.dir.x, s.dir.y, s.dir.z, s.dist);
+        p.pc_seg[2 * ci + 1] = make_float4(s.dir.x, s.dir.y, s.dir.z, s.dist);
 #pragma unroll
         for (int b = 0; b < NB; ++b) p.pc_energy[ci * NB + b] = s.energy[b];
     }
@@ -517,37 +517,84 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace2_kernel(const Trace
 template <int NB>
 __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceParams p)
 {
-    const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = ray < p.n_rays;
-    const int n = valid ? p.pc_nseg[ray] : 0;
-    int k = 0;
-    bool done = n == 0, cand = false;
+    const int lane = threadIdx.x & 31;
+    long long chunk_next = 0, chunk_end = 0;      // warp-uniform
+    bool have = false, exhausted = false, cand = false;
+    long long ray = 0;
+    int k = 0, n = 0;
     float4 ot = make_float4(0, 0, 0, 0), dd = make_float4(0, 0, 0, 0);
-    int rbin = -1, rear = 0, rnseg = n;
     float energy[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) energy[b] = 0.f;
+    unsigned long long segs = 0;
     Traversal tr;
     int stack[kStack];
+
+    // rays that leave the scan: miss (every cached segment passed) or receiver hit
+    auto finish = [&](int bin, int ear, int nseg) {
+        if (p.rec_bin) p.rec_bin[ray] = bin;
+        if (p.rec_ear) p.rec_ear[ray] = ear;
+        if (p.rec_nseg) p.rec_nseg[ray] = nseg;
+        if (p.rec_energy) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = ear ? energy[b] : 0.f;
+        }
+        segs += (unsigned long long)nseg;
+        have = false;
+    };
+
     for (;;) {
-        // ---- scan: advance to the next segment that enters the bounding ball
-        if (!done && !cand) {
+        // ---- refill: lanes without a ray claim the next ones of the warp's chunk, so the scan
+        // keeps ~32 lanes busy although the rays of a warp end at very different segments
+        // (r02 profile of the one-thread-per-ray version: 5.9 of 32 lanes per instruction)
+        unsigned need = __ballot_sync(FULL, !have && !exhausted);
+        while (need) {
+            if (chunk_next >= chunk_end) {
+                unsigned long long b = 0;
+                if (lane == 0) b = atomicAdd(p.counters, (unsigned long long)kChunk);
+                b = __shfl_sync(FULL, b, 0);
+                chunk_next = (long long)b;
+                chunk_end = min((long long)b + kChunk, p.n_rays);
+                if (chunk_next >= chunk_end) {
+                    if (!have) exhausted = true;
+                    break;
+                }
+            }
+            const int avail = (int)min((long long)32, chunk_end - chunk_next);
+            const int rank = __popc(need & ((1u << lane) - 1u));
+            if (((need >> lane) & 1u) && rank < avail) {
+                ray = chunk_next + rank;
+                n = p.pc_nseg[ray];
+                k = 0;
+                have = true;
+                if (n == 0) finish(-1, 0, 0);
+            }
+            chunk_next += min(__popc(need), avail);
+            need = __ballot_sync(FULL, !have && !exhausted);
+        }
+        if (!__any_sync(FULL, have)) break;
+
+        // ---- scan: advance to the next cached segment that enters the receiver's bounding ball
+        if (have && !cand) {
 #pragma unroll 1
-            for (int burst = 0; burst < 16 && !cand && !done; ++burst) {
+            for (int burst = 0; burst < 8; ++burst) {
                 const size_t ci = (size_t)k * (size_t)p.pc_stride + (size_t)ray;
-                ot = __ldcs(p.pc_org_t + ci);
-                dd = __ldcs(p.pc_dir_d + ci);
-                if (enters_receiver_ball(p, f3(ot.x, ot.y, ot.z), f3(dd.x, dd.y, dd.z), ot.w)) cand = true;
-                else if (++k >= n) done = true;
+                // one 32 B record = one sector = one 256-bit load, whatever k the other lanes are at
+                const F8 rec = ldg256(p.pc_seg + 2 * ci);
+                ot = rec.lo; dd = rec.hi;
+                if (enters_receiver_ball(p, f3(ot.x, ot.y, ot.z), f3(dd.x, dd.y, dd.z), ot.w)) { cand = true; break; }
+                if (++k >= n) { finish(-1, 0, n); break; }
             }
         }
+        // ---- receiver walk, batched: only when enough lanes hold a candidate (or nobody scans)
         const unsigned cm = __ballot_sync(FULL, cand);
-        const unsigned sm = __ballot_sync(FULL, !done && !cand);
-        if (cm == 0 && sm == 0) break;
-        if (cm != 0 && (__popc(cm) >= kRerenderBatch || sm == 0)) {
+        const unsigned sm = __ballot_sync(FULL, have && !cand);
+        const unsigned idle = __ballot_sync(FULL, !have && !exhausted);
+        if (cm != 0 && (__popc(cm) >= kRerenderBatch || (sm == 0 && idle == 0))) {
             bool dep = false;
             int bin = -1, primary = 0;
             if (cand) {
+                cand = false;
                 const F3 org = f3(ot.x, ot.y, ot.z), dir = f3(dd.x, dd.y, dd.z);
                 closest_hit(p, stack, tr, p.recv_root, org, dir, ot.w);
                 const Hit& h = tr.h;
@@ -563,29 +610,17 @@ __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceP
                     bin = receiver_hit<NB>(p, pt, dir, dist, energy);
                     primary = (mat == -1) ? 0 : 1;
                     dep = bin >= 0 && bin < p.ir_len;
-                    rbin = bin; rear = (mat == -1) ? 1 : 2; rnseg = k + 1;
-                    done = true;
+                    finish(bin, (mat == -1) ? 1 : 2, k + 1);
                 } else if (++k >= n) {
-                    done = true;
+                    finish(-1, 0, n);
                 }
-                cand = false;
             }
             deposit_warp<NB>(p, dep, bin, primary, energy);
         }
     }
-    if (valid) {
-        if (p.rec_bin) p.rec_bin[ray] = rbin;
-        if (p.rec_ear) p.rec_ear[ray] = rear;
-        if (p.rec_nseg) p.rec_nseg[ray] = rnseg;
-        if (p.rec_energy) {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = rear ? energy[b] : 0.f;
-        }
-    }
-    unsigned long long segs = valid ? (unsigned long long)rnseg : 0ull;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
-    if ((threadIdx.x & 31) == 0 && segs) atomicAdd(p.counters + 1, segs);
+    if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
 }
 
 __global__ void finalize_kernel(const double* __restrict__ hist, int n, int mono, float* __restrict__ l, float* __restrict__ r)
@@ -628,12 +663,17 @@ cudaError_t launch_trace(const TraceParams& p, int bands, int mode, int sm_count
 
 cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaStream_t stream)
 {
-    (void)sm_count;
-    const unsigned grid = (unsigned)((p.n_rays + kRerenderThreads - 1) / kRerenderThreads);
-    if (grid == 0) return cudaSuccess;
-    if (bands == 1) rerender_kernel<1><<<grid, kRerenderThreads, 0, stream>>>(p);
-    else if (bands == 8) rerender_kernel<8><<<grid, kRerenderThreads, 0, stream>>>(p);
-    else return cudaErrorInvalidValue;
+    if (p.n_rays == 0) return cudaSuccess;
+    if (bands != 1 && bands != 8) return cudaErrorInvalidValue;
+    int per_sm = 0;
+    cudaError_t e = bands == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rerender_kernel<1>, kRerenderThreads, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rerender_kernel<8>, kRerenderThreads, 0);
+    if (e != cudaSuccess) return e;
+    long long grid = (long long)sm_count * (per_sm < 1 ? 1 : per_sm);
+    const long long want = (p.n_rays + kRerenderThreads - 1) / kRerenderThreads;
+    if (want < grid) grid = want;
+    if (bands == 1) rerender_kernel<1><<<(unsigned)grid, kRerenderThreads, 0, stream>>>(p);
+    else rerender_kernel<8><<<(unsigned)grid, kRerenderThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

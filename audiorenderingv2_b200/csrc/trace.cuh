@@ -17,8 +17,7 @@ struct TraceParams {
     unsigned long long* counters; // [0] next ray chunk, [1] segments traced
     int* rec_bin; int* rec_ear; float* rec_energy; int* rec_nseg;   // optional per-ray records
     // receiver-independent path cache (optional): per segment k of ray r at [k*stride + r]
-    float4* pc_org_t;           // (origin.xyz, t_wall or 1e20 on miss)
-    float4* pc_dir_d;           // (dir.xyz, distance before the segment)
+    float4* pc_seg;             // 32 B per cached segment: (origin.xyz, t_wall or 1e20 on miss), (dir.xyz, distance before)
     float* pc_energy;           // [k*stride + r][bands]
     int* pc_nseg;               // [r] segments cached
     long long pc_stride;
