@@ -91,6 +91,7 @@ SYMBOLS = {
     "arv2_set_hrtf_absorption_rate": (C.c_int, [_vp, C.c_float]),
     "arv2_set_mono": (C.c_int, [_vp, C.c_int32]),
     "arv2_set_seed": (C.c_int, [_vp, C.c_uint64]),
+    "arv2_set_coherent_order": (C.c_int, [_vp, C.c_int32]),
     "arv2_set_stream": (C.c_int, [_vp, _vp]),
     "arv2_render": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "arv2_render_range": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
@@ -330,6 +331,9 @@ class AudioRenderer:
 
     def set_seed(self, seed):
         _check(lib().arv2_set_seed(self._h, int(seed)))
+
+    def set_coherent_order(self, on):
+        _check(lib().arv2_set_coherent_order(self._h, 1 if on else 0))
 
     def set_stream(self, cuda_stream_ptr):
         _check(lib().arv2_set_stream(self._h, cuda_stream_ptr))

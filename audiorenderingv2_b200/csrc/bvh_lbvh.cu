@@ -147,6 +147,35 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
     }
 }
 
+} // namespace
+
+// Stable LSD radix sort of (key, value) pairs on bits [lo_bit, hi_bit) of the keys, kRadixBits
+// per pass, with the count / scan / scatter kernels above.  Returns 0 or 1: which of the two
+// ping-pong buffers holds the result.
+cudaError_t radix_sort_pairs(unsigned* keys[2], int* vals[2], int n, int lo_bit, int hi_bit, int* result, cudaStream_t stream)
+{
+    *result = 0;
+    if (n <= 0) return cudaSuccess;
+    const int sort_blocks = (n + kSortTile - 1) / kSortTile;
+    unsigned* counts = nullptr;
+    cudaError_t e = cudaMalloc(&counts, (size_t)kRadix * sort_blocks * 4);
+    if (e != cudaSuccess) return e;
+    int cur = 0;
+    for (int shift = lo_bit; shift < hi_bit; shift += kRadixBits) {
+        radix_count_kernel<<<sort_blocks, kSortThreads, 0, stream>>>(keys[cur], n, shift, counts);
+        scan_single_block_kernel<<<1, 1024, 0, stream>>>(counts, kRadix * sort_blocks);
+        radix_scatter_kernel<<<sort_blocks, kSortThreads, 0, stream>>>(keys[cur], vals[cur], n, shift, counts, keys[cur ^ 1], vals[cur ^ 1]);
+        cur ^= 1;
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(counts);
+    *result = cur;
+    return e;
+}
+
+namespace {
+
 // ---- Karras 2012 radix tree over unique 64-bit keys (morton << 32 | sorted position) ---
 __device__ __forceinline__ int delta(const unsigned* __restrict__ keys, int n, int i, int j)
 {

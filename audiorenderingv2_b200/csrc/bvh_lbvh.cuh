@@ -14,4 +14,8 @@ struct LbvhResult { int n_nodes; float lo[3], hi[3]; };
 cudaError_t build_bvh_lbvh(const float* d_verts, const int* d_mats, int n, int id_base, float4* d_nodes, float4* d_tris,
                            int* d_order, int node_offset, int slot_offset, LbvhResult* out, cudaStream_t stream);
 
+// Stable radix sort of (key, value) pairs on key bits [lo_bit, hi_bit), 6 bits per pass; keys[0] / vals[0]
+// hold the input, *result says which ping-pong buffer holds the output.  Synchronises the stream.
+cudaError_t radix_sort_pairs(unsigned* keys[2], int* vals[2], int n, int lo_bit, int hi_bit, int* result, cudaStream_t stream);
+
 } // namespace arv2

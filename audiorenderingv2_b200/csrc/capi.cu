@@ -79,6 +79,8 @@ struct arv2_ctx {
     long long rec_capacity = 0, last_range_rays = 0;
     float4* d_pc_seg = nullptr; float* d_pc_energy = nullptr; int* d_pc_nseg = nullptr;
     long long pc_rays = 0; unsigned pc_bounces = 0;
+    int* d_ray_order = nullptr; long long order_begin = -1, order_n = -1; unsigned long long order_seed = 0;
+    bool coherent_order = true;
     // pinned staging for the receiver sub-tree
     float4* h_stage = nullptr; size_t stage_f4 = 0;
     unsigned long long* h_counters = nullptr;
@@ -213,6 +215,40 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     p->scene_root = c->n_scene > 0 ? 1 : -1;
     p->recv_root = c->has_receiver ? 1 + c->n_scene_nodes : -1;
     p->any_scatter = c->any_scatter;
+    // a warp tops up its free lanes only once at least 9 are free, 16 rays per claim: the rays it
+    // starts together are neighbours in the direction order (tuning aids: ARV2_CHUNK, ARV2_REFILL_BELOW)
+    p->chunk = 16;
+    p->refill_below = c->coherent_order ? 24 : 33;
+    if (const char* e = getenv("ARV2_CHUNK")) p->chunk = atoi(e) > 0 ? atoi(e) : p->chunk;
+    if (const char* e = getenv("ARV2_REFILL_BELOW")) p->refill_below = atoi(e) > 0 ? atoi(e) : p->refill_below;
+    p->ray_order = (c->d_ray_order && c->order_begin == ray_begin && c->order_n == n_rays && c->order_seed == c->seed) ? c->d_ray_order : nullptr;
+}
+
+// Coherent ray order: the rays of a launch are started in the order of their emission direction
+// (Morton code of the octahedral map, GPU radix sort on its top 24 bits), so the 32 lanes of a
+// warp walk the same part of the scene over the first bounces.  Depends only on (seed, range);
+// the result per ray and the fp64 histogram do not depend on the order.
+int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
+{
+    if (!c->coherent_order || n_rays <= 0 || n_rays > 0x7fffffffLL) return ARV2_OK;
+    if (c->d_ray_order && c->order_begin == ray_begin && c->order_n == n_rays && c->order_seed == c->seed) return ARV2_OK;
+    cudaFree(c->d_ray_order); c->d_ray_order = nullptr; c->order_n = -1;
+    unsigned* keys[2] = {nullptr, nullptr};
+    int* vals[2] = {nullptr, nullptr};
+    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); };
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaMalloc(&keys[k], (size_t)n_rays * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMalloc(&vals[k], (size_t)n_rays * sizeof(int));
+    }
+    int res = 0;
+    if (e == cudaSuccess) e = launch_direction_keys(c->seed, ray_begin, n_rays, keys[0], vals[0], c->stream);
+    if (e == cudaSuccess) e = radix_sort_pairs(keys, vals, (int)n_rays, 8, 32, &res, c->stream);
+    if (e != cudaSuccess) { cleanup(); set_error(std::string("ray order: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
+    c->d_ray_order = vals[res]; vals[res] = nullptr;
+    cleanup();
+    c->order_begin = ray_begin; c->order_n = n_rays; c->order_seed = c->seed;
+    return ARV2_OK;
 }
 
 int ensure_cache(arv2_ctx* c)
@@ -396,6 +432,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     CK(cudaSetDevice(desc->device));
 
     auto* c = new arv2_ctx;
+    if (getenv("ARV2_NO_SORT")) c->coherent_order = false;   // tuning aid (A/B)
     c->desc = *desc; c->desc.materials = nullptr; c->desc.n_materials = 0;
     c->device = desc->device;
     c->bands = desc->bands;
@@ -520,7 +557,7 @@ void arv2_destroy(arv2_ctx* c)
     cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_keep); cudaFree(c->d_scatter);
     cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_ir_r); cudaFree(c->d_counters);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
-    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg);
+    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg); cudaFree(c->d_ray_order);
     cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -557,6 +594,7 @@ int arv2_set_base_power(arv2_ctx* c, float v) { REQUIRE(c, "null ctx"); c->base_
 int arv2_set_hrtf_absorption_rate(arv2_ctx* c, float v) { REQUIRE(c, "null ctx"); c->hrtf = v; return ARV2_OK; }
 int arv2_set_mono(arv2_ctx* c, int32_t v) { REQUIRE(c, "null ctx"); c->mono = v ? 1 : 0; return ARV2_OK; }
 int arv2_set_seed(arv2_ctx* c, uint64_t s) { REQUIRE(c, "null ctx"); c->seed = s; c->cache_valid = false; return ARV2_OK; }
+int arv2_set_coherent_order(arv2_ctx* c, int32_t on) { REQUIRE(c, "null ctx"); c->coherent_order = on != 0; return ARV2_OK; }
 int arv2_set_stream(arv2_ctx* c, void* s) { REQUIRE(c, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return ARV2_OK; }
 
 int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t zero_first, double* ms)
@@ -569,6 +607,8 @@ int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t ze
     const size_t irn = (size_t)c->bands * c->ir_len;
     if (zero_first) CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));   // fillZeros, OR/AudioRenderer.cpp:491-492
     CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
+    rc = ensure_ray_order(c, ray_begin, n_rays);
+    if (rc != ARV2_OK) return rc;
     TraceParams p;
     fill_params(c, &p, ray_begin, n_rays);
     CK(cudaEventRecord(c->ev0, c->stream));
@@ -622,6 +662,8 @@ int arv2_render(arv2_ctx* c, double* ms)
     double ms_build = 0.0;
     if (!c->cache_valid) {
         rc = upload_receiver(c);
+        if (rc != ARV2_OK) return rc;
+        rc = ensure_ray_order(c, 0, c->n_rays_total);
         if (rc != ARV2_OK) return rc;
         CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
         TraceParams p;

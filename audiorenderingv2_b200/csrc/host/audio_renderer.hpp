@@ -102,6 +102,7 @@ public:
     void setBasePower(float p) { check(arv2_set_base_power(ctx_, p), "setBasePower"); }
     void setMonoOutput(bool v) { check(arv2_set_mono(ctx_, v ? 1 : 0), "setMonoOutput"); }
     void set_seed(unsigned long long s) { check(arv2_set_seed(ctx_, s), "set_seed"); }
+    void set_coherent_order(bool on) { check(arv2_set_coherent_order(ctx_, on ? 1 : 0), "set_coherent_order"); }
     void set_write_ir_to_file_flag(bool v) { write_ir_ = v; }
 
     // full_render_cycle (OR/AudioRenderer.cpp:790-798)

@@ -31,7 +31,7 @@ namespace arv2 {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int kChunk = 128;          // rays a warp claims per global atomic
+constexpr int kChunk = 128;          // rays a re-render warp claims per global atomic
 constexpr int kStack = kTraversalStack;
 #ifndef ARV2_THREADS
 #define ARV2_THREADS 128
@@ -322,6 +322,7 @@ __device__ __forceinline__ void end_path(const TraceParams& p, const Path<NB>& s
 template <int NB>
 __device__ __forceinline__ void new_path(const TraceParams& p, Path<NB>& s, long long ray)
 {
+    if (p.ray_order) ray = p.ray_order[ray];
     s.ray = ray;
     s.org = f3(p.emitter[0], p.emitter[1], p.emitter[2]);              // :210
     s.dir = emit_direction(p.seed, (uint64_t)(p.ray_begin + ray));     // :216-224
@@ -354,10 +355,10 @@ __device__ __forceinline__ bool refill(const TraceParams& p, bool want, long lon
     while (need) {
         if (chunk_next >= chunk_end) {
             unsigned long long b = 0;
-            if (lane == 0) b = atomicAdd(p.counters, (unsigned long long)kChunk);
+            if (lane == 0) b = atomicAdd(p.counters, (unsigned long long)p.chunk);
             b = __shfl_sync(FULL, b, 0);
             chunk_next = (long long)b;
-            chunk_end = min((long long)b + kChunk, p.n_rays);
+            chunk_end = min((long long)b + p.chunk, p.n_rays);
             if (chunk_next >= chunk_end) {
                 if (want && !got) exhausted = true;
                 break;
@@ -390,7 +391,8 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceP
     int stack[kStack];
 
     for (;;) {
-        if (refill<NB>(p, !have, chunk_next, chunk_end, exhausted, s)) have = true;
+        const bool open = __popc(__ballot_sync(FULL, have)) < p.refill_below;
+        if (refill<NB>(p, !have && open, chunk_next, chunk_end, exhausted, s)) have = true;
         if (!__any_sync(FULL, have)) break;
 
         bool ended = false;
@@ -623,6 +625,30 @@ __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceP
     if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
 }
 
+__device__ __forceinline__ unsigned spread16(unsigned v)
+{
+    v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// Morton code of the octahedral map of each ray's emission direction: rays that are neighbours
+// in this order leave the emitter in a narrow cone and stay together over the first bounces.
+__global__ void direction_keys_kernel(unsigned long long seed, long long ray_begin, long long n, unsigned* __restrict__ keys,
+                                      int* __restrict__ vals)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const F3 d = emit_direction(seed, (uint64_t)(ray_begin + i));
+    const float inv = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z) + 1e-30f);
+    float u = d.x * inv, v = d.y * inv;
+    if (d.z < 0.f) { const float uu = (1.f - fabsf(v)) * copysignf(1.f, u), vv = (1.f - fabsf(u)) * copysignf(1.f, v); u = uu; v = vv; }
+    const unsigned iu = (unsigned)fminf(fmaxf((u * 0.5f + 0.5f) * 65536.f, 0.f), 65535.f);
+    const unsigned iv = (unsigned)fminf(fmaxf((v * 0.5f + 0.5f) * 65536.f, 0.f), 65535.f);
+    keys[i] = spread16(iu) | (spread16(iv) << 1);
+    vals[i] = (int)i;
+}
+
 __global__ void finalize_kernel(const double* __restrict__ hist, int n, int mono, float* __restrict__ l, float* __restrict__ r)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -674,6 +700,13 @@ cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaS
     if (want < grid) grid = want;
     if (bands == 1) rerender_kernel<1><<<(unsigned)grid, kRerenderThreads, 0, stream>>>(p);
     else rerender_kernel<8><<<(unsigned)grid, kRerenderThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_direction_keys(unsigned long long seed, long long ray_begin, long long n, unsigned* keys, int* vals, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    direction_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(seed, ray_begin, n, keys, vals);
     return cudaGetLastError();
 }
 

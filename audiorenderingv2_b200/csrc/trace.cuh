@@ -31,6 +31,9 @@ struct TraceParams {
     int root;                   // node the full trace starts at (0 = two-level top node)
     int scene_root, recv_root;  // roots of the two sub-trees (-1: absent)
     int any_scatter;            // 0: skip the diffuse-bounce RNG entirely
+    const int* ray_order;       // optional: the order in which the launch's rays [0, n_rays) are started (direction-sorted)
+    int chunk;                  // rays a warp claims per global atomic
+    int refill_below;           // lanes of a warp are refilled only while fewer than this many hold a path (32 = always)
 };
 
 // mode 0: full trace (scene + receiver), deposits into hist.
@@ -41,5 +44,9 @@ cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaS
 // hist (fp64) -> ir_left / ir_right (fp32); mono: L = R = L + R (OR/kernels.cu:519-527).
 cudaError_t launch_finalize(const double* hist, int bands, int ir_len, int mono, float* ir_left, float* ir_right,
                             cudaStream_t stream);
+
+// keys[i] = Morton code of the octahedral map of the direction of ray (ray_begin + i), vals[i] = i
+cudaError_t launch_direction_keys(unsigned long long seed, long long ray_begin, long long n, unsigned* keys, int* vals,
+                                  cudaStream_t stream);
 
 } // namespace arv2

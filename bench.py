@@ -219,6 +219,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2 = BASELINE configs[1] (default), c4 = configs[3]")
     args = ap.parse_args()
     select_workload(args.workload)
+    if os.environ.get("ARV2_BENCH_RAYS"):           # tuning aid (tail-effect experiments); not a driver-facing line
+        global RAYS
+        RAYS = (int(os.environ["ARV2_BENCH_RAYS"]), 1, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "arv2" else args.warmup
 
     if args.impl == "reference":

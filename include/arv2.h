@@ -157,6 +157,10 @@ int arv2_set_hrtf_absorption_rate(arv2_ctx* ctx, float rate);
 int arv2_set_mono(arv2_ctx* ctx, int32_t mono);
 /* replaces clock64() as the RNG seed (OR/devicePrograms.cu:217). */
 int arv2_set_seed(arv2_ctx* ctx, uint64_t seed);
+/* Start the rays of a launch in the order of their emission direction (default on).  The
+ * ray set, every per-ray result and the IR are unchanged; only the lanes of a warp become
+ * neighbours in direction.  The order is computed on the GPU once per (seed, ray range). */
+int arv2_set_coherent_order(arv2_ctx* ctx, int32_t on);
 /* Run everything on this CUDA stream (cudaStream_t as void*; NULL = own stream). */
 int arv2_set_stream(arv2_ctx* ctx, void* cuda_stream);
 
