@@ -79,6 +79,9 @@ struct arv2_ctx {
     long long rec_capacity = 0, last_range_rays = 0;
     float4* d_pc_seg = nullptr; float* d_pc_energy = nullptr; int* d_pc_nseg = nullptr;
     long long pc_rays = 0; unsigned pc_bounces = 0;
+    // breadth-first tracer: per-depth path queues, grown on demand
+    float4* d_wave_paths = nullptr; size_t wave_slots = 0;
+    bool wave = true;
     int* d_ray_order = nullptr; long long order_begin = -1, order_n = -1; unsigned long long order_seed = 0;
     bool coherent_order = true;
     // pinned staging for the receiver sub-tree
@@ -251,6 +254,38 @@ int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
     return ARV2_OK;
 }
 
+// Queues of the breadth-first tracer for a launch of n_rays rays: per SM, wave_queues rings of wave_cap
+// path states.  Sets the wave_* fields of p (left null when the queues are off or cannot be allocated:
+// the launch then uses the depth-first persistent kernel).
+int ensure_wave(arv2_ctx* c, TraceParams* p, long long n_rays)
+{
+    if (!c->wave || n_rays <= 0 || n_rays > 0x7fffffffLL) return ARV2_OK;
+    // 4 segments per task, 2048 paths alive per SM (64 batches for 32 warps): measured best on B200 for 1M..16M rays
+    // (profiles/r05_wave_sweep.md; segments 1..8 x cap 1024..8192)
+    int per = 4;
+    if (const char* e = getenv("ARV2_WAVE_SEGMENTS")) per = atoi(e) > 0 ? atoi(e) : per;      // tuning aid
+    const unsigned mb = c->max_bounces < 1 ? 1u : c->max_bounces;
+    while ((mb + per - 1) / per > (unsigned)kWaveQueues) ++per;
+    const int nq = (int)((mb + per - 1) / per);
+    long long cap = 2048;
+    if (const char* e = getenv("ARV2_WAVE_CAP")) cap = atoll(e) >= 64 ? atoll(e) : cap;       // tuning aid
+    const long long share = (2 * n_rays / c->sm_count + 95) / 32 * 32;
+    if (share < cap) cap = share;
+    const size_t need = (size_t)c->sm_count * (size_t)nq * (size_t)cap;
+    if (need > c->wave_slots) {
+        cudaFree(c->d_wave_paths);
+        c->d_wave_paths = nullptr; c->wave_slots = 0;
+        if (cudaMalloc(&c->d_wave_paths, need * cont_f4(c->bands) * sizeof(float4)) != cudaSuccess) {
+            cudaGetLastError();
+            c->d_wave_paths = nullptr;
+            return ARV2_OK;                                   // not enough memory: depth-first kernel
+        }
+        c->wave_slots = need;
+    }
+    p->wave_paths = c->d_wave_paths; p->wave_cap = cap; p->wave_queues = nq; p->wave_segments = per;
+    return ARV2_OK;
+}
+
 int ensure_cache(arv2_ctx* c)
 {
     const long long n = c->n_rays_total;
@@ -270,7 +305,10 @@ int finish_timed(arv2_ctx* c, double* ms)
     CK(cudaMemcpyAsync(c->h_counters, c->d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));                    // CUDA_SYNC_CHECK, OR/AudioRenderer.cpp:511
     c->last_segments = (long long)c->h_counters[1];
-    if (getenv("ARV2_PRINT_STATS")) { for (int i = 0; i < 12; ++i) fprintf(stderr, "%llu ", c->h_counters[i]); fprintf(stderr, "\n"); }
+    if (c->h_counters[7] != 0) { set_error("trace: path-queue watchdog tripped (a warp waited too long for a queued path)"); return ARV2_ERR_CUDA; }
+    if (getenv("ARV2_TAILSTAT")) fprintf(stderr, "tail: pool empty -> first warp exit %.3f ms, -> last warp exit %.3f ms\n",
+                                         ((double)c->h_counters[6] - (double)c->h_counters[4]) * 1e-6, ((double)c->h_counters[5] - (double)c->h_counters[4]) * 1e-6);
+    if (getenv("ARV2_PRINT_STATS")) { for (int i = 0; i < 16; ++i) fprintf(stderr, "%llu ", c->h_counters[i]); fprintf(stderr, "\n"); }
     if (ms) { float t = 0.f; CK(cudaEventElapsedTime(&t, c->ev0, c->ev1)); *ms = t; }
     return ARV2_OK;
 }
@@ -432,7 +470,8 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     CK(cudaSetDevice(desc->device));
 
     auto* c = new arv2_ctx;
-    if (getenv("ARV2_NO_SORT")) c->coherent_order = false;   // tuning aid (A/B)
+    if (getenv("ARV2_NO_SORT")) c->coherent_order = false;   // tuning aids (A/B)
+    if (getenv("ARV2_NO_WAVE")) c->wave = false;
     c->desc = *desc; c->desc.materials = nullptr; c->desc.n_materials = 0;
     c->device = desc->device;
     c->bands = desc->bands;
@@ -536,7 +575,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     CKC(cudaMemset(c->d_hist, 0, 2 * irn * sizeof(double)));
     CKC(cudaMemset(c->d_ir_l, 0, irn * sizeof(float)));
     CKC(cudaMemset(c->d_ir_r, 0, irn * sizeof(float)));
-    CKC(cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long)));
+    CKC(cudaMalloc(&c->d_counters, kCounters * sizeof(unsigned long long)));
     if (desc->record_rays) {
         c->rec_capacity = n_total;
         CKC(cudaMalloc(&c->d_rec_bin, (size_t)n_total * sizeof(int)));
@@ -557,7 +596,7 @@ void arv2_destroy(arv2_ctx* c)
     cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_keep); cudaFree(c->d_scatter);
     cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_ir_r); cudaFree(c->d_counters);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
-    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg); cudaFree(c->d_ray_order);
+    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg); cudaFree(c->d_ray_order); cudaFree(c->d_wave_paths);
     cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -606,11 +645,14 @@ int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t ze
     if (rc != ARV2_OK) return rc;
     const size_t irn = (size_t)c->bands * c->ir_len;
     if (zero_first) CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));   // fillZeros, OR/AudioRenderer.cpp:491-492
-    CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->d_counters, 0, kCounters * sizeof(unsigned long long), c->stream));
+    if (getenv("ARV2_TAILSTAT")) { CK(cudaMemsetAsync(c->d_counters + 4, 0xFF, 8, c->stream)); CK(cudaMemsetAsync(c->d_counters + 6, 0xFF, 8, c->stream)); }
     rc = ensure_ray_order(c, ray_begin, n_rays);
     if (rc != ARV2_OK) return rc;
     TraceParams p;
     fill_params(c, &p, ray_begin, n_rays);
+    rc = ensure_wave(c, &p, n_rays);
+    if (rc != ARV2_OK) return rc;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (n_rays > 0) CK(launch_trace(p, c->bands, 0, c->sm_count, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -665,10 +707,12 @@ int arv2_render(arv2_ctx* c, double* ms)
         if (rc != ARV2_OK) return rc;
         rc = ensure_ray_order(c, 0, c->n_rays_total);
         if (rc != ARV2_OK) return rc;
-        CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
+        CK(cudaMemsetAsync(c->d_counters, 0, kCounters * sizeof(unsigned long long), c->stream));
         TraceParams p;
         fill_params(c, &p, 0, c->n_rays_total);
         p.rec_bin = nullptr; p.rec_ear = nullptr; p.rec_energy = nullptr; p.rec_nseg = nullptr;
+        rc = ensure_wave(c, &p, c->n_rays_total);
+        if (rc != ARV2_OK) return rc;
         CK(cudaEventRecord(c->ev0, c->stream));
         CK(launch_trace(p, c->bands, 1, c->sm_count, c->stream));
         CK(cudaEventRecord(c->ev1, c->stream));

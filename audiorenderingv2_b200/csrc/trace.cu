@@ -37,7 +37,10 @@ constexpr int kStack = kTraversalStack;
 #define ARV2_THREADS 128
 #endif
 #ifndef ARV2_MINB
-#define ARV2_MINB 6
+#define ARV2_MINB 9                  // 56 registers, 36 warps/SM for one band (no spills); 8 bands: 64 registers, 32 warps/SM
+#endif
+#ifndef ARV2_MINB8
+#define ARV2_MINB8 8
 #endif
 constexpr int kThreads = ARV2_THREADS;
 constexpr int kSentinel = INT_MIN;   // "nothing (left) to traverse"
@@ -360,6 +363,9 @@ __device__ __forceinline__ bool refill(const TraceParams& p, bool want, long lon
             chunk_next = (long long)b;
             chunk_end = min((long long)b + p.chunk, p.n_rays);
             if (chunk_next >= chunk_end) {
+#ifdef ARV2_TAILSTAT
+                if (lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(p.counters + 4, t); }
+#endif
                 if (want && !got) exhausted = true;
                 break;
             }
@@ -376,10 +382,61 @@ __device__ __forceinline__ bool refill(const TraceParams& p, bool want, long lon
     return got;
 }
 
+// ---- path states in the per-depth queues of wave_kernel ----
+// A path at a segment boundary is (ray, org, dir, dist, depth, energy[NB]); nseg == depth there
+// (every finished segment either ends the path or bounces it once).
+template <int NB>
+__device__ __forceinline__ void store_path(float4* o, const Path<NB>& s)
+{
+    __stcg(o + 0, make_float4(s.org.x, s.org.y, s.org.z, s.dist));
+    __stcg(o + 1, make_float4(s.dir.x, s.dir.y, s.dir.z, __int_as_float((int)s.ray)));
+    if (NB == 1) {
+        __stcg(o + 2, make_float4(s.energy[0], __int_as_float(s.depth), 0.f, 0.f));
+    } else {
+#pragma unroll
+        for (int q = 0; q < NB / 4; ++q) __stcg(o + 2 + q, make_float4(s.energy[4 * q], s.energy[4 * q + 1], s.energy[4 * q + 2], s.energy[4 * q + 3]));
+        __stcg(o + 2 + NB / 4, make_float4(__int_as_float(s.depth), 0.f, 0.f, 0.f));
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void load_path(const float4* i, Path<NB>& s)
+{
+    const float4 a = __ldcg(i), b = __ldcg(i + 1);
+    s.org = f3(a.x, a.y, a.z); s.dist = a.w;
+    s.dir = f3(b.x, b.y, b.z); s.ray = (long long)__float_as_int(b.w);
+    if (NB == 1) {
+        const float4 c = __ldcg(i + 2);
+        s.energy[0] = c.x; s.depth = __float_as_int(c.y);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NB / 4; ++q) {
+            const float4 c = __ldcg(i + 2 + q);
+            s.energy[4 * q] = c.x; s.energy[4 * q + 1] = c.y; s.energy[4 * q + 2] = c.z; s.energy[4 * q + 3] = c.w;
+        }
+        s.depth = __float_as_int(__ldcg(i + 2 + NB / 4).x);
+    }
+    s.nseg = s.depth;
+}
+
+// One segment of one path (the body of the loop of __raygen__renderFrame, :233-252).
+template <int NB, int MODE>
+__device__ __forceinline__ bool advance_segment(const TraceParams& p, Path<NB>& s, int* stack, Traversal& tr, Deposit& d)
+{
+    if (!path_goes_on<NB>(p, s)) return true;                                         // :233-236
+    begin_segment<NB, MODE>(p, s);
+    // only segments whose line meets the receiver's bounding ball start at the two-level
+    // top node; the others go straight into the scene tree (the top node's AABB of
+    // the ball would let 3x as many lanes into the receiver tree)
+    const bool to_recv = MODE == 0 && p.recv_root >= 0 && enters_receiver_ball(p, s.org, s.dir, 1e20f);
+    closest_hit(p, stack, tr, to_recv ? p.root : p.scene_root, s.org, s.dir, 1e20f);
+    return shade_segment<NB, MODE>(p, s, tr.h, d);
+}
+
 // ---------------------------------------------------------------------------------------
 // trace_kernel: while-while traversal, all lanes of a warp advance segment by segment.
 template <int NB, int MODE>
-__global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceParams p)
+__global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) trace_kernel(const TraceParams p)
 {
     const int lane = threadIdx.x & 31;
     long long chunk_next = 0, chunk_end = 0;      // warp-uniform
@@ -397,19 +454,7 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceP
 
         bool ended = false;
         Deposit d; d.dep = false; d.bin = -1; d.ear = 0; d.primary = 0;
-        if (have) {
-            if (!path_goes_on<NB>(p, s)) {
-                ended = true;                                                         // :233-236
-            } else {
-                begin_segment<NB, MODE>(p, s);
-                // only segments whose line meets the receiver's bounding ball start at the two-level
-                // top node; the others go straight into the scene tree (the top node's AABB of
-                // the ball would let 3x as many lanes into the receiver tree)
-                const bool to_recv = MODE == 0 && p.recv_root >= 0 && enters_receiver_ball(p, s.org, s.dir, 1e20f);
-                closest_hit(p, stack, tr, to_recv ? p.root : p.scene_root, s.org, s.dir, 1e20f);
-                ended = shade_segment<NB, MODE>(p, s, tr.h, d);
-            }
-        }
+        if (have) ended = advance_segment<NB, MODE>(p, s, stack, tr, d);
         if (MODE == 0) deposit_warp<NB>(p, d.dep, d.bin, d.primary, s.energy);
         if (ended) {
             end_path<NB, MODE>(p, s, d, segs);
@@ -419,6 +464,169 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceP
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
     if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+#ifdef ARV2_TAILSTAT
+    if (lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(p.counters + 5, t); atomicMin(p.counters + 6, t); }
+#endif
+}
+
+// ---------------------------------------------------------------------------------------
+// wave_kernel: breadth-first persistent tracer, one 32-warp CTA per SM.
+// A task = up to 32 paths of the same depth advanced by wave_segments segments; the paths that go on
+// are appended to the queue of their new depth.  A warp looking for work starts fresh rays while its
+// SM has room (wave_cap paths alive) and otherwise takes a batch from the SHALLOWEST non-empty queue.
+//   * The paths of a task were started together as neighbours of the direction order and have bounced
+//     equally often: a warp stays a coherent bundle for as long as the scene allows, without idle
+//     lanes, because the survivors are re-packed at every hand-over.
+//   * The youngest paths always run first, so the render has no ramp-down.  In trace_kernel a lane
+//     starts its last ray late and the warp then waits up to max_bounces segments for it: the last
+//     2 ms of a 7.5 ms render (1M rays, profiles/r05) ran at a few live lanes per warp.
+// Every SM owns its queues: positions and counters live in shared memory (reserve `tail`, in-order
+// publish `pub`, claim `head` by CAS), only the 48 B path states go through L2.  The only global
+// counter is the pool of unstarted rays.  wave_cap bounds the paths alive per SM, which keeps a
+// ring slot from being rewritten before it was read.
+constexpr int kWaveThreads = 1024;
+
+template <int NB, int MODE>
+__global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams p)
+{
+    __shared__ unsigned q_tail[kWaveQueues], q_pub[kWaveQueues], q_head[kWaveQueues];
+    __shared__ int sh_alive, sh_pool_done;
+    if (threadIdx.x < kWaveQueues) { q_tail[threadIdx.x] = 0; q_pub[threadIdx.x] = 0; q_head[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) { sh_alive = 0; sh_pool_done = 0; }
+    __syncthreads();
+    volatile unsigned* const v_pub = q_pub;
+    volatile unsigned* const v_head = q_head;
+    volatile int* const v_alive = &sh_alive;
+    volatile int* const v_done = &sh_pool_done;
+
+    const int lane = threadIdx.x & 31;
+    const int cap = (int)p.wave_cap;
+    const int nq = p.wave_queues;
+    float4* const paths = p.wave_paths + (size_t)blockIdx.x * (size_t)nq * (size_t)cap * cont_f4(NB);
+    unsigned long long segs = 0;
+    Path<NB> s;
+    s.ray = 0; s.org = f3(0, 0, 0); s.dir = f3(0, 0, 0); s.dist = 0.f; s.depth = 0; s.nseg = 0;
+    Traversal tr;
+    int stack[kStack];
+    unsigned idle = 0;
+#ifdef ARV2_WAVESTAT
+    unsigned long long st_tasks = 0, st_rays = 0, st_fail = 0, st_idle = 0;
+#define WST(x) x
+#else
+#define WST(x)
+#endif
+
+    for (;;) {
+        // ---------------- find work (warp-uniform: src, n, pos)
+        int src = -2, n = 0;                     // -1: fresh rays, >= 0: queue index
+        unsigned long long pos = 0;
+        if (lane == 0 && !*v_done && *v_alive + 32 <= cap) {
+            if (atomicAdd(&sh_alive, 32) + 32 <= cap) {
+                const long long b = (long long)atomicAdd(p.counters, 32ull);
+                long long take = p.n_rays - b;
+                take = take < 0 ? 0 : (take > 32 ? 32 : take);
+                if (take < 32) atomicSub(&sh_alive, 32 - (int)take);
+                if (take > 0) { src = -1; n = (int)take; pos = (unsigned long long)b; }
+                else *v_done = 1;
+            } else {
+                atomicSub(&sh_alive, 32);
+            }
+        }
+        src = __shfl_sync(FULL, src, 0);
+        if (src == -2) {
+            // shallowest queue with a full batch; a warp that found nothing last time also takes a partial one
+            const int need = idle == 0 ? 32 : 1;
+            int a0 = 0, a1 = 0;
+            if (lane < nq) { const unsigned h = v_head[lane]; a0 = (int)(v_pub[lane] - h); }
+            if (lane + 32 < nq) { const unsigned h = v_head[lane + 32]; a1 = (int)(v_pub[lane + 32] - h); }
+            unsigned long long cand = (unsigned long long)__ballot_sync(FULL, a0 >= need) | ((unsigned long long)__ballot_sync(FULL, a1 >= need) << 32);
+            if (lane == 0) {
+                while (cand && src == -2) {
+                    const int q = __ffsll((long long)cand) - 1;
+                    cand &= cand - 1;
+                    for (;;) {
+                        const unsigned h = v_head[q];
+                        const int av = (int)(v_pub[q] - h);
+                        if (av < need) { WST(++st_fail;) break; }
+                        const int take = av < 32 ? av : 32;
+                        if (atomicCAS(&q_head[q], h, h + (unsigned)take) == h) { n = take; pos = h; src = q; break; }
+                    }
+                }
+            }
+            src = __shfl_sync(FULL, src, 0);
+        }
+        n = __shfl_sync(FULL, n, 0);
+        pos = __shfl_sync(FULL, pos, 0);
+
+        if (src == -2) {
+            // nothing to take: done when no ray is left to start and no path of this SM is alive
+            int done = 0;
+            if (lane == 0) done = *v_done && *v_alive == 0;
+            if (__shfl_sync(FULL, done, 0)) break;
+            WST(if (lane == 0) ++st_idle;)
+            if (++idle > (1u << 24)) { if (lane == 0) atomicAdd(p.counters + 7, 1ull); break; }      // watchdog
+            __nanosleep(100);
+            continue;
+        }
+        idle = 0;
+        WST(if (lane == 0) { ++st_tasks; st_rays += n; })
+
+        // ---------------- take the batch
+        bool have = lane < n;
+        if (src == -1) {
+            if (have) new_path<NB>(p, s, (long long)pos + lane);
+        } else {
+            __threadfence_block();
+            if (have) load_path<NB>(paths + ((size_t)src * cap + (unsigned)(pos + lane) % (unsigned)cap) * cont_f4(NB), s);
+        }
+
+        // ---------------- advance
+        int ended_n = 0;
+        for (int k = 0; k < p.wave_segments; ++k) {
+            if (!__any_sync(FULL, have)) break;
+            bool ended = false;
+            Deposit d; d.dep = false; d.bin = -1; d.ear = 0; d.primary = 0;
+            if (have) ended = advance_segment<NB, MODE>(p, s, stack, tr, d);
+            if (MODE == 0) deposit_warp<NB>(p, d.dep, d.bin, d.primary, s.energy);
+            if (ended) { end_path<NB, MODE>(p, s, d, segs); have = false; ++ended_n; }
+        }
+        if (have && !path_goes_on<NB>(p, s)) {                   // would end at its next loop guard
+            Deposit none; none.dep = false; none.bin = -1; none.ear = 0; none.primary = 0;
+            end_path<NB, MODE>(p, s, none, segs); have = false; ++ended_n;
+        }
+
+        // ---------------- append the paths that go on to the queue of their depth
+        const int qn = src + 1;
+        const unsigned m = __ballot_sync(FULL, have);
+        if (m) {
+            if (qn >= nq) { if (lane == 0) atomicAdd(p.counters + 7, 1ull); break; }      // cannot happen: depth < max_bounces
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&q_tail[qn], (unsigned)__popc(m));
+            base = __shfl_sync(FULL, base, 0);
+            if (have) {
+                store_path<NB>(paths + ((size_t)qn * cap + (base + __popc(m & ((1u << lane) - 1u))) % (unsigned)cap) * cont_f4(NB), s);
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane == 0) {
+                while (v_pub[qn] != base) __nanosleep(20);       // publish in reservation order
+                v_pub[qn] = base + (unsigned)__popc(m);
+                __threadfence_block();
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ended_n += __shfl_xor_sync(FULL, ended_n, o);
+        if (lane == 0 && ended_n) atomicSub(&sh_alive, ended_n);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
+    if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+#ifdef ARV2_WAVESTAT
+    if (lane == 0) {
+        atomicAdd(p.counters + 8, st_tasks); atomicAdd(p.counters + 9, st_rays); atomicAdd(p.counters + 10, st_fail);
+        atomicAdd(p.counters + 11, st_idle);
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -441,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, ARV2_MINB) trace_kernel(const TraceP
 #define ARV2_BURST 4
 #endif
 template <int NB, int MODE>
-__global__ void __launch_bounds__(kThreads, ARV2_MINB) trace2_kernel(const TraceParams p)
+__global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) trace2_kernel(const TraceParams p)
 {
     const int lane = threadIdx.x & 31;
     long long chunk_next = 0, chunk_end = 0;      // warp-uniform
@@ -661,10 +869,14 @@ __global__ void finalize_kernel(const double* __restrict__ hist, int n, int mono
 template <int NB, int MODE>
 cudaError_t launch_trace_t(const TraceParams& p, int sm_count, cudaStream_t stream)
 {
-#ifdef ARV2_TRACE_V2
-    auto kernel = trace2_kernel<NB, MODE>;
-#else
+#ifndef ARV2_TRACE_V2
+    if (p.wave_paths) {
+        wave_kernel<NB, MODE><<<(unsigned)sm_count, kWaveThreads, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
     auto kernel = trace_kernel<NB, MODE>;
+#else
+    auto kernel = trace2_kernel<NB, MODE>;
 #endif
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);

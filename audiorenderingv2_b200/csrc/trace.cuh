@@ -14,7 +14,7 @@ struct TraceParams {
     const float* keep;          // [n_mats][bands]  1 - mat_absorption
     const float* scattering;    // [n_mats]
     double* hist;               // [2][bands][ir_len] fp64 accumulation
-    unsigned long long* counters; // [0] next ray chunk, [1] segments traced
+    unsigned long long* counters; // [0] next ray chunk, [1] segments traced, [7] watchdog
     int* rec_bin; int* rec_ear; float* rec_energy; int* rec_nseg;   // optional per-ray records
     // receiver-independent path cache (optional): per segment k of ray r at [k*stride + r]
     float4* pc_seg;             // 32 B per cached segment: (origin.xyz, t_wall or 1e20 on miss), (dir.xyz, distance before)
@@ -31,10 +31,19 @@ struct TraceParams {
     int root;                   // node the full trace starts at (0 = two-level top node)
     int scene_root, recv_root;  // roots of the two sub-trees (-1: absent)
     int any_scatter;            // 0: skip the diffuse-bounce RNG entirely
+    // breadth-first tracer (wave_kernel; optional): per-SM, per-depth queues of path states
+    float4* wave_paths;         // [sm][wave_queues][wave_cap][cont_f4(bands)]
+    long long wave_cap;         // ring slots per queue = most paths alive per SM
+    int wave_queues;            // queue j holds paths of depth (j + 1) * wave_segments
+    int wave_segments;          // segments per task
     const int* ray_order;       // optional: the order in which the launch's rays [0, n_rays) are started (direction-sorted)
     int chunk;                  // rays a warp claims per global atomic
     int refill_below;           // lanes of a warp are refilled only while fewer than this many hold a path (32 = always)
 };
+
+constexpr int kWaveQueues = 64;               // most per-depth queues of wave_kernel
+constexpr int kCounters = 16;                 // unsigned long long counters per context
+__host__ __device__ constexpr int cont_f4(int bands) { return bands == 1 ? 3 : 5; }   // float4 per queued path
 
 // mode 0: full trace (scene + receiver), deposits into hist.
 // mode 1: scene-only trace that fills the path cache (no deposits).

@@ -222,6 +222,9 @@ def main():
     if os.environ.get("ARV2_BENCH_RAYS"):           # tuning aid (tail-effect experiments); not a driver-facing line
         global RAYS
         RAYS = (int(os.environ["ARV2_BENCH_RAYS"]), 1, 1)
+    if os.environ.get("ARV2_BENCH_BOUNCES"):
+        global MAX_BOUNCES
+        MAX_BOUNCES = int(os.environ["ARV2_BENCH_BOUNCES"])
     args.warmup = max(args.warmup, 3) if args.impl == "arv2" else args.warmup
 
     if args.impl == "reference":
@@ -358,7 +361,7 @@ def main():
                 "d2h_bytes_per_step": ir_bytes + 16, "ms_per_step": float(t_e2e.sum().item()) / args.steps},
         "gpu_launches": 2 * args.steps,
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": f"trace_kernel<{BANDS},0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": f"wave_kernel<{BANDS},0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": segs_per_launch * BYTES_PER_SEGMENT,
                      "bytes_per_segment": BYTES_PER_SEGMENT, "kernel_ms": kernel_ms},
