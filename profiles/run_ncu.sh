@@ -10,7 +10,7 @@ mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.json 2> gpurun_out/plain_$TAG.err || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 3 -c 1 -o gpurun_out/trace_$TAG -f $CMD > gpurun_out/ncu_trace_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:wave_kernel|trace_kernel" -s 3 -c 1 -o gpurun_out/trace_$TAG -f $CMD > gpurun_out/ncu_trace_$TAG.log 2>&1
 echo "trace capture rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:rerender_kernel -s 5 -c 1 -o gpurun_out/rerender_$TAG -f $CMD > gpurun_out/ncu_rerender_$TAG.log 2>&1
 echo "rerender capture rc=$?"
