@@ -118,8 +118,16 @@ __global__ void __launch_bounds__(kConvThreads) block_spectra_kernel(const float
 // of a partition (X, H_left, H_right: block*8 B each) are instead pulled into a 4-stage
 // shared-memory ring by bulk async copies that complete on an mbarrier; the threads only
 // read shared memory.
-constexpr int kStages = 4;
-constexpr int kFftCostInPartitions = 8;   // forward FFT of one block ~ streaming 8 partitions (clock64-measured)
+// 4 stages x 12 KB in flight per SM already stream the spectra at the L2 rate (128 SMs x ~60 GB/s); 8 and 12
+// stages measured 26 us per step instead of 16.4 (profiles/micro/conv_ab.py)
+#ifndef ARV2_CONV_STAGES
+#define ARV2_CONV_STAGES 4
+#endif
+#ifndef ARV2_CONV_FFTCOST
+#define ARV2_CONV_FFTCOST 8
+#endif
+constexpr int kStages = ARV2_CONV_STAGES;
+constexpr int kFftCostInPartitions = ARV2_CONV_FFTCOST;   // forward FFT of one block ~ streaming 8 partitions (clock64-measured)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
