@@ -198,7 +198,7 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
         p->rec_bin = c->d_rec_bin; p->rec_ear = c->d_rec_ear; p->rec_energy = c->d_rec_energy; p->rec_nseg = c->d_rec_nseg;
     }
     p->pc_seg = c->d_pc_seg; p->pc_energy = c->d_pc_energy; p->pc_nseg = c->d_pc_nseg;
-    p->pc_stride = c->pc_rays;
+    p->pc_stride = (long long)c->pc_bounces;
     p->seed = c->seed; p->ray_begin = ray_begin; p->n_rays = n_rays;
     for (int a = 0; a < 3; ++a) { p->emitter[a] = c->emitter[a]; p->center[a] = c->center[a]; }
     p->recv_radius = c->recv_radius;
@@ -289,6 +289,7 @@ int ensure_wave(arv2_ctx* c, TraceParams* p, long long n_rays)
 int ensure_cache(arv2_ctx* c)
 {
     const long long n = c->n_rays_total;
+    if (c->max_bounces > 65535u || n > 0x7fffffffLL) { set_error("path cache: max_bounces <= 65535 and at most 2^31 rays"); return ARV2_ERR_INVALID; }
     if (c->d_pc_seg && c->pc_rays == n && c->pc_bounces >= c->max_bounces) return ARV2_OK;
     cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg);
     c->d_pc_seg = nullptr; c->d_pc_energy = nullptr; c->d_pc_nseg = nullptr;

@@ -45,7 +45,6 @@ constexpr int kStack = kTraversalStack;
 constexpr int kThreads = ARV2_THREADS;
 constexpr int kSentinel = INT_MIN;   // "nothing (left) to traverse"
 constexpr int kRerenderThreads = 256;
-constexpr int kRerenderBatch = 12;   // lanes that must hold a candidate before the receiver walk
 
 struct Hit { float t, u, v; int slot, id; };
 
@@ -58,6 +57,12 @@ __device__ __forceinline__ F8 ldg256(const float4* p)
         : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
         : "l"(p));
     return r;
+}
+
+__device__ __forceinline__ void stg256(float4* p, float4 lo, float4 hi)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
 }
 
 __device__ __forceinline__ float safe_rcp(float d)
@@ -259,7 +264,13 @@ struct Deposit { bool dep; int bin, ear, primary; };
 template <int NB, int MODE>
 __device__ __forceinline__ bool shade_segment(const TraceParams& p, Path<NB>& s, const Hit& h, Deposit& d)
 {
-    if (MODE == 1) p.pc_seg[2 * ((size_t)(s.nseg - 1) * (size_t)p.pc_stride + (size_t)s.ray)] = make_float4(s.org.x, s.org.y, s.org.z, h.t);
+    if (MODE == 1) {
+        // path cache: the finished segment as one 32 B record (s.dir, s.dist and s.energy still describe its start)
+        const size_t ci = (size_t)s.ray * (size_t)p.pc_stride + (size_t)(s.nseg - 1);
+        stg256(p.pc_seg + 2 * ci, make_float4(s.org.x, s.org.y, s.org.z, h.t), make_float4(s.dir.x, s.dir.y, s.dir.z, s.dist));
+#pragma unroll
+        for (int b = 0; b < NB; ++b) p.pc_energy[ci * NB + b] = s.energy[b];
+    }
     if (h.slot < 0) return true;                                                     // miss :186-190
     const F8 A = ldg256(p.tris + h.slot * 4), B = ldg256(p.tris + h.slot * 4 + 2);
     const F3 p1 = f3(A.lo.x, A.lo.y, A.lo.z), p2 = f3(A.hi.x, A.hi.y, A.hi.z), p3 = f3(B.lo.x, B.lo.y, B.lo.z);
@@ -337,12 +348,6 @@ __device__ __forceinline__ void new_path(const TraceParams& p, Path<NB>& s, long
 template <int NB, int MODE>
 __device__ __forceinline__ void begin_segment(const TraceParams& p, Path<NB>& s)
 {
-    if (MODE == 1) {
-        const size_t ci = (size_t)s.nseg * (size_t)p.pc_stride + (size_t)s.ray;
-        p.pc_seg[2 * ci + 1] = make_float4(s.dir.x, s.dir.y, s.dir.z, s.dist);
-#pragma unroll
-        for (int b = 0; b < NB; ++b) p.pc_energy[ci * NB + b] = s.energy[b];
-    }
     s.nseg++;
 }
 
@@ -716,23 +721,35 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
 }
 
 // ---------------------------------------------------------------------------------------
-// Receiver move: walk each ray's cached receiver-independent segments in order and
-// deposit at the first one the receiver intercepts before the wall (t_recv < t_wall;
-// ties go to the scene because scene triangle ids are lower).  One thread per ray,
-// lanes = consecutive rays, so every load of segment k is a coalesced 512 B row.
-// A segment is first tested against the receiver's bounding ball (a few FMAs, exact-
-// conservative); lanes whose segment passes park it and keep waiting until enough lanes of
-// the warp hold a candidate (or nobody is scanning), then those lanes walk the receiver
-// tree together -- the r01 profile had this traversal running at 2.9 of 32 lanes.
+// Receiver move: walk each ray's cached receiver-independent segments in order and deposit at
+// the first one the receiver intercepts before the wall (t_recv < t_wall; ties go to the scene
+// because scene triangle ids are lower).
+// The cache is ray-major (a ray's records are consecutive 32 B sectors), a lane streams its ray two
+// records (one 64 B DRAM burst) at a time.  A segment is first tested against the receiver's
+// bounding ball (a few FMAs, exact-conservative).  Two things keep the warp full (r04 profile of
+// the version that walked the receiver tree as soon as 12 lanes held a candidate: 6.8 of 32
+// lanes per instruction, 446 M warp instructions):
+//   * a lane whose segment enters the ball PARKS (ray, k) in the warp's candidate buffer and takes
+//     the next ray, so 32 lanes keep scanning;
+//   * the receiver tree is walked only when 32 candidates are parked -- a full warp of walks; a
+//     candidate that misses the mesh goes to the warp's resume buffer and is scanned on from k+1.
+// A warp admits new rays only while it holds at most 32 parked ones, so 64 slots per buffer suffice.
+constexpr int kParkSlots = 64;
+
 template <int NB>
 __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceParams p)
 {
+    __shared__ int2 sh_cand[kRerenderThreads / 32][kParkSlots];   // (ray, k | n << 16)
+    __shared__ int2 sh_res[kRerenderThreads / 32][kParkSlots];
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int2* const cand = sh_cand[threadIdx.x >> 5];
+    int2* const res = sh_res[threadIdx.x >> 5];
+    int n_cand = 0, n_res = 0;                    // warp-uniform
     long long chunk_next = 0, chunk_end = 0;      // warp-uniform
-    bool have = false, exhausted = false, cand = false;
-    long long ray = 0;
-    int k = 0, n = 0;
-    float4 ot = make_float4(0, 0, 0, 0), dd = make_float4(0, 0, 0, 0);
+    bool pool_empty = false;                      // warp-uniform
+    bool have = false;
+    int ray = 0, k = 0, n = 0;
     float energy[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) energy[b] = 0.f;
@@ -740,71 +757,72 @@ __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceP
     Traversal tr;
     int stack[kStack];
 
-    // rays that leave the scan: miss (every cached segment passed) or receiver hit
-    auto finish = [&](int bin, int ear, int nseg) {
-        if (p.rec_bin) p.rec_bin[ray] = bin;
-        if (p.rec_ear) p.rec_ear[ray] = ear;
-        if (p.rec_nseg) p.rec_nseg[ray] = nseg;
+    // a ray leaves: miss (every cached segment passed) or receiver hit
+    auto finish = [&](int r, int bin, int ear, int nseg) {
+        if (p.rec_bin) p.rec_bin[r] = bin;
+        if (p.rec_ear) p.rec_ear[r] = ear;
+        if (p.rec_nseg) p.rec_nseg[r] = nseg;
         if (p.rec_energy) {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) p.rec_energy[ray * NB + b] = ear ? energy[b] : 0.f;
+            for (int b = 0; b < NB; ++b) p.rec_energy[(size_t)r * NB + b] = ear ? energy[b] : 0.f;
         }
         segs += (unsigned long long)nseg;
-        have = false;
     };
 
     for (;;) {
-        // ---- refill: lanes without a ray claim the next ones of the warp's chunk, so the scan
-        // keeps ~32 lanes busy although the rays of a warp end at very different segments
-        // (r02 profile of the one-thread-per-ray version: 5.9 of 32 lanes per instruction)
-        unsigned need = __ballot_sync(FULL, !have && !exhausted);
-        while (need) {
+        // ---- refill the lanes without a ray: parked misses first, then the pool
+        unsigned need = __ballot_sync(FULL, !have);
+        if (need && n_res > 0) {
+            const int take = min(__popc(need), n_res);
+            const int rank = __popc(need & lt);
+            if (!have && rank < take) {
+                const int2 e = res[n_res - 1 - rank];
+                ray = e.x; k = e.y & 0xffff; n = (int)((unsigned)e.y >> 16); have = true;
+            }
+            n_res -= take;
+            __syncwarp();
+            need = __ballot_sync(FULL, !have);
+        }
+        while (need && !pool_empty && n_cand + n_res <= 32) {
             if (chunk_next >= chunk_end) {
                 unsigned long long b = 0;
                 if (lane == 0) b = atomicAdd(p.counters, (unsigned long long)kChunk);
                 b = __shfl_sync(FULL, b, 0);
                 chunk_next = (long long)b;
                 chunk_end = min((long long)b + kChunk, p.n_rays);
-                if (chunk_next >= chunk_end) {
-                    if (!have) exhausted = true;
-                    break;
-                }
+                if (chunk_next >= chunk_end) { pool_empty = true; break; }
             }
             const int avail = (int)min((long long)32, chunk_end - chunk_next);
-            const int rank = __popc(need & ((1u << lane) - 1u));
-            if (((need >> lane) & 1u) && rank < avail) {
-                ray = chunk_next + rank;
+            const int rank = __popc(need & lt);
+            if (!have && rank < avail) {
+                ray = (int)(chunk_next + rank);
                 n = p.pc_nseg[ray];
                 k = 0;
-                have = true;
-                if (n == 0) finish(-1, 0, 0);
+                have = n > 0;
+                if (n == 0) finish(ray, -1, 0, 0);
             }
             chunk_next += min(__popc(need), avail);
-            need = __ballot_sync(FULL, !have && !exhausted);
+            need = __ballot_sync(FULL, !have);
         }
-        if (!__any_sync(FULL, have)) break;
+        const unsigned hv = __ballot_sync(FULL, have);
+        if (hv == 0 && n_cand == 0) {
+            if (n_res == 0 && pool_empty) break;
+            if (n_res == 0 && !pool_empty) continue;     // (cannot happen: the pool refill ran)
+        }
 
-        // ---- scan: advance to the next cached segment that enters the receiver's bounding ball
-        if (have && !cand) {
-#pragma unroll 1
-            for (int burst = 0; burst < 8; ++burst) {
-                const size_t ci = (size_t)k * (size_t)p.pc_stride + (size_t)ray;
-                // one 32 B record = one sector = one 256-bit load, whatever k the other lanes are at
-                const F8 rec = ldg256(p.pc_seg + 2 * ci);
-                ot = rec.lo; dd = rec.hi;
-                if (enters_receiver_ball(p, f3(ot.x, ot.y, ot.z), f3(dd.x, dd.y, dd.z), ot.w)) { cand = true; break; }
-                if (++k >= n) { finish(-1, 0, n); break; }
-            }
-        }
-        // ---- receiver walk, batched: only when enough lanes hold a candidate (or nobody scans)
-        const unsigned cm = __ballot_sync(FULL, cand);
-        const unsigned sm = __ballot_sync(FULL, have && !cand);
-        const unsigned idle = __ballot_sync(FULL, !have && !exhausted);
-        if (cm != 0 && (__popc(cm) >= kRerenderBatch || (sm == 0 && idle == 0))) {
+        if (n_cand >= 32 || (hv == 0 && n_cand > 0)) {
+            // ---- receiver walk for up to 32 parked candidates
+            const int m = min(32, n_cand);
             bool dep = false;
             int bin = -1, primary = 0;
-            if (cand) {
-                cand = false;
+            bool miss = false;
+            int c_ray = 0, c_k = 0, c_n = 0;
+            if (lane < m) {
+                const int2 e = cand[n_cand - m + lane];
+                c_ray = e.x; c_k = e.y & 0xffff; c_n = (int)((unsigned)e.y >> 16);
+                const size_t ci = (size_t)c_ray * (size_t)p.pc_stride + (size_t)c_k;
+                const F8 rec = ldg256(p.pc_seg + 2 * ci);
+                const float4 ot = rec.lo, dd = rec.hi;
                 const F3 org = f3(ot.x, ot.y, ot.z), dir = f3(dd.x, dd.y, dd.z);
                 closest_hit(p, stack, tr, p.recv_root, org, dir, ot.w);
                 const Hit& h = tr.h;
@@ -814,18 +832,48 @@ __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceP
                     const F3 pt = hit_point(f3(A.lo.x, A.lo.y, A.lo.z), f3(A.hi.x, A.hi.y, A.hi.z), f3(B.lo.x, B.lo.y, B.lo.z), h.u, h.v);
                     const F3 dp = sub3(pt, org);
                     const float dist = __fadd_rn(dd.w, __fsqrt_rn(dot3(dp, dp)));
-                    const size_t ci = (size_t)k * (size_t)p.pc_stride + (size_t)ray;
 #pragma unroll
                     for (int b = 0; b < NB; ++b) energy[b] = p.pc_energy[ci * NB + b];
                     bin = receiver_hit<NB>(p, pt, dir, dist, energy);
                     primary = (mat == -1) ? 0 : 1;
                     dep = bin >= 0 && bin < p.ir_len;
-                    finish(bin, (mat == -1) ? 1 : 2, k + 1);
-                } else if (++k >= n) {
-                    finish(-1, 0, n);
+                    finish(c_ray, bin, (mat == -1) ? 1 : 2, c_k + 1);
+                } else if (c_k + 1 >= c_n) {
+                    finish(c_ray, -1, 0, c_n);
+                } else {
+                    miss = true;
                 }
             }
             deposit_warp<NB>(p, dep, bin, primary, energy);
+            n_cand -= m;
+            const unsigned mm = __ballot_sync(FULL, miss);
+            if (miss) res[n_res + __popc(mm & lt)] = make_int2(c_ray, (c_k + 1) | (c_n << 16));
+            n_res += __popc(mm);
+            __syncwarp();
+            continue;
+        }
+
+        // ---- scan: advance to the next cached segment that enters the receiver's bounding ball
+        bool found = false;
+        if (have) {
+            const float4* rec = p.pc_seg + 2 * ((size_t)ray * (size_t)p.pc_stride + (size_t)k);
+#pragma unroll 1
+            for (int burst = 0; burst < 4; ++burst) {
+                const F8 r0 = ldg256(rec);
+                F8 r1 = r0;
+                if (k + 1 < n) r1 = ldg256(rec + 2);
+                if (enters_receiver_ball(p, f3(r0.lo.x, r0.lo.y, r0.lo.z), f3(r0.hi.x, r0.hi.y, r0.hi.z), r0.lo.w)) { found = true; break; }
+                if (++k >= n) { finish(ray, -1, 0, n); have = false; break; }
+                if (enters_receiver_ball(p, f3(r1.lo.x, r1.lo.y, r1.lo.z), f3(r1.hi.x, r1.hi.y, r1.hi.z), r1.lo.w)) { found = true; break; }
+                if (++k >= n) { finish(ray, -1, 0, n); have = false; break; }
+                rec += 4;
+            }
+        }
+        const unsigned fm = __ballot_sync(FULL, found);
+        if (fm) {
+            if (found) { cand[n_cand + __popc(fm & lt)] = make_int2(ray, k | (n << 16)); have = false; }
+            n_cand += __popc(fm);
+            __syncwarp();
         }
     }
 #pragma unroll

@@ -16,11 +16,11 @@ struct TraceParams {
     double* hist;               // [2][bands][ir_len] fp64 accumulation
     unsigned long long* counters; // [0] next ray chunk, [1] segments traced, [7] watchdog
     int* rec_bin; int* rec_ear; float* rec_energy; int* rec_nseg;   // optional per-ray records
-    // receiver-independent path cache (optional): per segment k of ray r at [k*stride + r]
+    // receiver-independent path cache (optional), ray-major: segment k of ray r at [r*stride + k]
     float4* pc_seg;             // 32 B per cached segment: (origin.xyz, t_wall or 1e20 on miss), (dir.xyz, distance before)
-    float* pc_energy;           // [k*stride + r][bands]
+    float* pc_energy;           // [r*stride + k][bands]
     int* pc_nseg;               // [r] segments cached
-    long long pc_stride;
+    long long pc_stride;        // records per ray (>= max_bounces)
     unsigned long long seed;
     long long ray_begin, n_rays;
     float emitter[3], center[3];
