@@ -59,6 +59,8 @@ __device__ __forceinline__ F8 ldg256(const float4* p)
     return r;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 __device__ __forceinline__ void stg256(float4* p, float4 lo, float4 hi)
 {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -724,8 +726,8 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
 // Receiver move: walk each ray's cached receiver-independent segments in order and deposit at
 // the first one the receiver intercepts before the wall (t_recv < t_wall; ties go to the scene
 // because scene triangle ids are lower).
-// The cache is ray-major (a ray's records are consecutive 32 B sectors), a lane streams its ray two
-// records (one 64 B DRAM burst) at a time.  A segment is first tested against the receiver's
+// The cache is ray-major (a ray's records are consecutive 32 B sectors), a lane streams its ray four
+// records (one 128 B line) at a time and prefetches the next two lines into L2.  A segment is first tested against the receiver's
 // bounding ball (a few FMAs, exact-conservative).  Two things keep the warp full (r04 profile of
 // the version that walked the receiver tree as soon as 12 lanes held a candidate: 6.8 of 32
 // lanes per instruction, 446 M warp instructions):
@@ -734,10 +736,13 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
 //   * the receiver tree is walked only when 32 candidates are parked -- a full warp of walks; a
 //     candidate that misses the mesh goes to the warp's resume buffer and is scanned on from k+1.
 // A warp admits new rays only while it holds at most 32 parked ones, so 64 slots per buffer suffice.
+#ifndef ARV2_RR_MINB
+#define ARV2_RR_MINB 4
+#endif
 constexpr int kParkSlots = 64;
 
 template <int NB>
-__global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceParams p)
+__global__ void __launch_bounds__(kRerenderThreads, ARV2_RR_MINB) rerender_kernel(const TraceParams p)
 {
     __shared__ int2 sh_cand[kRerenderThreads / 32][kParkSlots];   // (ray, k | n << 16)
     __shared__ int2 sh_res[kRerenderThreads / 32][kParkSlots];
@@ -856,17 +861,23 @@ __global__ void __launch_bounds__(kRerenderThreads) rerender_kernel(const TraceP
         // ---- scan: advance to the next cached segment that enters the receiver's bounding ball
         bool found = false;
         if (have) {
-            const float4* rec = p.pc_seg + 2 * ((size_t)ray * (size_t)p.pc_stride + (size_t)k);
 #pragma unroll 1
-            for (int burst = 0; burst < 4; ++burst) {
+            for (int burst = 0; burst < 2 && have && !found; ++burst) {
+                const float4* rec = p.pc_seg + 2 * ((size_t)ray * (size_t)p.pc_stride + (size_t)k);
+                if (k + 4 < n) prefetch_l2(rec + 8);                 // the next lines of this ray: the scan is otherwise a
+                if (k + 8 < n) prefetch_l2(rec + 16);                // chain of dependent DRAM round trips
                 const F8 r0 = ldg256(rec);
-                F8 r1 = r0;
+                F8 r1 = r0, r2 = r0, r3 = r0;
                 if (k + 1 < n) r1 = ldg256(rec + 2);
-                if (enters_receiver_ball(p, f3(r0.lo.x, r0.lo.y, r0.lo.z), f3(r0.hi.x, r0.hi.y, r0.hi.z), r0.lo.w)) { found = true; break; }
-                if (++k >= n) { finish(ray, -1, 0, n); have = false; break; }
-                if (enters_receiver_ball(p, f3(r1.lo.x, r1.lo.y, r1.lo.z), f3(r1.hi.x, r1.hi.y, r1.hi.z), r1.lo.w)) { found = true; break; }
-                if (++k >= n) { finish(ray, -1, 0, n); have = false; break; }
-                rec += 4;
+                if (k + 2 < n) r2 = ldg256(rec + 4);
+                if (k + 3 < n) r3 = ldg256(rec + 6);
+#define ARV2_SCAN_STEP(r)                                                                                                          \
+                if (have && !found) {                                                                                              \
+                    if (enters_receiver_ball(p, f3(r.lo.x, r.lo.y, r.lo.z), f3(r.hi.x, r.hi.y, r.hi.z), r.lo.w)) found = true;     \
+                    else if (++k >= n) { finish(ray, -1, 0, n); have = false; }                                                    \
+                }
+                ARV2_SCAN_STEP(r0) ARV2_SCAN_STEP(r1) ARV2_SCAN_STEP(r2) ARV2_SCAN_STEP(r3)
+#undef ARV2_SCAN_STEP
             }
         }
         const unsigned fm = __ballot_sync(FULL, found);
