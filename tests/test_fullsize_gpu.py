@@ -1,0 +1,88 @@
+"""BASELINE.json's full sizes (C2: 331k-triangle room, 1M rays, 50 bounces, 2 s IR @48 kHz), checked through
+properties that do not need the CPU oracle at that size: the result must not depend on how the rays are
+scheduled (breadth-first tasks vs depth-first lanes, direction-sorted vs id order, one launch vs ranges), and a
+re-render from the path cache must equal a fresh trace.  Plus the long-path case of the per-depth queues."""
+import numpy as np
+import pytest
+
+from audiorenderingv2_b200 import scenes
+from util import Case, check_parity
+
+pytestmark = pytest.mark.gpu
+
+N_FULL = 1_000_000
+
+
+@pytest.fixture(scope="module")
+def c2(golden_receiver):
+    tv, tm, names = scenes.conference_room()
+    return Case(tv, tm, names, golden_receiver, rays=(N_FULL, 1, 1), emitter=(2.0, 1.5, 2.0), center=(9.0, 1.4, 5.5),
+                yaw=30.0, materials=scenes.materials(), base_power=100.0, max_bounces=50, sample_rate=48000, ir_seconds=2,
+                hrtf=0.9, seed=7)
+
+
+def _render(r):
+    r.render()
+    l, rr = r.get_ir()
+    return l, rr, r.last_segments(), r.records()
+
+
+def test_c2_fullsize_result_is_scheduling_invariant(c2, monkeypatch):
+    """wave_kernel (32-path tasks, per-depth queues, direction-sorted start order, 2048 paths alive per SM: the
+    cap binds at this size) against the depth-first kernel in ray-id order, and against three ray ranges."""
+    ra = c2.renderer(record_rays=True)
+    la, rra, sa, reca = _render(ra)
+    monkeypatch.setenv("ARV2_NO_WAVE", "1")
+    rb = c2.renderer(record_rays=True)
+    monkeypatch.delenv("ARV2_NO_WAVE")
+    rb.set_coherent_order(False)
+    lb, rrb, sb, recb = _render(rb)
+    assert sa == sb and sa > 20 * N_FULL
+    for key in ("bin", "ear", "nseg", "energy"):
+        assert np.array_equal(reca[key], recb[key]), key
+    assert np.allclose(la, lb, rtol=1e-6, atol=0) and np.allclose(rra, rrb, rtol=1e-6, atol=0)
+    # conservation: what the rays deposit is what the bins hold (primary ear + hrtf-attenuated other ear)
+    hit = reca["ear"] > 0
+    inside = hit & (reca["bin"] >= 0) & (reca["bin"] < la.shape[-1])
+    dep = reca["energy"].reshape(len(hit), -1)[:, 0].astype(np.float64)
+    tot = float(la.astype(np.float64).sum() + rra.astype(np.float64).sum())
+    assert abs(tot - dep[inside].sum() * (1.0 + (1.0 - c2.hrtf))) <= 1e-5 * tot
+    # ray ranges (the multi-GPU sharding) reproduce the single launch
+    cuts = [0, 333_333, 600_001, N_FULL]
+    segs = 0
+    for i in range(3):
+        ra.render_range(cuts[i], cuts[i + 1] - cuts[i], zero_first=(i == 0))
+        segs += ra.last_segments()
+    ra.finalize()
+    lc, rrc = ra.get_ir()
+    assert segs == sa
+    assert np.allclose(lc, la, rtol=1e-6, atol=0) and np.allclose(rrc, rra, rtol=1e-6, atol=0)
+
+
+def test_c2_fullsize_rerender_equals_trace(c2):
+    """IR re-render from the path cache after receiver moves = a fresh full trace at that position."""
+    full = c2.renderer()
+    cached = c2.renderer(path_cache=True)
+    cached.render()
+    for k in (1, 3):
+        pos, yaw = (9.0 - 0.7 * k, 1.4, 5.5 - 0.4 * k), 30.0 + 20.0 * k
+        full.setSphereCenterInOptix(pos, yaw); cached.setSphereCenterInOptix(pos, yaw)
+        full.render(); ms = cached.rerender()
+        la, ra = full.get_ir(); lb, rb = cached.get_ir()
+        assert full.last_segments() == cached.last_segments()
+        assert np.allclose(la, lb, rtol=1e-6, atol=0) and np.allclose(ra, rb, rtol=1e-6, atol=0)
+        assert ms < 5.0
+
+
+def test_long_paths_use_multi_segment_queues(golden_scenes, golden_receiver):
+    """300 bounces in the closed box: more depths than queues, so a task advances 5 segments; parity with the
+    oracle ray for ray."""
+    case = Case(golden_scenes["caja_verts"], golden_scenes["caja_mesh"], golden_scenes["caja_names"], golden_receiver,
+                rays=(32, 16, 8), emitter=(3, 1, -2), center=(-8, 4, 6), yaw=20.0, max_bounces=300, ir_seconds=60,
+                sample_rate=8000, materials=[("Material.001", 0.01)])
+    r = case.renderer(record_rays=True)
+    r.render()
+    l, rr = r.get_ir()
+    o = case.oracle_run()
+    assert check_parity(r.records(), l, rr, r.last_segments(), o) == 1.0
+    assert r.records()["nseg"].max() > 150
