@@ -115,16 +115,15 @@ struct Traversal {
         const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
         const bool go0 = c0min <= c0max, go1 = c1min <= c1max;
         const int i0 = __float_as_int(n3.x), i1 = __float_as_int(n3.y);
-        if (!go0 && !go1) {
-            cur = stack[--sp];
-        } else {
-            cur = go0 ? i0 : i1;
-            if (go0 && go1) {
-                int far = i1;
-                if (c1min < c0min) { cur = i1; far = i0; }
-                stack[sp++] = far;
-            }
-        }
+        // predicated push / pop instead of a divergent if-else: lanes that pop and lanes that descend share the
+        // same instructions
+        const bool both = go0 && go1;
+        const bool swap = both && c1min < c0min;
+        int next = (go0 && !swap) ? i0 : i1;
+        if (both) stack[sp] = swap ? i0 : i1;
+        sp += both ? 1 : 0;
+        if (!(go0 || go1)) next = stack[--sp];
+        cur = next;
     }
 
     // one leaf: exact tests of its <= 4 triangles
