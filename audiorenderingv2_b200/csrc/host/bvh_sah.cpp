@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <limits>
@@ -36,6 +37,28 @@ struct Prim { Box b; float c[3]; int32_t id; };
 
 struct TmpNode { Box box[2]; int32_t child[2]; };
 
+// Build parameters.  Defaults are the measured best for the tracer (profiles/r07_bvh_experiments.md);
+// the environment variables are tuning aids.
+//   leaf_max  largest leaf (<= 8: three count bits in the leaf code)            ARV2_LEAF_MAX
+//   ct        cost of one node visit in triangle tests for the SAH leaf test;   ARV2_SAH_CT
+//             0 = always split down to leaf_max
+//   bins      SAH bins per axis for large nodes                                  ARV2_SAH_BINS
+//   sweep     nodes of at most this many triangles use the exact sweep           ARV2_SAH_SWEEP
+constexpr int kMaxBins = 64;
+struct BuildKnobs { int leaf_max = kMaxLeafTris; float ct = 1.f; int bins = 16; int sweep = 0; };
+const BuildKnobs& knobs()
+{
+    static const BuildKnobs k = [] {
+        BuildKnobs b;
+        if (const char* e = getenv("ARV2_LEAF_MAX")) { const int x = atoi(e); if (x >= 1 && x <= 8) b.leaf_max = x; }
+        if (const char* e = getenv("ARV2_SAH_CT")) { const float x = (float)atof(e); if (x >= 0.f) b.ct = x; }
+        if (const char* e = getenv("ARV2_SAH_BINS")) { const int x = atoi(e); if (x >= 2 && x <= kMaxBins) b.bins = x; }
+        if (const char* e = getenv("ARV2_SAH_SWEEP")) { const int x = atoi(e); if (x >= 0) b.sweep = x; }
+        return b;
+    }();
+    return k;
+}
+
 struct Builder {
     std::vector<Prim> prims;
     std::vector<TmpNode> nodes;
@@ -45,53 +68,84 @@ struct Builder {
     static int32_t leaf_code(int64_t first, int count) { return ~(int32_t)((first << kLeafShift) | (count - 1)); }
 
     // Builds the subtree over prims[first, first+count); returns its child code.
+    // `bounds` = exact bounds of these prims (the SAH leaf test needs the parent's area).
     int32_t build(int64_t first, int64_t count, const Box& bounds, int depth, int par_depth)
     {
-        (void)bounds;
-        if (count <= kMaxLeafTris) return leaf_code(first, (int)count);
+        const BuildKnobs& K = knobs();
+        if (count <= 1) return leaf_code(first, (int)count);
+        if (count <= K.leaf_max && K.ct <= 0.f) return leaf_code(first, (int)count);
 
         Box cb; cb.reset();
         for (int64_t i = first; i < first + count; ++i) cb.grow(prims[i].c);
 
-        constexpr int NB = 16;
         float best_cost = INFINITY; int best_axis = -1, best_split = -1;
-        for (int a = 0; a < 3; ++a) {
-            const float ext = cb.hi[a] - cb.lo[a];
-            if (!(ext > 0.f)) continue;
-            Box bb[NB]; int cnt[NB];
-            for (int k = 0; k < NB; ++k) { bb[k].reset(); cnt[k] = 0; }
-            const float scale = NB / ext;
-            for (int64_t i = first; i < first + count; ++i) {
-                int k = (int)((prims[i].c[a] - cb.lo[a]) * scale);
-                k = std::min(NB - 1, std::max(0, k));
-                bb[k].grow(prims[i].b); cnt[k]++;
+        int64_t mid = -1;
+        if (count <= K.sweep) {
+            // small node: exact sweep over the centroid order of every axis
+            std::vector<Prim> tmp(prims.begin() + first, prims.begin() + first + count), best_order;
+            std::vector<float> right_area((size_t)count);
+            for (int a = 0; a < 3; ++a) {
+                if (!(cb.hi[a] - cb.lo[a] > 0.f)) continue;
+                std::stable_sort(tmp.begin(), tmp.end(), [a](const Prim& x, const Prim& y) { return x.c[a] < y.c[a]; });
+                Box acc; acc.reset();
+                for (int64_t i = count - 1; i > 0; --i) { acc.grow(tmp[i].b); right_area[i] = acc.half_area(); }
+                acc.reset();
+                bool better = false;
+                for (int64_t i = 0; i < count - 1; ++i) {
+                    acc.grow(tmp[i].b);
+                    const float cost = acc.half_area() * (float)(i + 1) + right_area[i + 1] * (float)(count - 1 - i);
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; mid = first + i + 1; better = true; }
+                }
+                if (better) best_order = tmp;
             }
-            float right_area[NB]; int right_cnt[NB];
-            Box acc; acc.reset(); int c = 0;
-            for (int k = NB - 1; k > 0; --k) { acc.grow(bb[k]); c += cnt[k]; right_area[k] = acc.half_area(); right_cnt[k] = c; }
-            acc.reset(); c = 0;
-            for (int k = 0; k < NB - 1; ++k) {
-                acc.grow(bb[k]); c += cnt[k];
-                if (c == 0 || right_cnt[k + 1] == 0) continue;
-                const float cost = acc.half_area() * (float)c + right_area[k + 1] * (float)right_cnt[k + 1];
-                if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = k; }
+            if (best_axis >= 0) {
+                if (count <= K.leaf_max && K.ct + best_cost / std::max(bounds.half_area(), 1e-30f) >= (float)count)
+                    return leaf_code(first, (int)count);
+                std::copy(best_order.begin(), best_order.end(), prims.begin() + first);
             }
-        }
-        int64_t mid;
-        if (best_axis >= 0) {
-            const int a = best_axis;
-            const float scale = NB / (cb.hi[a] - cb.lo[a]);
-            const float lo = cb.lo[a];
-            auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const Prim& p) {
-                int k = (int)((p.c[a] - lo) * scale);
-                k = std::min(NB - 1, std::max(0, k));
-                return k <= best_split;
-            });
-            mid = it - prims.begin();
         } else {
-            mid = first + count / 2;   // coincident centroids: split by position
+            const int NB = K.bins;
+            for (int a = 0; a < 3; ++a) {
+                const float ext = cb.hi[a] - cb.lo[a];
+                if (!(ext > 0.f)) continue;
+                Box bb[kMaxBins]; int cnt[kMaxBins];
+                for (int k = 0; k < NB; ++k) { bb[k].reset(); cnt[k] = 0; }
+                const float scale = NB / ext;
+                for (int64_t i = first; i < first + count; ++i) {
+                    int k = (int)((prims[i].c[a] - cb.lo[a]) * scale);
+                    k = std::min(NB - 1, std::max(0, k));
+                    bb[k].grow(prims[i].b); cnt[k]++;
+                }
+                float right_area[kMaxBins]; int right_cnt[kMaxBins];
+                Box acc; acc.reset(); int c = 0;
+                for (int k = NB - 1; k > 0; --k) { acc.grow(bb[k]); c += cnt[k]; right_area[k] = acc.half_area(); right_cnt[k] = c; }
+                acc.reset(); c = 0;
+                for (int k = 0; k < NB - 1; ++k) {
+                    acc.grow(bb[k]); c += cnt[k];
+                    if (c == 0 || right_cnt[k + 1] == 0) continue;
+                    const float cost = acc.half_area() * (float)c + right_area[k + 1] * (float)right_cnt[k + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = k; }
+                }
+            }
+            if (best_axis >= 0) {
+                if (count <= K.leaf_max && K.ct + best_cost / std::max(bounds.half_area(), 1e-30f) >= (float)count)
+                    return leaf_code(first, (int)count);
+                const int a = best_axis;
+                const float scale = NB / (cb.hi[a] - cb.lo[a]);
+                const float lo = cb.lo[a];
+                auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const Prim& p) {
+                    int k = (int)((p.c[a] - lo) * scale);
+                    k = std::min(NB - 1, std::max(0, k));
+                    return k <= best_split;
+                });
+                mid = it - prims.begin();
+            }
         }
-        if (mid == first || mid == first + count) mid = first + count / 2;
+        if (best_axis < 0) {
+            if (count <= K.leaf_max) return leaf_code(first, (int)count);   // coincident centroids
+            mid = first + count / 2;                                       // split by position
+        }
+        if (mid <= first || mid >= first + count) mid = first + count / 2;
 
         Box lb, rb; lb.reset(); rb.reset();
         for (int64_t i = first; i < mid; ++i) lb.grow(prims[i].b);
@@ -152,12 +206,14 @@ void build_bvh_sah(const float* tv, int64_t n, HostBvh* out, int n_threads)
     if (n == 0) {
         TmpNode r; r.box[0].reset(); r.box[1].reset(); r.child[0] = r.child[1] = Builder::leaf_code(0, 1);
         B.nodes[0] = r; B.next = 1; root_code = 0;
-    } else if (n <= kMaxLeafTris) {
-        TmpNode r; r.box[0] = all; r.box[1].reset();
-        r.child[0] = Builder::leaf_code(0, (int)n); r.child[1] = Builder::leaf_code(0, 1);
-        B.nodes[0] = r; B.next = 1; root_code = 0;
     } else {
-        root_code = B.build(0, n, all, 0, par_depth);
+        root_code = n <= kMaxLeafTris ? Builder::leaf_code(0, (int)n) : B.build(0, n, all, 0, par_depth);
+        if (root_code < 0) {        // everything fits one leaf: the root must still be an inner node
+            TmpNode r; r.box[0] = all; r.box[1].reset();
+            r.child[0] = root_code; r.child[1] = Builder::leaf_code(0, 1);
+            const int32_t me = B.next.fetch_add(1);
+            B.nodes[me] = r; root_code = me;
+        }
     }
 
     // Re-lay out in depth-first pre-order with the root at index 0.

@@ -126,7 +126,7 @@ struct Traversal {
         cur = next;
     }
 
-    // one leaf: exact tests of its <= 4 triangles
+    // one leaf: exact tests of its <= 8 triangles; the test needs the first 48 B of a record (P1, id, P2, material, P3)
     __device__ __forceinline__ void step_leaf(int* stack, const float4* __restrict__ tris, F3 org, F3 dir)
     {
         const int code = ~cur;
@@ -134,9 +134,10 @@ struct Traversal {
         const int cnt = (code & 7) + 1;
         for (int i = 0; i < cnt; ++i) {
             const int slot = first + i;
-            const F8 A = ldg256(tris + slot * 4), B = ldg256(tris + slot * 4 + 2);
+            const F8 A = ldg256(tris + slot * 4);
+            const float4 B = __ldg(tris + slot * 4 + 2);
             float t, u, v;
-            if (tri_test(f3(A.lo.x, A.lo.y, A.lo.z), f3(A.hi.x, A.hi.y, A.hi.z), f3(B.lo.x, B.lo.y, B.lo.z), org, dir, &t, &u, &v)) {
+            if (tri_test(f3(A.lo.x, A.lo.y, A.lo.z), f3(A.hi.x, A.hi.y, A.hi.z), f3(B.x, B.y, B.z), org, dir, &t, &u, &v)) {
                 const int id = __float_as_int(A.lo.w);
                 if (t < h.t || (t == h.t && id < h.id)) { h.t = t; h.u = u; h.v = v; h.slot = slot; h.id = id; }
             }
