@@ -260,9 +260,10 @@ int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
 int ensure_wave(arv2_ctx* c, TraceParams* p, long long n_rays)
 {
     if (!c->wave || n_rays <= 0 || n_rays > 0x7fffffffLL) return ARV2_OK;
-    // 4 segments per task, 2048 paths alive per SM (64 batches for 32 warps): measured best on B200 for 1M..16M rays
-    // (profiles/r05_wave_sweep.md; segments 1..8 x cap 1024..8192)
-    int per = 4;
+    // 8 segments per task, 2048 paths alive per SM (64 batches for 32 warps): measured best on B200 for 1M..8M rays
+    // (profiles/r05_trace_experiments.md section 2: segments 1..8 x cap 1024..8192; r07 section 5: 8 segments are
+    // +1.2 % over 4 at 8M rays on the SAH-leaf tree and halve the queue memory)
+    int per = 8;
     if (const char* e = getenv("ARV2_WAVE_SEGMENTS")) per = atoi(e) > 0 ? atoi(e) : per;      // tuning aid
     const unsigned mb = c->max_bounces < 1 ? 1u : c->max_bounces;
     while ((mb + per - 1) / per > (unsigned)kWaveQueues) ++per;

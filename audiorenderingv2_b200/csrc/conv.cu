@@ -14,6 +14,7 @@
 // each CTA accumulates 1/8 of the partitions, partial sums are reduce-scattered through
 // distributed shared memory, and the cluster's rank 0 runs the inverse FFT + overlap-add.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include <cooperative_groups.h>
@@ -156,6 +157,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): step k+1 may become resident while step k is still running; everything
+// that depends on step k comes after pdl_wait(), which returns once step k has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // acc += X[k] * H_e[k] for this thread's bins k = tid*BPT + i (contiguous, so that a
 // thread's BPT bins are one 8*BPT-byte shared-memory access); bin 0 holds (DC, Nyquist).
 template <int BPT>
@@ -276,25 +282,22 @@ __global__ void __launch_bounds__(kConvThreads) stream_step_kernel(const ConvStr
     float2 accL[BPT], accR[BPT];
 #pragma unroll
     for (int i = 0; i < BPT; ++i) { accL[i] = make_float2(0.f, 0.f); accR[i] = make_float2(0.f, 0.f); }
-    // Partition 0 is the block being transformed right now; rank 0 runs that forward FFT
-    // (~8 partitions' worth of time, measured with clock64) and therefore takes a shorter
-    // contiguous range of the older partitions 1..P-1; the rest is split evenly over ranks 1..C-1.
-    const int T = a.P - 1;
+    // Consecutive steps overlap (programmatic dependent launch): partitions 2..P-1 pair spectra that step k-1 and
+    // older steps wrote into the delay line with the (static) IR spectra, so they are accumulated BEFORE waiting
+    // for step k; partition 1 (written by step k), the forward FFT of the newest block (its slot is the one step k
+    // read as its oldest partition) and the tail update come after the wait.  A step lets its successor in only
+    // after its own wait, so "step k-1 is complete" holds whenever step k+1 runs.
+    // Rank 0 runs the forward FFT (~8 partitions' worth of time, measured with clock64) and therefore takes a
+    // shorter contiguous range of the old partitions; the rest is split evenly over ranks 1..C-1.
+    const int T = max(0, a.P - 2);
     int n0 = C > 1 ? (T - kFftCostInPartitions * ((int)C - 1)) / (int)C : T;
     n0 = max(0, min(T, n0));
     int first, n;
-    if (rank == 0) { first = 1; n = n0; }
+    if (rank == 0) { first = 2; n = n0; }
     else {
         const int rest = T - n0, per = rest / ((int)C - 1), extra = rest % ((int)C - 1), r1 = (int)rank - 1;
-        first = 1 + n0 + r1 * per + min(r1, extra);
+        first = 2 + n0 + r1 * per + min(r1, extra);
         n = per + (r1 < extra ? 1 : 0);
-    }
-    if (rank == 0) {
-        // newest block: forward FFT, publish into the frequency-domain delay line
-        const float* in = a.in + (size_t)src * block;
-        float2* slot = fdl + (size_t)a.slot * block;
-        forward_block(bufa, bufb, block, a.tw, [&](int t) { return in[t]; }, [&](int k, float2 v) { slot[k] = v; });
-        mac_rows<BPT>(slot, H, H + (size_t)a.P * block, block, accL, accR);
     }
     mac_pipeline<BPT>(ring, full, n, block,
                       [&](int i, const float2** X, const float2** HL, const float2** HR) {
@@ -303,6 +306,20 @@ __global__ void __launch_bounds__(kConvThreads) stream_step_kernel(const ConvStr
                           *X = fdl + (size_t)s * block; *HL = H + (size_t)p * block; *HR = H + ((size_t)a.P + p) * block;
                       },
                       accL, accR);
+    pdl_wait();
+    pdl_launch_dependents();
+    if (rank == 0) {
+        // newest block: forward FFT, publish into the frequency-domain delay line
+        const float* in = a.in + (size_t)src * block;
+        float2* slot = fdl + (size_t)a.slot * block;
+        forward_block(bufa, bufb, block, a.tw, [&](int t) { return in[t]; }, [&](int k, float2 v) { slot[k] = v; });
+        mac_rows<BPT>(slot, H, H + (size_t)a.P * block, block, accL, accR);
+    }
+    if (rank == C - 1 && a.P > 1) {
+        // the previous block: its spectrum was published by the step this one waited for
+        const int s1 = a.slot >= 1 ? a.slot - 1 : a.slot - 1 + a.P;
+        mac_rows<BPT>(fdl + (size_t)s1 * block, H + (size_t)block, H + ((size_t)a.P + 1) * block, block, accL, accR);
+    }
     float2* y = reduce_and_inverse<BPT>(cluster, part, yacc, bufa, bufb, block, a.tw, accL, accR);
     if (!y) return;
     const float sc = 1.0f / (float)N;
@@ -367,16 +384,18 @@ size_t fft_smem_bytes(int block) { return (size_t)4 * block * sizeof(float2); }
 size_t step_smem_bytes(int block) { return (size_t)(8 + 3 * kStages) * block * sizeof(float2); }
 
 template <class K>
-cudaError_t launch_cluster(K kernel, unsigned grid, size_t smem, cudaStream_t stream, void** args)
+cudaError_t launch_cluster(K kernel, unsigned grid, size_t smem, cudaStream_t stream, void** args, bool pdl = false)
 {
     cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kConvCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
     return cudaLaunchKernelExC(&cfg, (const void*)kernel, args);
 }
 
@@ -423,10 +442,11 @@ cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream)
     const unsigned grid = (unsigned)(a.n_src * kConvCluster);
     const size_t smem = step_smem_bytes(a.block);
     const int bpt = (a.block + kConvThreads - 1) / kConvThreads;
+    static const bool pdl = getenv("ARV2_CONV_NO_PDL") == nullptr;     // A/B switch
     switch (bpt) {
-    case 1: return launch_cluster(stream_step_kernel<1>, grid, smem, stream, kargs);
-    case 2: return launch_cluster(stream_step_kernel<2>, grid, smem, stream, kargs);
-    case 4: return launch_cluster(stream_step_kernel<4>, grid, smem, stream, kargs);
+    case 1: return launch_cluster(stream_step_kernel<1>, grid, smem, stream, kargs, pdl);
+    case 2: return launch_cluster(stream_step_kernel<2>, grid, smem, stream, kargs, pdl);
+    case 4: return launch_cluster(stream_step_kernel<4>, grid, smem, stream, kargs, pdl);
     default: return cudaErrorInvalidValue;
     }
 }

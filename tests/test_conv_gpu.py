@@ -109,6 +109,42 @@ def test_stream_matches_direct(block, n_src, ir_len):
     assert rel_l2(ol, oracle.direct_conv(x[0], irs[0][0])[: nb * block]) <= 1e-4
 
 
+def test_stream_back_to_back_steps_overlap_safely():
+    """Device-resident steps launched back to back overlap (programmatic dependent launch: step k+1 accumulates its
+    old partitions while step k finishes).  The result must equal, bit for bit, the same steps run one at a time
+    through the host-buffer call (a copy between steps serialises them), and match the fp64 direct convolution."""
+    import torch
+    n_src, block, ir_len, nb = 4, 512, 20000, 120
+    rng = np.random.default_rng(5)
+    irs = [(decaying_ir(ir_len, 130 + i, 0.2, 48000), decaying_ir(ir_len, 160 + i, 0.15, 48000)) for i in range(n_src)]
+    x = (0.1 * rng.standard_normal((nb, n_src, block))).astype(np.float32)
+    outs = []
+    for mode in ("device", "host"):
+        st = arv.ConvStream(n_src, block, ir_len)
+        for i, (a, b) in enumerate(irs):
+            st.set_ir(i, a, b)
+        if mode == "device":
+            dev = torch.device("cuda", 0)
+            dx = torch.from_numpy(x).to(dev)
+            dy = torch.empty(nb, n_src, 2, block, device=dev)
+            s = torch.cuda.Stream(device=dev)
+            torch.cuda.synchronize()
+            with torch.cuda.stream(s):
+                for k in range(nb):
+                    st.process_device(dx[k].data_ptr(), dy[k].data_ptr(), s.cuda_stream)
+            torch.cuda.synchronize()
+            outs.append(dy.cpu().numpy())
+        else:
+            outs.append(np.stack([st.process(x[k]) for k in range(nb)]))
+        st.close()
+    assert np.array_equal(outs[0], outs[1])
+    y = np.concatenate(list(outs[0]), axis=2)          # [n_src][2][nb*block]
+    xs = np.concatenate(list(x), axis=1)
+    for i, (a, b) in enumerate(irs):
+        assert rel_l2(y[i, 0], oracle.direct_conv(xs[i], a)[: nb * block]) <= TOL
+        assert rel_l2(y[i, 1], oracle.direct_conv(xs[i], b)[: nb * block]) <= TOL
+
+
 def test_stream_ir_swap_and_reset():
     block, ir_len = 256, 2000
     st = arv.ConvStream(1, block, ir_len)
