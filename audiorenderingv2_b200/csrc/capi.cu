@@ -857,8 +857,8 @@ int arv2_convolve_file(arv2_ctx* c, const float* x, size_t n, float* y_left, flo
     CK(cudaMemsetAsync(w.d_out, 0, 2 * n * sizeof(float), c->stream));                        // :682-683
     CK(cudaEventRecord(c->ev0, c->stream));
     // IR spectra of both ears (band 0): items = {ir_left, ir_right}
-    CK(conv_ir_spectra(c->d_ir_l, 1, ir_len, block, P, w.d_tw, w.d_H, c->stream));
-    CK(conv_ir_spectra(c->d_ir_r, 1, ir_len, block, P, w.d_tw, w.d_H + (size_t)P * block, c->stream));
+    CK(conv_ir_spectra(c->d_ir_l, 1, 0, ir_len, block, P, w.d_tw, w.d_H, c->stream));
+    CK(conv_ir_spectra(c->d_ir_r, 1, 1, ir_len, block, P, w.d_tw, w.d_H, c->stream));
     if (n_seg > 0) {
         CK(conv_block_spectra(w.d_x, (long long)n, seg_len, n_seg, bps, block, w.d_tw, w.d_X, c->stream));
         ConvFileArgs a{};
@@ -932,7 +932,7 @@ static int stream_swap_ir(arv2_stream* s, int32_t source)
     const size_t spec = (size_t)s->P * s->block;
     const int nb = 1 - s->active[source];
     float2* H = s->d_H[nb] + (size_t)source * 2 * spec;
-    CK(conv_ir_spectra(s->d_ir, 2, s->ir_len, s->block, s->P, s->d_tw, H, s->stream));
+    CK(conv_ir_spectra(s->d_ir, 2, 0, s->ir_len, s->block, s->P, s->d_tw, H, s->stream));
     s->active[source] = nb;
     s->h_Hptr[source] = H;
     CK(cudaMemcpyAsync(s->d_Hptr + source, s->h_Hptr + source, sizeof(float2*), cudaMemcpyHostToDevice, s->stream));

@@ -14,6 +14,7 @@
 // each CTA accumulates 1/8 of the partitions, partial sums are reduce-scattered through
 // distributed shared memory, and the cluster's rank 0 runs the inverse FFT + overlap-add.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -42,7 +43,7 @@ __device__ float2* fft_smem(float2* x, float2* y, int N, const float2* __restric
         const int n1 = n >> 2;
         for (int b = threadIdx.x; b < (N >> 2); b += blockDim.x) {
             const int p = b >> ls, q = b & (s - 1);
-            float2 w1 = __ldg(tw + p * s), w2 = __ldg(tw + 2 * p * s), w3 = __ldg(tw + 3 * p * s);
+            float2 w1 = tw[p * s], w2 = tw[2 * p * s], w3 = tw[3 * p * s];
             if (inverse) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
             const float2 a = x[q + s * p], bb = x[q + s * (p + n1)], c = x[q + s * (p + 2 * n1)], d = x[q + s * (p + 3 * n1)];
             const float2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(bb, d);
@@ -83,14 +84,14 @@ __device__ void forward_block(float2* bufa, float2* bufb, int block, const float
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kConvThreads) ir_spectra_kernel(const float* __restrict__ h, int ir_len, int block, int P,
+__global__ void __launch_bounds__(kConvThreads) ir_spectra_kernel(const float* __restrict__ h, int ir_len, int block, int P, int ear0,
                                                                   const float2* __restrict__ tw, float2* __restrict__ H)
 {
     extern __shared__ float2 smem[];
     float2* bufa = smem; float2* bufb = smem + 2 * block;
     const int item = blockIdx.x / P, p = blockIdx.x % P;
     const float* src = h + (size_t)item * ir_len;
-    float2* dst = H + ((size_t)item * P + p) * block;
+    float2* dst = H + ((size_t)p * 2 + ear0 + item) * block;      // [P][2 ears][block]: one bulk copy per partition
     forward_block(bufa, bufb, block, tw,
                   [&](int t) { const long long i = (long long)p * block + t; return i < ir_len ? src[i] : 0.f; },
                   [&](int k, float2 v) { dst[k] = v; });
@@ -119,15 +120,23 @@ __global__ void __launch_bounds__(kConvThreads) block_spectra_kernel(const float
 // of a partition (X, H_left, H_right: block*8 B each) are instead pulled into a 4-stage
 // shared-memory ring by bulk async copies that complete on an mbarrier; the threads only
 // read shared memory.
-// 4 stages x 12 KB in flight per SM already stream the spectra at the L2 rate (128 SMs x ~60 GB/s); 8 and 12
-// stages measured 26 us per step instead of 16.4 (profiles/micro/conv_ab.py)
+// The ring takes what two co-resident CTAs per SM leave (2 x 104 KB): with one CTA per SM the 8-CTA clusters of a
+// 16-source step no longer fit the GPCs in one wave (26 us per step instead of 16, r05), and a step could not share
+// the SMs with its predecessor.  block = 512: 8 stages x 12 KB in flight per CTA.
 #ifndef ARV2_CONV_STAGES
-#define ARV2_CONV_STAGES 4
+#define ARV2_CONV_STAGES 8
 #endif
 #ifndef ARV2_CONV_FFTCOST
 #define ARV2_CONV_FFTCOST 8
 #endif
-constexpr int kStages = ARV2_CONV_STAGES;
+constexpr int kStages = ARV2_CONV_STAGES;                  // most stages (mbarrier pairs) of the ring
+__host__ __device__ constexpr int ring_stages(int block)
+{
+    const int budget = 104 * 1024 - 2 * block * (int)sizeof(float2);       // minus the twiddle table
+    const int fit = budget / (3 * block * (int)sizeof(float2));
+    return fit < 2 ? 2 : (fit > kStages ? kStages : fit);
+}
+constexpr int kConvStepThreads = kConvThreads + 32;     // stream / file kernels: kConvThreads consumers + one producer warp
 constexpr int kFftCostInPartitions = ARV2_CONV_FFTCOST;   // forward FFT of one block ~ streaming 8 partitions (clock64-measured)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -151,6 +160,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -164,120 +177,162 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 // acc += X[k] * H_e[k] for this thread's bins k = tid*BPT + i (contiguous, so that a
 // thread's BPT bins are one 8*BPT-byte shared-memory access); bin 0 holds (DC, Nyquist).
+__device__ __forceinline__ void mac_bin(int k, float2 xv, float2 hl, float2 hr, float2& accL, float2& accR)
+{
+    if (k == 0) {   // packed (DC, Nyquist): two real products
+        accL.x = fmaf(xv.x, hl.x, accL.x); accL.y = fmaf(xv.y, hl.y, accL.y);
+        accR.x = fmaf(xv.x, hr.x, accR.x); accR.y = fmaf(xv.y, hr.y, accR.y);
+    } else {
+        accL.x = fmaf(xv.x, hl.x, fmaf(-xv.y, hl.y, accL.x)); accL.y = fmaf(xv.x, hl.y, fmaf(xv.y, hl.x, accL.y));
+        accR.x = fmaf(xv.x, hr.x, fmaf(-xv.y, hr.y, accR.x)); accR.y = fmaf(xv.x, hr.y, fmaf(xv.y, hr.x, accR.y));
+    }
+}
+
 template <int BPT>
 __device__ __forceinline__ void mac_rows(const float2* X, const float2* HL, const float2* HR, int block, float2 accL[BPT], float2 accR[BPT])
 {
 #pragma unroll
     for (int i = 0; i < BPT; ++i) {
         const int k = threadIdx.x * BPT + i;
-        if (k < block) {
-            const float2 xv = X[k], hl = HL[k], hr = HR[k];
-            if (k == 0) {   // packed (DC, Nyquist): two real products
-                accL[i].x = fmaf(xv.x, hl.x, accL[i].x); accL[i].y = fmaf(xv.y, hl.y, accL[i].y);
-                accR[i].x = fmaf(xv.x, hr.x, accR[i].x); accR[i].y = fmaf(xv.y, hr.y, accR[i].y);
-            } else {
-                accL[i].x = fmaf(xv.x, hl.x, fmaf(-xv.y, hl.y, accL[i].x)); accL[i].y = fmaf(xv.x, hl.y, fmaf(xv.y, hl.x, accL[i].y));
-                accR[i].x = fmaf(xv.x, hr.x, fmaf(-xv.y, hr.y, accR[i].x)); accR[i].y = fmaf(xv.x, hr.y, fmaf(xv.y, hr.x, accR[i].y));
-            }
-        }
+        if (k < block) mac_bin(k, X[k], HL[k], HR[k], accL[i], accR[i]);
     }
 }
 
-// Multiply-accumulate `n` partitions through the TMA ring.  rows(i, &X, &HL, &HR) yields the
-// global rows of this CTA's i-th partition.  ring: float2[kStages][3][block]; all threads call.
-template <int BPT, class Rows>
-__device__ __forceinline__ void mac_pipeline(float2* ring, unsigned long long* full, int n, int block, Rows rows,
-                                             float2 accL[BPT], float2 accR[BPT])
+// Rows of the partitions one CTA accumulates: partition i pairs the input spectrum at x (block float2) with the
+// two IR spectra at h (2*block float2, left then right); x and h advance by fixed steps, x wraps inside the
+// delay line.
+struct MacRows {
+    const float2* x; long long x_step; const float2* x_lo; long long x_wrap;     // after a partition: x += x_step; if (x < x_lo) x += x_wrap
+    const float2* h; long long h_step;
+};
+
+// Multiply-accumulate `n` partitions through the TMA ring; ring: float2[stages][3][block]; all threads call.
+// Warp-specialised: the CTA's last warp is the producer (one lane waits for a stage to be released and issues its
+// two bulk copies: 4 KB of input spectrum, 8 KB of IR spectra at block = 512), the first kConvThreads threads consume
+// (wait for the stage's bytes, accumulate, release the stage with one arrive per warp).  No CTA-wide barrier inside
+// the loop.  The producer's instruction count is what bounds the loop (r07: thread 0 issuing three copies between two
+// __syncthreads: 350 ns per partition whatever the ring depth; a producer lane recomputing the three row addresses
+// per partition: 85 instructions, 280 ns), hence the stepped pointers and the interleaved IR rows.
+template <int BPT>
+__device__ __forceinline__ void mac_pipeline(float2* ring, unsigned long long* full, unsigned long long* empty, int n, int block,
+                                             MacRows r, float2 accL[BPT], float2 accR[BPT])
 {
     const unsigned row_bytes = (unsigned)block * sizeof(float2);
-    auto issue = [&](int i, int s) {
-        const float2 *X, *HL, *HR;
-        rows(i, &X, &HL, &HR);
-        float2* dst = ring + (size_t)s * 3 * block;
-        mbar_expect_tx(&full[s], 3 * row_bytes);
-        bulk_g2s(dst, X, row_bytes, &full[s]);
-        bulk_g2s(dst + block, HL, row_bytes, &full[s]);
-        bulk_g2s(dst + 2 * block, HR, row_bytes, &full[s]);
-    };
-    if (threadIdx.x == 0)
-        for (int s = 0; s < kStages && s < n; ++s) issue(s, s);
+    const int S = ring_stages(block);
+    if (threadIdx.x >= kConvThreads) {
+        if (threadIdx.x == kConvThreads) {
+            int s = 0;
+            unsigned parity = 1;                          // parity of the phase that precedes the first release
+            float2* dst = ring;
+            for (int i = 0; i < n; ++i) {
+                if (i >= S) mbar_wait(&empty[s], parity);
+                mbar_expect_tx(&full[s], 3 * row_bytes);
+                bulk_g2s(dst, r.x, row_bytes, &full[s]);
+                bulk_g2s(dst + block, r.h, 2 * row_bytes, &full[s]);
+                r.x += r.x_step; if (r.x < r.x_lo) r.x += r.x_wrap;
+                r.h += r.h_step;
+                dst += 3 * block;
+                if (++s == S) { s = 0; dst = ring; parity ^= 1u; }
+            }
+        }
+        return;
+    }
+    int s = 0;
+    unsigned parity = 0;
+    const float2* src = ring;
     for (int i = 0; i < n; ++i) {
-        const int s = i % kStages;
-        mbar_wait(&full[s], (unsigned)((i / kStages) & 1));
-        const float2* src = ring + (size_t)s * 3 * block;
+        mbar_wait(&full[s], parity);
         mac_rows<BPT>(src, src + block, src + 2 * block, block, accL, accR);
-        __syncthreads();                                   // everyone is done with stage s
-        if (threadIdx.x == 0 && i + kStages < n) issue(i + kStages, s);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
+        src += 3 * block;
+        if (++s == S) { s = 0; src = ring; parity ^= 1u; }
     }
 }
 
-// Cluster-wide reduce-scatter of the per-CTA partial sums into rank 0's `yacc`, then
-// rank 0 unpacks Z = YL + i*YR, inverse-transforms and returns the time-domain buffer
-// (re = left, im = right, unnormalised); other ranks return nullptr.
+// Cluster-wide reduction of the per-CTA partial sums, then the inverse transform on rank 0.  Rank r owns the bins
+// [r*block/C, (r+1)*block/C) of both ears: it sums the C partial sums through distributed shared memory (all C
+// remote loads in flight at once) and writes Z = YL + i*YR, already unpacked to the full Hermitian layout, straight
+// into rank 0's FFT buffer.  Rank 0 returns the time-domain buffer (re = left, im = right, unnormalised); other
+// ranks return nullptr.
 template <int BPT>
-__device__ float2* reduce_and_inverse(cg::cluster_group& cluster, float2* part, float2* yacc, float2* bufa, float2* bufb,
+__device__ float2* reduce_and_inverse(cg::cluster_group& cluster, float2* part, float2* bufa, float2* bufb,
                                       int block, const float2* tw, const float2 accL[BPT], const float2 accR[BPT])
 {
     const unsigned rank = cluster.block_rank();
-    const unsigned C = cluster.num_blocks();
+    constexpr int C = kConvCluster;
+    if (threadIdx.x < kConvThreads) {
 #pragma unroll
-    for (int i = 0; i < BPT; ++i) {
-        const int k = threadIdx.x * BPT + i;
-        if (k < block) { part[k] = accL[i]; part[block + k] = accR[i]; }
+        for (int i = 0; i < BPT; ++i) {
+            const int k = threadIdx.x * BPT + i;
+            if (k < block) { part[k] = accL[i]; part[block + k] = accR[i]; }
+        }
     }
     cluster.sync();
     {
-        // rank r owns elements [r*chunk, (r+1)*chunk) of the 2*block partial sums
-        const int total = 2 * block;
-        const int chunk = (total + (int)C - 1) / (int)C;
-        float2* dst = cluster.map_shared_rank(yacc, 0);
-        for (int e = threadIdx.x; e < chunk; e += blockDim.x) {
-            const int idx = (int)rank * chunk + e;
-            if (idx < total) {
-                float2 s = make_float2(0.f, 0.f);
-                for (unsigned r = 0; r < C; ++r) {
-                    const float2 v = cluster.map_shared_rank(part, r)[idx];
-                    s.x += v.x; s.y += v.y;
-                }
-                dst[idx] = s;
+        const int N = 2 * block;
+        const int per = block / C;                       // block is a power of two >= 64, C = 8
+        const float2* remote[C];
+#pragma unroll
+        for (int r = 0; r < C; ++r) remote[r] = cluster.map_shared_rank(part, r);
+        float2* z = cluster.map_shared_rank(bufa, 0);
+        for (int e = threadIdx.x; e < per; e += blockDim.x) {
+            const int k = (int)rank * per + e;
+            float2 vl[C], vr[C];
+#pragma unroll
+            for (int r = 0; r < C; ++r) { vl[r] = remote[r][k]; vr[r] = remote[r][block + k]; }
+            float2 l = vl[0], rr = vr[0];
+#pragma unroll
+            for (int r = 1; r < C; ++r) { l.x += vl[r].x; l.y += vl[r].y; rr.x += vr[r].x; rr.y += vr[r].y; }
+            if (k == 0) {
+                z[0] = make_float2(l.x, rr.x);
+                z[block] = make_float2(l.y, rr.y);
+            } else {
+                z[k] = make_float2(l.x - rr.y, l.y + rr.x);
+                z[N - k] = make_float2(l.x + rr.y, rr.x - l.y);
             }
         }
     }
     cluster.sync();
     if (rank != 0) return nullptr;
-    const int N = 2 * block;
-    for (int k = threadIdx.x; k < block; k += blockDim.x) {
-        const float2 l = yacc[k], r = yacc[block + k];
-        if (k == 0) {
-            bufa[0] = make_float2(l.x, r.x);
-            bufa[block] = make_float2(l.y, r.y);
-        } else {
-            bufa[k] = make_float2(l.x - r.y, l.y + r.x);
-            bufa[N - k] = make_float2(l.x + r.y, r.x - l.y);
-        }
-    }
-    __syncthreads();
-    return fft_smem(bufa, bufb, N, tw, true);
+    return fft_smem(bufa, bufb, 2 * block, tw, true);
 }
 
+#ifdef ARV2_CONV_TIMING
+#define CT_DECL unsigned long long ct_[10]; long long cc_[10]; int ct_n = 0;
+#define CT_STAMP() do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); cc_[ct_n] = clock64(); ct_[ct_n++] = t_; } while (0)
+#else
+#define CT_DECL
+#define CT_STAMP() do {} while (0)
+#endif
+
 template <int BPT>
-__global__ void __launch_bounds__(kConvThreads) stream_step_kernel(const ConvStreamArgs a)
+__global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const ConvStreamArgs a)
 {
+    CT_DECL
+    CT_STAMP();
     extern __shared__ __align__(128) float2 smem[];
-    __shared__ unsigned long long full[kStages];
+    __shared__ unsigned long long full[kStages], empty[kStages];
     const int block = a.block, N = 2 * block;
-    float2* bufa = smem; float2* bufb = bufa + N; float2* part = bufb + N; float2* yacc = part + N; float2* ring = yacc + N;
+    // twiddles, then the TMA ring; the FFT buffers and the partial sums are only needed once the ring has drained
+    // and live on top of it (a deeper ring instead of 24 KB of idle buffers)
+    float2* stw = smem; float2* ring = stw + N;
+    float2* bufa = ring; float2* bufb = bufa + N; float2* part = bufb + N;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
-    const unsigned C = cluster.num_blocks();
+    constexpr unsigned C = kConvCluster;
     const int src = blockIdx.x / C;
     float2* fdl = a.fdl + (size_t)src * a.P * block;
     const float2* H = a.H[src];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConvThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // twiddles (5 passes x 3 gathers per FFT) into shared memory, by the consumer threads while the producer already
+    // fills the ring; first used after the __syncthreads that follows the ring
+    if (threadIdx.x < kConvThreads)
+        for (int t = threadIdx.x; t < N; t += kConvThreads) stw[t] = a.tw[t];
 
     float2 accL[BPT], accR[BPT];
 #pragma unroll
@@ -290,7 +345,7 @@ __global__ void __launch_bounds__(kConvThreads) stream_step_kernel(const ConvStr
     // Rank 0 runs the forward FFT (~8 partitions' worth of time, measured with clock64) and therefore takes a
     // shorter contiguous range of the old partitions; the rest is split evenly over ranks 1..C-1.
     const int T = max(0, a.P - 2);
-    int n0 = C > 1 ? (T - kFftCostInPartitions * ((int)C - 1)) / (int)C : T;
+    int n0 = (T - kFftCostInPartitions * ((int)C - 1)) / (int)C;
     n0 = max(0, min(T, n0));
     int first, n;
     if (rank == 0) { first = 2; n = n0; }
@@ -299,48 +354,100 @@ __global__ void __launch_bounds__(kConvThreads) stream_step_kernel(const ConvStr
         first = 2 + n0 + r1 * per + min(r1, extra);
         n = per + (r1 < extra ? 1 : 0);
     }
-    mac_pipeline<BPT>(ring, full, n, block,
-                      [&](int i, const float2** X, const float2** HL, const float2** HR) {
-                          const int p = first + i;
-                          int s = a.slot - p; if (s < 0) s += a.P;
-                          *X = fdl + (size_t)s * block; *HL = H + (size_t)p * block; *HR = H + ((size_t)a.P + p) * block;
-                      },
-                      accL, accR);
+    // IR rows of the partition this rank multiplies after the wait (rank 0: partition 0, rank C-1: partition 1):
+    // static data, fetched now so that their latency hides under the ring
+    const int pq = rank == 0 ? 0 : 1;
+    const bool late = (rank == 0 || (rank == C - 1 && a.P > 1)) && threadIdx.x < kConvThreads;
+    float2 hqL[BPT], hqR[BPT];
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+        const int k = threadIdx.x * BPT + i;
+        const bool on = late && k < block;
+        hqL[i] = on ? H[(size_t)pq * 2 * block + k] : make_float2(0.f, 0.f);
+        hqR[i] = on ? H[((size_t)pq * 2 + 1) * block + k] : make_float2(0.f, 0.f);
+    }
+    {
+        int s0 = a.slot - first; if (s0 < 0) s0 += a.P;
+        MacRows r;
+        r.x = fdl + (size_t)s0 * block; r.x_step = -(long long)block; r.x_lo = fdl; r.x_wrap = (long long)a.P * block;
+        r.h = H + (size_t)first * 2 * block; r.h_step = 2 * (long long)block;
+        mac_pipeline<BPT>(ring, full, empty, n, block, r, accL, accR);
+    }
+    CT_STAMP();
     pdl_wait();
     pdl_launch_dependents();
+    CT_STAMP();
+    __syncthreads();                                      // the ring has drained: its memory becomes bufa / bufb / part
+    float tl[BPT], tr[BPT];                               // overlap-add tails of this thread's output samples (rank 0)
+    float* tail = a.tail + (size_t)src * 2 * block;
     if (rank == 0) {
-        // newest block: forward FFT, publish into the frequency-domain delay line
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const int t = threadIdx.x * BPT + i;
+            const bool on = threadIdx.x < kConvThreads && t < block;
+            tl[i] = on ? tail[t] : 0.f; tr[i] = on ? tail[block + t] : 0.f;
+        }
+        // newest block: forward FFT, publish into the frequency-domain delay line, multiply by partition 0
         const float* in = a.in + (size_t)src * block;
         float2* slot = fdl + (size_t)a.slot * block;
-        forward_block(bufa, bufb, block, a.tw, [&](int t) { return in[t]; }, [&](int k, float2 v) { slot[k] = v; });
-        mac_rows<BPT>(slot, H, H + (size_t)a.P * block, block, accL, accR);
+        for (int t = threadIdx.x; t < N; t += blockDim.x) bufa[t] = make_float2(t < block ? in[t] : 0.f, 0.f);
+        __syncthreads();
+        const float2* F = fft_smem(bufa, bufb, N, stw, false);
+        if (threadIdx.x < kConvThreads) {
+#pragma unroll
+            for (int i = 0; i < BPT; ++i) {
+                const int k = threadIdx.x * BPT + i;
+                if (k < block) {
+                    const float2 xv = k == 0 ? make_float2(F[0].x, F[block].x) : F[k];
+                    slot[k] = xv;
+                    mac_bin(k, xv, hqL[i], hqR[i], accL[i], accR[i]);
+                }
+            }
+        }
+        __syncthreads();                                  // F (bufa or bufb) is read above; part and bufa are written next
     }
-    if (rank == C - 1 && a.P > 1) {
+    if (rank == C - 1 && a.P > 1 && threadIdx.x < kConvThreads) {
         // the previous block: its spectrum was published by the step this one waited for
         const int s1 = a.slot >= 1 ? a.slot - 1 : a.slot - 1 + a.P;
-        mac_rows<BPT>(fdl + (size_t)s1 * block, H + (size_t)block, H + ((size_t)a.P + 1) * block, block, accL, accR);
+        const float2* X1 = fdl + (size_t)s1 * block;
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const int k = threadIdx.x * BPT + i;
+            if (k < block) mac_bin(k, X1[k], hqL[i], hqR[i], accL[i], accR[i]);
+        }
     }
-    float2* y = reduce_and_inverse<BPT>(cluster, part, yacc, bufa, bufb, block, a.tw, accL, accR);
-    if (!y) return;
+    CT_STAMP();
+    float2* y = reduce_and_inverse<BPT>(cluster, part, bufa, bufb, block, stw, accL, accR);
+    CT_STAMP();
+#ifdef ARV2_CONV_TIMING
+    if ((blockIdx.x == 0 || blockIdx.x == 7) && threadIdx.x == 0 && a.slot == 100)
+        printf("cta %d: mac %llu wait %llu fft+p01 %llu reduce+ifft %llu ns (start %llu); mac %lld cycles, whole %lld cycles / %llu ns\n", blockIdx.x,
+               ct_[1] - ct_[0], ct_[2] - ct_[1], ct_[3] - ct_[2], ct_[4] - ct_[3], ct_[0] % 1000000ull, cc_[1] - cc_[0], cc_[4] - cc_[0], ct_[4] - ct_[0]);
+#endif
+    if (!y || threadIdx.x >= kConvThreads) return;
     const float sc = 1.0f / (float)N;
     float* out = a.out + (size_t)src * 2 * block;
-    float* tail = a.tail + (size_t)src * 2 * block;
-    for (int t = threadIdx.x; t < block; t += blockDim.x) {
-        const float2 lo = y[t], hi = y[block + t];
-        out[t] = fmaf(lo.x, sc, tail[t]);
-        out[block + t] = fmaf(lo.y, sc, tail[block + t]);
-        tail[t] = hi.x * sc;
-        tail[block + t] = hi.y * sc;
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+        const int t = threadIdx.x * BPT + i;
+        if (t < block) {
+            const float2 lo = y[t], hi = y[block + t];
+            out[t] = fmaf(lo.x, sc, tl[i]);
+            out[block + t] = fmaf(lo.y, sc, tr[i]);
+            tail[t] = hi.x * sc;
+            tail[block + t] = hi.y * sc;
+        }
     }
 }
 
 template <int BPT>
-__global__ void __launch_bounds__(kConvThreads) file_kernel(const ConvFileArgs a, int out_blocks_per_seg)
+__global__ void __launch_bounds__(kConvStepThreads) file_kernel(const ConvFileArgs a, int out_blocks_per_seg)
 {
     extern __shared__ __align__(128) float2 smem[];
-    __shared__ unsigned long long full[kStages];
+    __shared__ unsigned long long full[kStages], empty[kStages];
     const int block = a.block, N = 2 * block;
-    float2* bufa = smem; float2* bufb = bufa + N; float2* part = bufb + N; float2* yacc = part + N; float2* ring = yacc + N;
+    float2* stw = smem; float2* ring = stw + N;                    // same layout as stream_step_kernel
+    float2* bufa = ring; float2* bufb = bufa + N; float2* part = bufb + N;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     const unsigned C = cluster.num_blocks();
@@ -348,10 +455,14 @@ __global__ void __launch_bounds__(kConvThreads) file_kernel(const ConvFileArgs a
     const int seg = cid / out_blocks_per_seg, j = cid % out_blocks_per_seg;
     const float2* X = a.X + (size_t)seg * a.blocks_per_seg * block;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConvThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // twiddles (5 passes x 3 gathers per FFT) into shared memory, by the consumer threads while the producer already
+    // fills the ring; first used after the __syncthreads that follows the ring
+    if (threadIdx.x < kConvThreads)
+        for (int t = threadIdx.x; t < N; t += kConvThreads) stw[t] = a.tw[t];
 
     float2 accL[BPT], accR[BPT];
 #pragma unroll
@@ -359,13 +470,14 @@ __global__ void __launch_bounds__(kConvThreads) file_kernel(const ConvFileArgs a
     const int p_lo = max(0, j - (a.blocks_per_seg - 1)), p_hi = min(a.P - 1, j);
     const int first = p_lo + (int)rank;
     const int n = first <= p_hi ? (p_hi - first) / (int)C + 1 : 0;
-    mac_pipeline<BPT>(ring, full, n, block,
-                      [&](int i, const float2** Xr, const float2** HL, const float2** HR) {
-                          const int p = first + i * (int)C;
-                          *Xr = X + (size_t)(j - p) * block; *HL = a.H + (size_t)p * block; *HR = a.H + ((size_t)a.P + p) * block;
-                      },
-                      accL, accR);
-    float2* y = reduce_and_inverse<BPT>(cluster, part, yacc, bufa, bufb, block, a.tw, accL, accR);
+    {
+        MacRows r;
+        r.x = X + (size_t)(j - first) * block; r.x_step = -(long long)C * block; r.x_lo = nullptr; r.x_wrap = 0;
+        r.h = a.H + (size_t)first * 2 * block; r.h_step = 2 * (long long)C * block;
+        mac_pipeline<BPT>(ring, full, empty, n, block, r, accL, accR);
+    }
+    __syncthreads();                                      // the ring has drained: its memory becomes bufa / bufb / part
+    float2* y = reduce_and_inverse<BPT>(cluster, part, bufa, bufb, block, stw, accL, accR);
     if (!y) return;
     const float sc = a.gain / (float)N;
     const long long seg_base = (long long)seg * a.seg_len;
@@ -381,7 +493,7 @@ __global__ void __launch_bounds__(kConvThreads) file_kernel(const ConvFileArgs a
 }
 
 size_t fft_smem_bytes(int block) { return (size_t)4 * block * sizeof(float2); }
-size_t step_smem_bytes(int block) { return (size_t)(8 + 3 * kStages) * block * sizeof(float2); }
+size_t step_smem_bytes(int block) { return (size_t)(2 + 3 * ring_stages(block)) * block * sizeof(float2); }
 
 template <class K>
 cudaError_t launch_cluster(K kernel, unsigned grid, size_t smem, cudaStream_t stream, void** args, bool pdl = false)
@@ -389,7 +501,7 @@ cudaError_t launch_cluster(K kernel, unsigned grid, size_t smem, cudaStream_t st
     cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvStepThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kConvCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -413,13 +525,13 @@ cudaError_t conv_upload_twiddles(float2* d_tw, int N, cudaStream_t stream)
     return cudaStreamSynchronize(stream);   // tw is a host temporary
 }
 
-cudaError_t conv_ir_spectra(const float* d_h, int n_items, int ir_len, int block, int P, const float2* d_tw, float2* d_H,
+cudaError_t conv_ir_spectra(const float* d_h, int n_items, int ear0, int ir_len, int block, int P, const float2* d_tw, float2* d_H,
                             cudaStream_t stream)
 {
     const size_t smem = fft_smem_bytes(block);
     cudaError_t e = cudaFuncSetAttribute(ir_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    ir_spectra_kernel<<<(unsigned)(n_items * P), kConvThreads, smem, stream>>>(d_h, ir_len, block, P, d_tw, d_H);
+    ir_spectra_kernel<<<(unsigned)(n_items * P), kConvThreads, smem, stream>>>(d_h, ir_len, block, P, ear0, d_tw, d_H);
     return cudaGetLastError();
 }
 

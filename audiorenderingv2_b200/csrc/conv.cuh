@@ -16,8 +16,9 @@ constexpr int kConvCluster = 8;      // CTAs cooperating on one (source, block) 
 // Twiddle table W_N^k = exp(-2*pi*i*k/N), k < N, computed in fp64 on the host.
 cudaError_t conv_upload_twiddles(float2* d_tw, int N, cudaStream_t stream);
 
-// K10: IR -> partition spectra.  h: [n_items][ir_len] (device), H: [n_items][P][block].
-cudaError_t conv_ir_spectra(const float* d_h, int n_items, int ir_len, int block, int P, const float2* d_tw,
+// K10: IR -> partition spectra.  h: [n_items][ir_len] (device); H: [P][2 ears][block] (the two ears of a partition
+// are adjacent: one bulk copy per partition); item i goes to ear ear0 + i.
+cudaError_t conv_ir_spectra(const float* d_h, int n_items, int ear0, int ir_len, int block, int P, const float2* d_tw,
                             float2* d_H, cudaStream_t stream);
 
 // Forward spectra of consecutive zero-padded input blocks (file mode).
@@ -30,7 +31,7 @@ struct ConvStreamArgs {
     const float* in;         // [n_src][block] newest input block per source
     float* out;              // [n_src][2][block]
     float2* fdl;             // [n_src][P][block] ring of input spectra
-    const float2* const* H;  // [n_src] -> [2][P][block] active IR spectra of each source
+    const float2* const* H;  // [n_src] -> [P][2][block] active IR spectra of each source
     float* tail;             // [n_src][2][block] overlap-add tails
     const float2* tw;
     int n_src, block, P, slot; // slot = ring position of the newest block
@@ -41,7 +42,7 @@ cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream);
 
 struct ConvFileArgs {
     const float2* X;         // [n_seg*blocks_per_seg][block]
-    const float2* H;         // [2][P][block]
+    const float2* H;         // [P][2][block]
     float* out_l; float* out_r; // [n] pre-zeroed, accumulated with RED.ADD.F32
     const float2* tw;
     long long n;             // output length
