@@ -79,6 +79,9 @@ struct arv2_ctx {
     long long rec_capacity = 0, last_range_rays = 0;
     float4* d_pc_seg = nullptr; float* d_pc_energy = nullptr; int* d_pc_nseg = nullptr;
     long long pc_rays = 0; unsigned pc_bounces = 0;
+    // data-parallel re-render: candidate list, per-candidate results, per-ray first hit (trace.cuh)
+    int2* d_rr_cand = nullptr; int2* d_rr_res = nullptr; float* d_rr_energy = nullptr; int* d_rr_first = nullptr;
+    long long rr_cap = 0;
     // breadth-first tracer: per-depth path queues, grown on demand
     float4* d_wave_paths = nullptr; size_t wave_slots = 0;
     bool wave = true;
@@ -199,6 +202,7 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     }
     p->pc_seg = c->d_pc_seg; p->pc_energy = c->d_pc_energy; p->pc_nseg = c->d_pc_nseg;
     p->pc_stride = (long long)c->pc_bounces;
+    p->rr_cand = c->d_rr_cand; p->rr_res = c->d_rr_res; p->rr_energy = c->d_rr_energy; p->rr_first = c->d_rr_first; p->rr_cap = c->rr_cap;
     p->seed = c->seed; p->ray_begin = ray_begin; p->n_rays = n_rays;
     for (int a = 0; a < 3; ++a) { p->emitter[a] = c->emitter[a]; p->center[a] = c->center[a]; }
     p->recv_radius = c->recv_radius;
@@ -293,11 +297,26 @@ int ensure_cache(arv2_ctx* c)
     if (c->max_bounces > 65535u || n > 0x7fffffffLL) { set_error("path cache: max_bounces <= 65535 and at most 2^31 rays"); return ARV2_ERR_INVALID; }
     if (c->d_pc_seg && c->pc_rays == n && c->pc_bounces >= c->max_bounces) return ARV2_OK;
     cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg);
+    cudaFree(c->d_rr_cand); cudaFree(c->d_rr_res); cudaFree(c->d_rr_energy); cudaFree(c->d_rr_first);
     c->d_pc_seg = nullptr; c->d_pc_energy = nullptr; c->d_pc_nseg = nullptr;
+    c->d_rr_cand = nullptr; c->d_rr_res = nullptr; c->d_rr_energy = nullptr; c->d_rr_first = nullptr; c->rr_cap = 0;
     const size_t segs = (size_t)n * c->max_bounces;
     CK(cudaMalloc(&c->d_pc_seg, segs * 2 * sizeof(float4)));
     CK(cudaMalloc(&c->d_pc_energy, segs * sizeof(float) * c->bands));
     CK(cudaMalloc(&c->d_pc_nseg, (size_t)n * sizeof(int)));
+    // room for 4 ball-entering segments per ray (the conference room has 1.3); more than that, or no memory for the
+    // lists, and the re-render takes the persistent per-ray kernel
+    long long cap = std::max<long long>(1 << 16, std::min<long long>(4 * n, (long long)segs));
+    if (const char* e = getenv("ARV2_RR_CAP")) cap = atoll(e) > 0 ? atoll(e) : cap;     // tests: force the overflow fallback
+    if (!getenv("ARV2_RR_SERIAL") &&
+        cudaMalloc(&c->d_rr_cand, (size_t)cap * sizeof(int2)) == cudaSuccess && cudaMalloc(&c->d_rr_res, (size_t)cap * sizeof(int2)) == cudaSuccess &&
+        cudaMalloc(&c->d_rr_energy, (size_t)cap * sizeof(float) * c->bands) == cudaSuccess && cudaMalloc(&c->d_rr_first, (size_t)n * sizeof(int)) == cudaSuccess) {
+        c->rr_cap = cap;
+    } else {
+        cudaGetLastError();
+        cudaFree(c->d_rr_cand); cudaFree(c->d_rr_res); cudaFree(c->d_rr_energy); cudaFree(c->d_rr_first);
+        c->d_rr_cand = nullptr; c->d_rr_res = nullptr; c->d_rr_energy = nullptr; c->d_rr_first = nullptr; c->rr_cap = 0;
+    }
     c->pc_rays = n; c->pc_bounces = c->max_bounces; c->cache_valid = false;
     return ARV2_OK;
 }
@@ -599,6 +618,7 @@ void arv2_destroy(arv2_ctx* c)
     cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_ir_r); cudaFree(c->d_counters);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
     cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg); cudaFree(c->d_ray_order); cudaFree(c->d_wave_paths);
+    cudaFree(c->d_rr_cand); cudaFree(c->d_rr_res); cudaFree(c->d_rr_energy); cudaFree(c->d_rr_first);
     cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -684,10 +704,25 @@ int arv2_rerender(arv2_ctx* c, double* ms)
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
-    CK(launch_rerender(p, c->bands, c->sm_count, c->stream));
+    const bool parallel = c->rr_cap > 0;
+    if (parallel) {
+        CK(cudaMemsetAsync(c->d_rr_first, 0x7f, (size_t)c->n_rays_total * sizeof(int), c->stream));     // kRrNoHit
+        CK(launch_rerender_parallel(p, c->bands, c->sm_count, c->stream));
+    } else {
+        CK(launch_rerender(p, c->bands, c->sm_count, c->stream));
+    }
     CK(launch_finalize(c->d_hist, c->bands, c->ir_len, c->mono, c->d_ir_l, c->d_ir_r, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
     c->last_range_rays = c->n_rays_total;
+    rc = finish_timed(c, ms);
+    if (rc != ARV2_OK || !parallel || c->h_counters[2] <= (unsigned long long)c->rr_cap) return rc;
+    // more ball-entering segments than the candidate list holds (a receiver that fills the room): the per-ray kernel
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
+    CK(launch_rerender(p, c->bands, c->sm_count, c->stream));
+    CK(launch_finalize(c->d_hist, c->bands, c->ir_len, c->mono, c->d_ir_l, c->d_ir_r, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
     return finish_timed(c, ms);
 }
 

@@ -892,6 +892,143 @@ __global__ void __launch_bounds__(kRerenderThreads, ARV2_RR_MINB) rerender_kerne
     if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
 }
 
+// ---------------------------------------------------------------------------------------
+// Data-parallel re-render.  The persistent kernel above walks every ray's cached segments in order: a chain of
+// dependent DRAM round trips per lane (0.61 ms for 27 M segments, 4x the HBM time of the cache).  Here the order is
+// restored afterwards instead:
+//   rr_scan     one warp per ray, lane k tests cached segment k against the receiver's bounding ball (coalesced
+//               1 KB reads, no dependence between rays) and appends the candidates (ray, k) to a global list;
+//   rr_walk     one lane per candidate walks the receiver tree; a hit stores (bin, ear, weighted energy) and lowers
+//               rr_first[ray] to its k with atomicMin;
+//   rr_resolve  the candidate whose k equals rr_first[ray] deposits (the trace would have ended that ray there);
+//               rays without a hit are closed as misses.
+// A few walks are wasted on segments behind a ray's first hit; every pass runs at full occupancy.
+constexpr int kRrThreads = 256;
+
+template <int NB>
+__global__ void __launch_bounds__(kRrThreads) rr_scan_kernel(const TraceParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int stride = (int)p.pc_stride;
+    for (long long ray = warp0; ray < p.n_rays; ray += n_warps) {
+        const float4* base = p.pc_seg + 2 * (size_t)ray * (size_t)stride;
+        // the first 32 records are fetched together with the ray's segment count (no dependent round trip)
+        const int n = __ldg(p.pc_nseg + ray);
+        F8 rec;
+        rec.lo = make_float4(0.f, 0.f, 0.f, 0.f); rec.hi = rec.lo;
+        if (lane < stride) rec = ldg256(base + 2 * lane);
+        for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            if (k0 > 0 && k < n) rec = ldg256(base + 2 * k);
+            const bool cand = k < n && enters_receiver_ball(p, f3(rec.lo.x, rec.lo.y, rec.lo.z), f3(rec.hi.x, rec.hi.y, rec.hi.z), rec.lo.w);
+            const unsigned m = __ballot_sync(FULL, cand);
+            if (m) {
+                unsigned long long b = 0;
+                if (lane == 0) b = atomicAdd(p.counters + 2, (unsigned long long)__popc(m));
+                b = __shfl_sync(FULL, b, 0);
+                const long long idx = (long long)b + __popc(m & lt);
+                if (cand && idx < p.rr_cap) p.rr_cand[idx] = make_int2((int)ray, k);
+            }
+        }
+    }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kRrThreads) rr_walk_kernel(const TraceParams p)
+{
+    const unsigned long long found = p.counters[2];
+    const long long n_cand = (long long)(found < (unsigned long long)p.rr_cap ? found : (unsigned long long)p.rr_cap);
+    Traversal tr;
+    int stack[kStack];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (long long)gridDim.x * blockDim.x) {
+        const int2 c = p.rr_cand[i];
+        const size_t ci = (size_t)c.x * (size_t)p.pc_stride + (size_t)c.y;
+        const F8 rec = ldg256(p.pc_seg + 2 * ci);
+        const float4 ot = rec.lo, dd = rec.hi;
+        const F3 org = f3(ot.x, ot.y, ot.z), dir = f3(dd.x, dd.y, dd.z);
+        closest_hit(p, stack, tr, p.recv_root, org, dir, ot.w);
+        const Hit& h = tr.h;
+        int2 res = make_int2(-1, 0);
+        if (h.slot >= 0 && h.t < ot.w) {
+            const F8 A = ldg256(p.tris + h.slot * 4), B = ldg256(p.tris + h.slot * 4 + 2);
+            const int mat = __float_as_int(A.hi.w);
+            const F3 pt = hit_point(f3(A.lo.x, A.lo.y, A.lo.z), f3(A.hi.x, A.hi.y, A.hi.z), f3(B.lo.x, B.lo.y, B.lo.z), h.u, h.v);
+            const F3 dp = sub3(pt, org);
+            const float dist = __fadd_rn(dd.w, __fsqrt_rn(dot3(dp, dp)));
+            float energy[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) energy[b] = p.pc_energy[ci * NB + b];
+            res.x = receiver_hit<NB>(p, pt, dir, dist, energy);
+            res.y = (mat == -1) ? 1 : 2;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) p.rr_energy[(size_t)i * NB + b] = energy[b];
+            atomicMin(p.rr_first + c.x, c.y);
+        }
+        p.rr_res[i] = res;
+    }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kRrThreads) rr_resolve_kernel(const TraceParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned long long found = p.counters[2];
+    const long long n_cand = (long long)(found < (unsigned long long)p.rr_cap ? found : (unsigned long long)p.rr_cap);
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n_thr = (long long)gridDim.x * blockDim.x;
+    unsigned long long segs = 0;
+    // hits: only a ray's first one counts (warp-uniform trip count: deposit_warp is a warp collective)
+    for (long long i0 = tid - lane; i0 < n_cand; i0 += n_thr) {
+        const long long i = i0 + lane;
+        bool dep = false;
+        int bin = -1, primary = 0;
+        float energy[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) energy[b] = 0.f;
+        if (i < n_cand) {
+            const int2 res = p.rr_res[i];
+            if (res.y != 0) {
+                const int2 c = p.rr_cand[i];
+                if (p.rr_first[c.x] == c.y) {
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) energy[b] = p.rr_energy[(size_t)i * NB + b];
+                    bin = res.x; primary = res.y - 1;
+                    dep = bin >= 0 && bin < p.ir_len;
+                    if (p.rec_bin) p.rec_bin[c.x] = bin;
+                    if (p.rec_ear) p.rec_ear[c.x] = res.y;
+                    if (p.rec_nseg) p.rec_nseg[c.x] = c.y + 1;
+                    if (p.rec_energy) {
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) p.rec_energy[(size_t)c.x * NB + b] = energy[b];
+                    }
+                    segs += (unsigned long long)(c.y + 1);
+                }
+            }
+        }
+        deposit_warp<NB>(p, dep, bin, primary, energy);
+    }
+    // misses: every cached segment passed
+    for (long long r = tid; r < p.n_rays; r += n_thr) {
+        if (p.rr_first[r] == kRrNoHit) {
+            const int n = p.pc_nseg[r];
+            if (p.rec_bin) p.rec_bin[r] = -1;
+            if (p.rec_ear) p.rec_ear[r] = 0;
+            if (p.rec_nseg) p.rec_nseg[r] = n;
+            if (p.rec_energy) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) p.rec_energy[(size_t)r * NB + b] = 0.f;
+            }
+            segs += (unsigned long long)n;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
+    if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+}
+
 __device__ __forceinline__ unsigned spread16(unsigned v)
 {
     v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu;
@@ -972,6 +1109,25 @@ cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaS
     if (bands == 1) rerender_kernel<1><<<(unsigned)grid, kRerenderThreads, 0, stream>>>(p);
     else rerender_kernel<8><<<(unsigned)grid, kRerenderThreads, 0, stream>>>(p);
     return cudaGetLastError();
+}
+
+template <int NB>
+static cudaError_t launch_rerender_parallel_t(const TraceParams& p, int sm_count, cudaStream_t stream)
+{
+    const unsigned grid = (unsigned)(sm_count * (2048 / kRrThreads));
+    rr_scan_kernel<NB><<<grid, kRrThreads, 0, stream>>>(p);
+    rr_walk_kernel<NB><<<grid, kRrThreads, 0, stream>>>(p);
+    rr_resolve_kernel<NB><<<grid, kRrThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rerender_parallel(const TraceParams& p, int bands, int sm_count, cudaStream_t stream)
+{
+    if (p.n_rays == 0) return cudaSuccess;
+    if (!p.rr_cand || !p.rr_res || !p.rr_energy || !p.rr_first) return cudaErrorInvalidValue;
+    if (bands == 1) return launch_rerender_parallel_t<1>(p, sm_count, stream);
+    if (bands == 8) return launch_rerender_parallel_t<8>(p, sm_count, stream);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_direction_keys(unsigned long long seed, long long ray_begin, long long n, unsigned* keys, int* vals, cudaStream_t stream)

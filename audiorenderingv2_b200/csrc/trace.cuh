@@ -36,6 +36,12 @@ struct TraceParams {
     long long wave_cap;         // ring slots per queue = most paths alive per SM
     int wave_queues;            // queue j holds paths of depth (j + 1) * wave_segments
     int wave_segments;          // segments per task
+    // data-parallel re-render (rr_scan / rr_walk / rr_resolve kernels; optional): candidate list and per-ray first hit
+    int2* rr_cand;              // [rr_cap] (ray, k) of every cached segment that enters the receiver's bounding ball
+    int2* rr_res;               // [rr_cap] (bin, ear) of the candidate's receiver hit, ear 0 = the walk missed
+    float* rr_energy;           // [rr_cap][bands] chord-weighted energy of the hit
+    int* rr_first;              // [n_rays] smallest k with a receiver hit (pre-set to 0x7f7f7f7f)
+    long long rr_cap;           // counters[2] = candidates found (may exceed rr_cap: the caller then falls back)
     const int* ray_order;       // optional: the order in which the launch's rays [0, n_rays) are started (direction-sorted)
     int chunk;                  // rays a warp claims per global atomic
     int refill_below;           // lanes of a warp are refilled only while fewer than this many hold a path (32 = always)
@@ -48,8 +54,11 @@ __host__ __device__ constexpr int cont_f4(int bands) { return bands == 1 ? 3 : 5
 // mode 0: full trace (scene + receiver), deposits into hist.
 // mode 1: scene-only trace that fills the path cache (no deposits).
 cudaError_t launch_trace(const TraceParams& p, int bands, int mode, int sm_count, cudaStream_t stream);
-// Re-deposit from the path cache against the current receiver sub-tree.
+// Re-deposit from the path cache against the current receiver sub-tree: persistent per-ray scan (fallback) ...
 cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaStream_t stream);
+// ... and the data-parallel version (needs p.rr_*; rr_first pre-set to 0x7f bytes, counters zeroed).
+cudaError_t launch_rerender_parallel(const TraceParams& p, int bands, int sm_count, cudaStream_t stream);
+constexpr int kRrNoHit = 0x7f7f7f7f;
 // hist (fp64) -> ir_left / ir_right (fp32); mono: L = R = L + R (OR/kernels.cu:519-527).
 cudaError_t launch_finalize(const double* hist, int bands, int ir_len, int mono, float* ir_left, float* ir_right,
                             cudaStream_t stream);
