@@ -304,11 +304,12 @@ int ensure_cache(arv2_ctx* c)
     CK(cudaMalloc(&c->d_pc_seg, segs * 2 * sizeof(float4)));
     CK(cudaMalloc(&c->d_pc_energy, segs * sizeof(float) * c->bands));
     CK(cudaMalloc(&c->d_pc_nseg, (size_t)n * sizeof(int)));
-    // room for 4 ball-entering segments per ray (the conference room has 1.3); more than that, or no memory for the
-    // lists, and the re-render takes the persistent per-ray kernel
+    // data-parallel re-render (experiment, ARV2_RR_PARALLEL=1; 1.2 ms against 0.61 ms for the persistent per-ray
+    // kernel on C2, profiles/r07_trace_experiments.md section 8): room for 4 ball-entering segments per ray; more
+    // than that, or no memory for the lists, and the re-render takes the per-ray kernel
     long long cap = std::max<long long>(1 << 16, std::min<long long>(4 * n, (long long)segs));
     if (const char* e = getenv("ARV2_RR_CAP")) cap = atoll(e) > 0 ? atoll(e) : cap;     // tests: force the overflow fallback
-    if (!getenv("ARV2_RR_SERIAL") &&
+    if (getenv("ARV2_RR_PARALLEL") &&
         cudaMalloc(&c->d_rr_cand, (size_t)cap * sizeof(int2)) == cudaSuccess && cudaMalloc(&c->d_rr_res, (size_t)cap * sizeof(int2)) == cudaSuccess &&
         cudaMalloc(&c->d_rr_energy, (size_t)cap * sizeof(float) * c->bands) == cudaSuccess && cudaMalloc(&c->d_rr_first, (size_t)n * sizeof(int)) == cudaSuccess) {
         c->rr_cap = cap;

@@ -893,26 +893,45 @@ __global__ void __launch_bounds__(kRerenderThreads, ARV2_RR_MINB) rerender_kerne
 }
 
 // ---------------------------------------------------------------------------------------
-// Data-parallel re-render.  The persistent kernel above walks every ray's cached segments in order: a chain of
-// dependent DRAM round trips per lane (0.61 ms for 27 M segments, 4x the HBM time of the cache).  Here the order is
-// restored afterwards instead:
+// Data-parallel re-render (experiment, ARV2_RR_PARALLEL=1; measured SLOWER than the persistent kernel, which stays
+// the default: 1.2 ms against 0.61 ms on C2, profiles/r07_trace_experiments.md section 8).  The persistent kernel
+// above walks every ray's cached segments in order: a chain of dependent DRAM round trips per lane (0.61 ms for
+// 27 M segments, 4x the HBM time of the cache).  Here the order is restored afterwards instead:
 //   rr_scan     one warp per ray, lane k tests cached segment k against the receiver's bounding ball (coalesced
 //               1 KB reads, no dependence between rays) and appends the candidates (ray, k) to a global list;
 //   rr_walk     one lane per candidate walks the receiver tree; a hit stores (bin, ear, weighted energy) and lowers
 //               rr_first[ray] to its k with atomicMin;
 //   rr_resolve  the candidate whose k equals rr_first[ray] deposits (the trace would have ended that ray there);
 //               rays without a hit are closed as misses.
-// A few walks are wasted on segments behind a ray's first hit; every pass runs at full occupancy.
+// The scan does run at 4.5 TB/s (0.36 ms cold, reading all 50 slots of every ray), but the walks behind a ray's
+// first hit are not "a few": 473 M warp instructions at 7 lanes for the walk pass alone, more than the whole
+// persistent kernel (330 M).
 constexpr int kRrThreads = 256;
 
 template <int NB>
 __global__ void __launch_bounds__(kRrThreads) rr_scan_kernel(const TraceParams p)
 {
+    // candidates are collected per warp and appended 32 at a time: one atomic per 32 candidates on the list's
+    // counter (one per ray with a candidate serialised the kernel on that address: 2 ms, r07)
+    __shared__ int2 sh_buf[kRrThreads / 32][64];
+    int2* const buf = sh_buf[threadIdx.x >> 5];
+    int n_buf = 0;                                            // warp-uniform
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int stride = (int)p.pc_stride;
+    auto flush = [&](int count) {                             // the first `count` (<= 32) buffered candidates
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(p.counters + 2, (unsigned long long)count);
+        b = __shfl_sync(FULL, b, 0);
+        const long long idx = (long long)b + lane;
+        if (lane < count && idx < p.rr_cap) p.rr_cand[idx] = buf[lane];
+        __syncwarp();
+        if (lane + 32 < n_buf) buf[lane] = buf[lane + 32];    // n_buf <= 64: what is left moves to the front
+        n_buf -= count;
+        __syncwarp();
+    };
     for (long long ray = warp0; ray < p.n_rays; ray += n_warps) {
         const float4* base = p.pc_seg + 2 * (size_t)ray * (size_t)stride;
         // the first 32 records are fetched together with the ray's segment count (no dependent round trip)
@@ -926,14 +945,14 @@ __global__ void __launch_bounds__(kRrThreads) rr_scan_kernel(const TraceParams p
             const bool cand = k < n && enters_receiver_ball(p, f3(rec.lo.x, rec.lo.y, rec.lo.z), f3(rec.hi.x, rec.hi.y, rec.hi.z), rec.lo.w);
             const unsigned m = __ballot_sync(FULL, cand);
             if (m) {
-                unsigned long long b = 0;
-                if (lane == 0) b = atomicAdd(p.counters + 2, (unsigned long long)__popc(m));
-                b = __shfl_sync(FULL, b, 0);
-                const long long idx = (long long)b + __popc(m & lt);
-                if (cand && idx < p.rr_cap) p.rr_cand[idx] = make_int2((int)ray, k);
+                if (cand) buf[n_buf + __popc(m & lt)] = make_int2((int)ray, k);
+                n_buf += __popc(m);
+                __syncwarp();
+                if (n_buf >= 32) flush(32);
             }
         }
     }
+    if (n_buf > 0) flush(n_buf);
 }
 
 template <int NB>
