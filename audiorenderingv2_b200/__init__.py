@@ -112,6 +112,7 @@ SYMBOLS = {
     "arv2_stream_set_ir_device": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
     "arv2_stream_process": (C.c_int, [_vp, _fp, _fp]),
     "arv2_stream_process_device": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "arv2_stream_process_device_blocks": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp]),
     "arv2_stream_reset": (C.c_int, [_vp]),
     "arv2_stream_close": (None, [_vp]),
     "arv2_global_angle": (C.c_float, [C.c_float, C.c_float]),
@@ -440,6 +441,10 @@ class ConvStream:
 
     def process_device(self, d_in, d_out, cuda_stream=None):
         _check(lib().arv2_stream_process_device(self._h, d_in, d_out, cuda_stream))
+
+    def process_device_blocks(self, d_in, d_out, n_blocks, cuda_stream=None):
+        """n_blocks consecutive blocks: d_in [n_blocks][n_sources][block], d_out [n_blocks][n_sources][2][block]."""
+        _check(lib().arv2_stream_process_device_blocks(self._h, d_in, d_out, n_blocks, cuda_stream))
 
     def reset(self):
         _check(lib().arv2_stream_reset(self._h))

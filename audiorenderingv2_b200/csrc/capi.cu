@@ -1006,6 +1006,17 @@ int arv2_stream_process_device(arv2_stream* s, const float* d_in, float* d_out, 
     return ARV2_OK;
 }
 
+int arv2_stream_process_device_blocks(arv2_stream* s, const float* d_in, float* d_out, int32_t n_blocks, void* cuda_stream)
+{
+    REQUIRE(s && d_in && d_out && n_blocks >= 0, "arv2_stream_process_device_blocks: bad argument");
+    const size_t nin = (size_t)s->n_src * s->block;
+    for (int32_t b = 0; b < n_blocks; ++b) {
+        const int rc = arv2_stream_process_device(s, d_in + (size_t)b * nin, d_out + (size_t)b * 2 * nin, cuda_stream);
+        if (rc != ARV2_OK) return rc;
+    }
+    return ARV2_OK;
+}
+
 int arv2_stream_process(arv2_stream* s, const float* in, float* out)
 {
     REQUIRE(s && in && out, "arv2_stream_process: null argument");

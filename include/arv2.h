@@ -230,6 +230,11 @@ int arv2_stream_set_ir_device(arv2_stream* s, int32_t source, const float* d_lef
 int arv2_stream_process(arv2_stream* s, const float* in, float* out);
 /* Same with device-resident buffers, enqueued on `cuda_stream` without syncing. */
 int arv2_stream_process_device(arv2_stream* s, const float* d_in, float* d_out, void* cuda_stream);
+/* n_blocks consecutive blocks in one call (an RtAudio callback of the reference carries 4096 frames = 8 blocks of
+ * 512, OR/main.cpp:99-135): d_in = float[n_blocks][n_sources][block], d_out = float[n_blocks][n_sources][2][block],
+ * device-resident, enqueued on `cuda_stream` without syncing.  The steps are launched back to back and overlap on
+ * the device (programmatic dependent launch); the result is the one n_blocks single-block calls give. */
+int arv2_stream_process_device_blocks(arv2_stream* s, const float* d_in, float* d_out, int32_t n_blocks, void* cuda_stream);
 int arv2_stream_reset(arv2_stream* s);
 void arv2_stream_close(arv2_stream* s);
 

@@ -91,7 +91,8 @@ def test_file_reference_mode_two_second_ir():
     assert rel_l2(yl, lin) <= TOL
 
 
-@pytest.mark.parametrize("block,n_src,ir_len", [(512, 3, 4800), (128, 2, 1000), (256, 1, 256), (1024, 2, 5000), (64, 1, 130)])
+@pytest.mark.parametrize("block,n_src,ir_len", [(512, 3, 4800), (128, 2, 1000), (256, 1, 256), (1024, 2, 5000), (64, 1, 130), (512, 1, 1000),
+                                                (1024, 1, 40000)])
 def test_stream_matches_direct(block, n_src, ir_len):
     rng = np.random.default_rng(block + n_src)
     st = arv.ConvStream(n_src, block, ir_len)
@@ -119,11 +120,20 @@ def test_stream_back_to_back_steps_overlap_safely():
     irs = [(decaying_ir(ir_len, 130 + i, 0.2, 48000), decaying_ir(ir_len, 160 + i, 0.15, 48000)) for i in range(n_src)]
     x = (0.1 * rng.standard_normal((nb, n_src, block))).astype(np.float32)
     outs = []
-    for mode in ("device", "host"):
+    for mode in ("device", "blocks", "host"):
         st = arv.ConvStream(n_src, block, ir_len)
         for i, (a, b) in enumerate(irs):
             st.set_ir(i, a, b)
-        if mode == "device":
+        if mode == "blocks":                              # the same through the multi-block entry point
+            dev = torch.device("cuda", 0)
+            dx = torch.from_numpy(x).to(dev)
+            dy = torch.empty(nb, n_src, 2, block, device=dev)
+            s = torch.cuda.Stream(device=dev)
+            torch.cuda.synchronize()
+            st.process_device_blocks(dx.data_ptr(), dy.data_ptr(), nb, s.cuda_stream)
+            torch.cuda.synchronize()
+            outs.append(dy.cpu().numpy())
+        elif mode == "device":
             dev = torch.device("cuda", 0)
             dx = torch.from_numpy(x).to(dev)
             dy = torch.empty(nb, n_src, 2, block, device=dev)
@@ -137,7 +147,7 @@ def test_stream_back_to_back_steps_overlap_safely():
         else:
             outs.append(np.stack([st.process(x[k]) for k in range(nb)]))
         st.close()
-    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[2])
     y = np.concatenate(list(outs[0]), axis=2)          # [n_src][2][nb*block]
     xs = np.concatenate(list(x), axis=1)
     for i, (a, b) in enumerate(irs):
