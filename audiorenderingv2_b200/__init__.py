@@ -73,6 +73,7 @@ SYMBOLS = {
     "arv2_scene_get_triangles": (C.c_int, [_vp, _fp, _ip]),
     "arv2_scene_mesh_material": (C.c_char_p, [_vp, C.c_int32]),
     "arv2_scene_bounds": (C.c_int, [_vp, _fp, _fp]),
+    "arv2_scene_bvh_stats": (C.c_int, [_vp, _vp]),
     "arv2_scene_destroy": (None, [_vp]),
     "arv2_receiver_load": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(_vp)]),
     "arv2_receiver_from_triangles": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, C.POINTER(_vp)]),
@@ -159,6 +160,12 @@ def _i(a):
     return a.ctypes.data_as(_ip)
 
 
+class BvhStats(C.Structure):
+    """struct arv2_bvh_stats (include/arv2.h)."""
+    _fields_ = [("n_tris", C.c_int64), ("n_nodes", C.c_int64), ("n_leaves", C.c_int64), ("max_leaf_tris", C.c_int32),
+                ("depth", C.c_int32), ("valid", C.c_int32), ("sah_nodes", C.c_double), ("sah_tris", C.c_double)]
+
+
 class Scene:
     """struct OptixModel (OR/OptixModel.h:21-32)."""
 
@@ -201,6 +208,12 @@ class Scene:
         lo = np.empty(3, np.float32); hi = np.empty(3, np.float32)
         _check(lib().arv2_scene_bounds(self._h, _f(lo), _f(hi)))
         return lo, hi
+
+    def bvh_stats(self):
+        """Builds (on the host) the BVH the renderer would upload and checks it; dict of arv2_bvh_stats."""
+        st = BvhStats()
+        _check(lib().arv2_scene_bvh_stats(self._h, C.byref(st)))
+        return {n: getattr(st, n) for n, _ in BvhStats._fields_}
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

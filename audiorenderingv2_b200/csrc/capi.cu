@@ -403,6 +403,60 @@ int arv2_scene_bounds(const arv2_scene* s, float* lo, float* hi)
     return ARV2_OK;
 }
 
+int arv2_scene_bvh_stats(const arv2_scene* s, arv2_bvh_stats* out)
+{
+    REQUIRE(s && out, "null argument");
+    const std::vector<float>& tv = s->s.tri_verts;
+    const int64_t n = s->s.n_tris();
+    HostBvh b;
+    build_bvh_sah(tv.data(), n, &b, 8);
+    std::memset(out, 0, sizeof *out);
+    out->n_tris = n; out->n_nodes = (int64_t)b.nodes.size(); out->depth = bvh2_depth(b);
+    auto area = [](const float* lo, const float* hi) {
+        const double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    const double root_area = n > 0 ? area(b.lo, b.hi) : 0.0;
+    std::vector<int32_t> seen((size_t)n, 0);
+    bool ok = b.order.size() == (size_t)n && !b.nodes.empty();
+    double cn = n > 0 ? 1.0 : 0.0, ct = 0.0;
+    for (size_t i = 0; i < b.nodes.size() && ok; ++i) {
+        const BvhNode& nd = b.nodes[i];
+        int32_t c[4];
+        std::memcpy(c, &nd.q[12], sizeof c);
+        for (int w = 0; w < 2; ++w) {
+            const float lo[3] = {nd.q[w * 4 + 0], nd.q[w * 4 + 2], nd.q[8 + w * 2]}, hi[3] = {nd.q[w * 4 + 1], nd.q[w * 4 + 3], nd.q[8 + w * 2 + 1]};
+            if (lo[0] == kEmptyBox) continue;                         // absent child
+            const double a = root_area > 0.0 ? area(lo, hi) / root_area : 0.0;
+            if (c[w] >= 0) {
+                cn += a;
+                if (c[w] <= (int32_t)i || c[w] >= (int32_t)b.nodes.size()) ok = false;
+            } else {
+                const int32_t code = ~c[w];
+                const int64_t first = code >> kLeafShift;
+                const int cnt = (code & 7) + 1;
+                out->n_leaves++;
+                out->max_leaf_tris = std::max(out->max_leaf_tris, cnt);
+                ct += a * cnt;
+                if (first < 0 || first + cnt > n) { ok = false; break; }
+                for (int t = 0; t < cnt; ++t) {
+                    const int32_t id = b.order[(size_t)(first + t)];
+                    if (id < 0 || id >= n) { ok = false; break; }
+                    seen[(size_t)id]++;
+                    for (int k = 0; k < 3; ++k)
+                        for (int ax = 0; ax < 3; ++ax) {
+                            const float v = tv[9 * (size_t)id + 3 * k + ax];
+                            if (v < lo[ax] || v > hi[ax]) ok = false;
+                        }
+                }
+            }
+        }
+    }
+    for (int64_t i = 0; i < n && ok; ++i) if (seen[(size_t)i] != 1) ok = false;
+    out->valid = ok ? 1 : 0; out->sah_nodes = cn; out->sah_tris = ct;
+    return ARV2_OK;
+}
+
 void arv2_scene_destroy(arv2_scene* s) { delete s; }
 
 int arv2_receiver_load(const char* left_obj, const char* right_obj, arv2_receiver** out)

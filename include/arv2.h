@@ -62,6 +62,16 @@ int arv2_scene_get_triangles(const arv2_scene* s, float* tri_verts, int32_t* tri
 const char* arv2_scene_mesh_material(const arv2_scene* s, int32_t mesh);
 /* OptixModel::bounds (OR/OptixModel.cpp:143-147): lo[3], hi[3]. */
 int arv2_scene_bounds(const arv2_scene* s, float* lo3, float* hi3);
+/* Host-only diagnostic of the acceleration structure built for this scene (replaces what optixAccelBuild +
+ * optixAccelCompact report, OR/AudioRenderer.cpp:152-207): builds the SAH BVH the renderer would upload and checks
+ * it -- every triangle in exactly one leaf, every child box contains its triangles, children stored after their
+ * parent.  sah_nodes / sah_tris = expected node visits / triangle tests of a random line (surface-area heuristic). */
+typedef struct arv2_bvh_stats {
+    int64_t n_tris, n_nodes, n_leaves;
+    int32_t max_leaf_tris, depth, valid;
+    double sah_nodes, sah_tris;
+} arv2_bvh_stats;
+int arv2_scene_bvh_stats(const arv2_scene* s, arv2_bvh_stats* out);
 void arv2_scene_destroy(arv2_scene* s);
 
 /* class HalfSphere / Sphere (OR/HalfSphere.cpp, OR/Sphere.cpp): the two half-ball

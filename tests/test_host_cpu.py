@@ -102,6 +102,45 @@ def test_scene_roundtrip_and_bounds(golden_scenes):
     assert np.allclose(lo, [-13.453613, 0.0, -14.577106]) and np.allclose(hi[0], 18.02746)
 
 
+def _bvh_stats_in_subprocess(tris, env):
+    """The builder reads its tuning knobs once per process, so every setting gets a fresh interpreter."""
+    import subprocess, sys, tempfile
+    with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+        np.save(f.name, np.ascontiguousarray(tris, np.float32))
+        code = ("import json, sys, numpy as np; sys.path.insert(0, %r); import audiorenderingv2_b200 as arv; t = np.load(%r); "
+                "print(json.dumps(arv.Scene.from_triangles(t, np.zeros(len(t), np.int32), ['m']).bvh_stats()))") % (ROOT, f.name)
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, check=True)
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def test_host_bvh_is_valid_for_ragged_inputs(golden_scenes):
+    """Host SAH builder (replaces optixAccelBuild, OR/AudioRenderer.cpp:95-218): every triangle in exactly one leaf,
+    child boxes contain their triangles, children after parents -- for empty, tiny, degenerate (coincident
+    centroids, zero-area) and real inputs, with the SAH leaf test (default) and without it."""
+    rng = np.random.default_rng(3)
+    one = rng.standard_normal((1, 3, 3)).astype(np.float32)
+    cases = {
+        "empty": np.zeros((0, 3, 3), np.float32),
+        "one": one,
+        "five": rng.standard_normal((5, 3, 3)).astype(np.float32),
+        "coincident": np.repeat(one, 37, axis=0),                                   # 37 copies of one triangle
+        "zero_area": np.zeros((9, 3, 3), np.float32),
+        "test_obj": golden_scenes["test_verts"],
+        "random_2000": (rng.standard_normal((2000, 1, 3)) * 10 + rng.standard_normal((2000, 3, 3)) * 0.3).astype(np.float32),
+    }
+    for name, tris in cases.items():
+        for env in ({}, {"ARV2_SAH_CT": "0"}, {"ARV2_LEAF_MAX": "8", "ARV2_SAH_CT": "1.5"}, {"ARV2_LEAF_MAX": "1"}, {"ARV2_SAH_SWEEP": "64"}):
+            st = _bvh_stats_in_subprocess(tris, env)
+            assert st["valid"] == 1, (name, env, st)
+            assert st["n_tris"] == len(tris) and st["max_leaf_tris"] <= int(env.get("ARV2_LEAF_MAX", 4)) or len(tris) <= 4, (name, env, st)
+            assert st["depth"] + 3 <= 64, (name, env, st)              # kTraversalStack of the kernels
+    # the SAH leaf test ends the tessellated scenes in quads: fewer triangle tests for a few more nodes
+    tv, _, _ = scenes.conference_room(target_tris=20_000)
+    with_test, without = _bvh_stats_in_subprocess(tv, {}), _bvh_stats_in_subprocess(tv, {"ARV2_SAH_CT": "0"})
+    assert with_test["valid"] == 1 and without["valid"] == 1
+    assert with_test["sah_tris"] < 0.75 * without["sah_tris"] and with_test["sah_nodes"] < 1.15 * without["sah_nodes"]
+
+
 CONFIG_CASES = [
     "{}",
     json.dumps({"pathtracer_parameters": {"hrtf_absorption_rate": 0.9, "ray_max_bounces": 99.5, "base_power": 3.62,
