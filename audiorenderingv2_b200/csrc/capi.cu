@@ -328,6 +328,8 @@ int finish_timed(arv2_ctx* c, double* ms)
     CK(cudaStreamSynchronize(c->stream));                    // CUDA_SYNC_CHECK, OR/AudioRenderer.cpp:511
     c->last_segments = (long long)c->h_counters[1];
     if (c->h_counters[7] != 0) { set_error("trace: path-queue watchdog tripped (a warp waited too long for a queued path)"); return ARV2_ERR_CUDA; }
+    if (getenv("ARV2_TAILSTAT") && c->h_counters[13]) fprintf(stderr, "tail: CTA busy time min %.3f ms, mean %.3f ms over %llu CTAs\n", (double)c->h_counters[14] * 1e-6,
+                                                                (double)c->h_counters[12] / (double)c->h_counters[13] * 1e-6, c->h_counters[13]);
     if (getenv("ARV2_TAILSTAT")) fprintf(stderr, "tail: pool empty -> first warp exit %.3f ms, -> last warp exit %.3f ms\n",
                                          ((double)c->h_counters[6] - (double)c->h_counters[4]) * 1e-6, ((double)c->h_counters[5] - (double)c->h_counters[4]) * 1e-6);
     if (getenv("ARV2_PRINT_STATS")) { for (int i = 0; i < 16; ++i) fprintf(stderr, "%llu ", c->h_counters[i]); fprintf(stderr, "\n"); }
@@ -723,7 +725,7 @@ int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t ze
     const size_t irn = (size_t)c->bands * c->ir_len;
     if (zero_first) CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));   // fillZeros, OR/AudioRenderer.cpp:491-492
     CK(cudaMemsetAsync(c->d_counters, 0, kCounters * sizeof(unsigned long long), c->stream));
-    if (getenv("ARV2_TAILSTAT")) { CK(cudaMemsetAsync(c->d_counters + 4, 0xFF, 8, c->stream)); CK(cudaMemsetAsync(c->d_counters + 6, 0xFF, 8, c->stream)); }
+    if (getenv("ARV2_TAILSTAT")) { CK(cudaMemsetAsync(c->d_counters + 4, 0xFF, 8, c->stream)); CK(cudaMemsetAsync(c->d_counters + 6, 0xFF, 8, c->stream)); CK(cudaMemsetAsync(c->d_counters + 14, 0xFF, 8, c->stream)); }
     rc = ensure_ray_order(c, ray_begin, n_rays);
     if (rc != ARV2_OK) return rc;
     TraceParams p;

@@ -569,6 +569,9 @@ __global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams
     Traversal tr;
     int stack[kStack];
     unsigned idle = 0;
+#ifdef ARV2_TAILSTAT
+    unsigned long long t_begin; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+#endif
 #ifdef ARV2_WAVESTAT
     unsigned long long st_tasks = 0, st_rays = 0, st_fail = 0, st_idle = 0;
 #define WST(x) x
@@ -587,7 +590,12 @@ __global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams
                 take = take < 0 ? 0 : (take > 32 ? 32 : take);
                 if (take < 32) atomicSub(&sh_alive, 32 - (int)take);
                 if (take > 0) { src = -1; n = (int)take; pos = (unsigned long long)b; }
-                else *v_done = 1;
+                else {
+                    *v_done = 1;
+#ifdef ARV2_TAILSTAT
+                    { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(p.counters + 4, t); }
+#endif
+                }
             } else {
                 atomicSub(&sh_alive, 32);
             }
@@ -681,6 +689,13 @@ __global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
     if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+#ifdef ARV2_TAILSTAT
+    if (lane == 0) {      // per warp: exit time; per CTA: how long this SM was busy
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(p.counters + 5, t); atomicMin(p.counters + 6, t);
+        if (threadIdx.x == 0) { atomicAdd(p.counters + 12, t - t_begin); atomicAdd(p.counters + 13, 1ull); atomicMin(p.counters + 14, t - t_begin); }
+    }
+#endif
 #ifdef ARV2_WAVESTAT
     if (lane == 0) {
         atomicAdd(p.counters + 8, st_tasks); atomicAdd(p.counters + 9, st_rays); atomicAdd(p.counters + 10, st_fail);
