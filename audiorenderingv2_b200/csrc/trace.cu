@@ -545,6 +545,15 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
 // counter is the pool of unstarted rays.  wave_cap bounds the paths alive per SM, which keeps a
 // ring slot from being rewritten before it was read.
 constexpr int kWaveThreads = 1024;
+#ifndef ARV2_DRAIN_SPREAD
+#define ARV2_DRAIN_SPREAD 1
+#endif
+#ifndef ARV2_DRAIN_BELOW
+#define ARV2_DRAIN_BELOW 2048        // paths alive per SM below which batches shrink (batch = 32 * alive / this)
+#endif
+#ifndef ARV2_DRAIN_MIN
+#define ARV2_DRAIN_MIN 1
+#endif
 
 template <int NB, int MODE>
 __global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams p)
@@ -602,8 +611,16 @@ __global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams
         }
         src = __shfl_sync(FULL, src, 0);
         if (src == -2) {
-            // shallowest queue with a full batch; a warp that found nothing last time also takes a partial one
-            const int need = idle == 0 ? 32 : 1;
+            // shallowest queue with a full batch; a warp that found nothing last time also takes a partial one.
+            // Once no ray is left to start and fewer paths are alive than the SM has lanes, the paths are spread over
+            // all warps (a segment takes a warp as long as its slowest lane: 8 paths per warp finish their segments
+            // sooner than 32, and the end of a launch is a chain of dependent segments)
+            int batch = 32;
+#if ARV2_DRAIN_SPREAD
+            if (lane == 0 && *v_done) { const int al = *v_alive; if (al < ARV2_DRAIN_BELOW) batch = max(ARV2_DRAIN_MIN, (al * 32 + ARV2_DRAIN_BELOW - 1) / ARV2_DRAIN_BELOW); }
+            batch = __shfl_sync(FULL, batch, 0);
+#endif
+            const int need = (idle == 0 && batch == 32) ? 32 : 1;
             int a0 = 0, a1 = 0;
             if (lane < nq) { const unsigned h = v_head[lane]; a0 = (int)(v_pub[lane] - h); }
             if (lane + 32 < nq) { const unsigned h = v_head[lane + 32]; a1 = (int)(v_pub[lane + 32] - h); }
@@ -616,7 +633,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams
                         const unsigned h = v_head[q];
                         const int av = (int)(v_pub[q] - h);
                         if (av < need) { WST(++st_fail;) break; }
-                        const int take = av < 32 ? av : 32;
+                        const int take = av < batch ? av : batch;
                         if (atomicCAS(&q_head[q], h, h + (unsigned)take) == h) { n = take; pos = h; src = q; break; }
                     }
                 }
