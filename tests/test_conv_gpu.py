@@ -172,6 +172,47 @@ def test_stream_ir_swap_and_reset():
     assert rel_l2(y3, oracle.direct_conv(x[: 5 * block], b)[: 5 * block]) <= TOL
 
 
+def test_stream_ir_swap_between_overlapped_blocks():
+    """An IR swap enqueued between two runs of overlapped device-resident blocks lands exactly at the block boundary
+    (the spectra kernel and the pointer copy are ordinary stream operations: the step after them waits for them, the
+    steps before them are complete): bit-identical to the serialised host-buffer path."""
+    import torch
+    block, ir_len, n_src, half = 512, 6000, 2, 24
+    rng = np.random.default_rng(21)
+    irs_a = [(decaying_ir(ir_len, 300 + i, 0.05, 48000), decaying_ir(ir_len, 310 + i, 0.04, 48000)) for i in range(n_src)]
+    irs_b = [(decaying_ir(ir_len, 320 + i, 0.05, 48000), decaying_ir(ir_len, 330 + i, 0.04, 48000)) for i in range(n_src)]
+    x = (0.1 * rng.standard_normal((2 * half, n_src, block))).astype(np.float32)
+    dev = torch.device("cuda", 0)
+
+    def run(device_path):
+        st = arv.ConvStream(n_src, block, ir_len)
+        for i, (a, b) in enumerate(irs_a):
+            st.set_ir(i, a, b)
+        if device_path:
+            dx = torch.from_numpy(x).to(dev)
+            dy = torch.empty(2 * half, n_src, 2, block, device=dev)
+            s = torch.cuda.Stream(device=dev)
+            torch.cuda.synchronize()
+            st.process_device_blocks(dx.data_ptr(), dy.data_ptr(), half, s.cuda_stream)
+            torch.cuda.synchronize()          # set_ir runs on the stream object's own CUDA stream
+            for i, (a, b) in enumerate(irs_b):
+                st.set_ir(i, a, b)
+            st.process_device_blocks(dx[half].data_ptr(), dy[half].data_ptr(), half, s.cuda_stream)
+            torch.cuda.synchronize()
+            out = dy.cpu().numpy()
+        else:
+            out = np.empty((2 * half, n_src, 2, block), np.float32)
+            for k in range(2 * half):
+                if k == half:
+                    for i, (a, b) in enumerate(irs_b):
+                        st.set_ir(i, a, b)
+                out[k] = st.process(x[k])
+        st.close()
+        return out
+
+    assert np.array_equal(run(True), run(False))
+
+
 def test_live_reference_semantics():
     """convoluteLiveInput (one 4096-sample callback, OR/AudioRenderer.cpp:593-661): the
     first ir_len output samples of the stream convolver x2 equal the reference's circular
