@@ -155,6 +155,15 @@ struct Traversal {
     __device__ __forceinline__ void step_inner(int* stack, const float4* __restrict__ nodes, const RayGrid& g)
     {
         const F8 na = ldg256_node(nodes + cur * 4), nb = ldg256_node(nodes + cur * 4 + 2);
+#ifdef ARV2_EXTRA_NODE_LOAD
+        {   // sensitivity probe: one more 256-bit load of the same line per visit (result unused but kept alive)
+            F8 nx;
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=f"(nx.lo.x), "=f"(nx.lo.y), "=f"(nx.lo.z), "=f"(nx.lo.w), "=f"(nx.hi.x), "=f"(nx.hi.y), "=f"(nx.hi.z), "=f"(nx.hi.w)
+                : "l"(nodes + cur * 4));
+            if (nx.lo.x == 1.2345e-30f) h.u = nx.hi.w;
+        }
+#endif
         const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
         const float c0lox = fmaf(n0.x, g.ix, -g.ox), c0hix = fmaf(n0.y, g.ix, -g.ox);
         const float c0loy = fmaf(n0.z, g.iy, -g.oy), c0hiy = fmaf(n0.w, g.iy, -g.oy);
