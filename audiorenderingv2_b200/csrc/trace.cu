@@ -553,7 +553,10 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
 // publish `pub`, claim `head` by CAS), only the 48 B path states go through L2.  The only global
 // counter is the pool of unstarted rays.  wave_cap bounds the paths alive per SM, which keeps a
 // ring slot from being rewritten before it was read.
-constexpr int kWaveThreads = 1024;
+#ifndef ARV2_WAVE_THREADS
+#define ARV2_WAVE_THREADS 1024       // occupancy probe: 512 / 768 / 896 (r07 section 14)
+#endif
+constexpr int kWaveThreads = ARV2_WAVE_THREADS;
 #ifndef ARV2_DRAIN_SPREAD
 #define ARV2_DRAIN_SPREAD 1
 #endif
