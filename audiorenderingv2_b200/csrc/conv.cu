@@ -11,8 +11,10 @@
 // a step is a 2*block-point Stockham FFT of the newest input block, a multiply-
 // accumulate of P spectra pairs, and one inverse FFT that yields both ears at once
 // (Z = Y_left + i*Y_right).  All of it is one launch of 8-CTA thread-block clusters:
-// each CTA accumulates 1/8 of the partitions, partial sums are reduce-scattered through
-// distributed shared memory, and the cluster's rank 0 runs the inverse FFT + overlap-add.
+// each CTA accumulates 1/8 of the partitions (a producer lane feeds a shared-memory ring with
+// bulk async copies, eight warps consume), the partial sums are reduced through distributed
+// shared memory, and the cluster's rank 0 runs the inverse FFT + overlap-add.  Consecutive
+// steps of a stream overlap through programmatic dependent launch (stream_step_kernel).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -117,8 +119,8 @@ __global__ void __launch_bounds__(kConvThreads) block_spectra_kernel(const float
 // ---- TMA (cp.async.bulk) staging --------------------------------------------------------
 // One CTA streams ~300 KB of spectra per step with only 8 warps, far too few loads in flight
 // for plain LDGs (r01 profile: 18.5 us per step, long_scoreboard 20 warps/issue).  The rows
-// of a partition (X, H_left, H_right: block*8 B each) are instead pulled into a 4-stage
-// shared-memory ring by bulk async copies that complete on an mbarrier; the threads only
+// of a partition (X: block*8 B, H_left + H_right: 2*block*8 B, adjacent) are instead pulled into a
+// shared-memory ring by bulk async copies that complete on an mbarrier; the consumer threads only
 // read shared memory.
 // The ring takes what two co-resident CTAs per SM leave (2 x 104 KB): with one CTA per SM the 8-CTA clusters of a
 // 16-source step no longer fit the GPCs in one wave (26 us per step instead of 16, r05), and a step could not share
@@ -137,7 +139,7 @@ __host__ __device__ constexpr int ring_stages(int block)
     return fit < 2 ? 2 : (fit > kStages ? kStages : fit);
 }
 constexpr int kConvStepThreads = kConvThreads + 32;     // stream / file kernels: kConvThreads consumers + one producer warp
-constexpr int kFftCostInPartitions = ARV2_CONV_FFTCOST;   // forward FFT of one block ~ streaming 8 partitions (clock64-measured)
+constexpr int kFftCostInPartitions = ARV2_CONV_FFTCOST;   // rank 0 also runs the forward FFT and takes this many partitions less per peer (8, 16, 24: same step time, r07)
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
