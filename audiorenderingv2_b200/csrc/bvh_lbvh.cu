@@ -247,20 +247,55 @@ __global__ void refit_kernel(const float* __restrict__ verts, const int* __restr
     }
 }
 
-// flags[i] = 1 when internal node i survives the collapse (covers more than 4 triangles)
-__global__ void emit_flag_kernel(const int* __restrict__ first, const int* __restrict__ last, int n, unsigned* __restrict__ flags)
+// Collapse of the radix tree into leaves of <= 4 triangles, with the SAH leaf test of the host builder
+// (host/bvh_sah.cpp): a subtree of <= 4 triangles stays an inner node only if splitting it as the radix tree does
+// is cheaper than testing its triangles, a node visit priced at one triangle test:
+//     1 + (A_left * N_left + A_right * N_right) / A  <  N.
+// want[i] = node i passes its own test (always, above 4 triangles).
+__global__ void emit_want_kernel(const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ first,
+                                 const int* __restrict__ last, const float* __restrict__ boxes, int n, unsigned char* __restrict__ want)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n - 1) flags[i] = (last[i] - first[i] + 1 > kMaxLeafTris) ? 1u : 0u;
+    if (i >= n - 1) return;
+    const int cnt = last[i] - first[i] + 1;
+    if (cnt > kMaxLeafTris) { want[i] = 1; return; }
+    auto half_area = [&](const float* b) {
+        const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    const int ch[2] = {left[i], right[i]};
+    float cost = 0.f;
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const int c = ch[w];
+        if (c & kLeafFlag) cost += half_area(boxes + 6 * (size_t)(n - 1 + (c & ~kLeafFlag)));
+        else cost += half_area(boxes + 6 * (size_t)c) * (float)(last[c] - first[c] + 1);
+    }
+    const float a = fmaxf(half_area(boxes + 6 * (size_t)i), 1e-30f);
+    want[i] = (1.0f + cost / a < (float)cnt) ? 1 : 0;
+}
+
+// flags[i] = 1 when internal node i survives the collapse: it passes its test and so does every ancestor inside
+// its <= 4-triangle subtree (at most two of them)
+__global__ void emit_flag_kernel(const int* __restrict__ first, const int* __restrict__ last, const int* __restrict__ parent,
+                                 const unsigned char* __restrict__ want, int n, unsigned* __restrict__ flags, unsigned char* __restrict__ keep)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    bool k = want[i] != 0;
+    int p = parent[i];
+    while (k && p >= 0 && last[p] - first[p] + 1 <= kMaxLeafTris) { k = want[p] != 0; p = parent[p]; }
+    keep[i] = k ? 1 : 0;
+    flags[i] = k ? 1u : 0u;
 }
 
 __global__ void emit_kernel(int n, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ first,
                             const int* __restrict__ last, const float* __restrict__ boxes, const unsigned* __restrict__ new_index,
-                            int node_offset, int slot_offset, float pad, float4* __restrict__ nodes)
+                            const unsigned char* __restrict__ keep, int node_offset, int slot_offset, float pad, float4* __restrict__ nodes)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    if (last[i] - first[i] + 1 <= kMaxLeafTris) return;
+    if (!keep[i]) return;
     int code[2];
     float bx[2][6];
     const int ch[2] = {left[i], right[i]};
@@ -274,7 +309,7 @@ __global__ void emit_kernel(int n, const int* __restrict__ left, const int* __re
             b = boxes + 6 * (size_t)(n - 1 + s);
         } else {
             const int cnt = last[c] - first[c] + 1;
-            code[w] = cnt > kMaxLeafTris ? (int)new_index[c] + node_offset : ~(((first[c] + slot_offset) << kLeafShift) | (cnt - 1));
+            code[w] = keep[c] ? (int)new_index[c] + node_offset : ~(((first[c] + slot_offset) << kLeafShift) | (cnt - 1));
             b = boxes + 6 * (size_t)c;
         }
 #pragma unroll
@@ -309,16 +344,19 @@ cudaError_t build_bvh_lbvh(const float* d_verts, const int* d_mats, int n, int i
 {
     if (n <= kMaxLeafTris) return cudaErrorInvalidValue;    // tiny inputs take the host builder
     unsigned *keys[2] = {nullptr, nullptr}, *counts = nullptr, *flags = nullptr;
+    unsigned char *want = nullptr, *keep = nullptr;
     int *vals[2] = {nullptr, nullptr}, *left = nullptr, *right = nullptr, *first = nullptr, *last = nullptr, *parent = nullptr, *visits = nullptr, *bounds = nullptr;
     float* boxes = nullptr;
     auto cleanup = [&]() {
         cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(counts); cudaFree(flags);
         cudaFree(left); cudaFree(right); cudaFree(first); cudaFree(last); cudaFree(parent); cudaFree(visits); cudaFree(bounds); cudaFree(boxes);
+        cudaFree(want); cudaFree(keep);
     };
     const int sort_blocks = (n + kSortTile - 1) / kSortTile;
     for (int k = 0; k < 2; ++k) { LB(cudaMalloc(&keys[k], (size_t)n * 4)); LB(cudaMalloc(&vals[k], (size_t)n * 4)); }
     LB(cudaMalloc(&counts, (size_t)kRadix * sort_blocks * 4));
     LB(cudaMalloc(&flags, (size_t)n * 4));
+    LB(cudaMalloc(&want, (size_t)n)); LB(cudaMalloc(&keep, (size_t)n));
     LB(cudaMalloc(&left, (size_t)n * 4)); LB(cudaMalloc(&right, (size_t)n * 4));
     LB(cudaMalloc(&first, (size_t)n * 4)); LB(cudaMalloc(&last, (size_t)n * 4));
     LB(cudaMalloc(&parent, (size_t)2 * n * 4)); LB(cudaMalloc(&visits, (size_t)n * 4));
@@ -339,7 +377,8 @@ cudaError_t build_bvh_lbvh(const float* d_verts, const int* d_mats, int n, int i
     hierarchy_kernel<<<G, T, 0, stream>>>(keys[cur], n, left, right, first, last, parent);
     LB(cudaMemsetAsync(visits, 0, (size_t)n * 4, stream));
     refit_kernel<<<G, T, 0, stream>>>(d_verts, vals[cur], n, left, right, parent, boxes, visits);
-    emit_flag_kernel<<<G, T, 0, stream>>>(first, last, n, flags);
+    emit_want_kernel<<<G, T, 0, stream>>>(left, right, first, last, boxes, n, want);
+    emit_flag_kernel<<<G, T, 0, stream>>>(first, last, parent, want, n, flags, keep);
     // exclusive scan of the n-1 flags -> dense node indices (root keeps index 0); the total lands in flags[n-1]
     LB(cudaMemsetAsync(flags + (n - 1), 0, 4, stream));
     scan_single_block_kernel<<<1, 1024, 0, stream>>>(flags, n);
@@ -359,7 +398,7 @@ cudaError_t build_bvh_lbvh(const float* d_verts, const int* d_mats, int n, int i
     const float pad = bvh_pad(ext);
     for (int a = 0; a < 3; ++a) { out->lo[a] -= pad; out->hi[a] += pad; }
     out->n_nodes = (int)h_nodes;
-    emit_kernel<<<G, T, 0, stream>>>(n, left, right, first, last, boxes, flags, node_offset, slot_offset, pad, d_nodes);
+    emit_kernel<<<G, T, 0, stream>>>(n, left, right, first, last, boxes, flags, keep, node_offset, slot_offset, pad, d_nodes);
     if (d_tris) tri_gather_kernel<<<G, T, 0, stream>>>(d_verts, d_mats, vals[cur], n, id_base, slot_offset, d_tris);
     if (d_order) LB(cudaMemcpyAsync(d_order, vals[cur], (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, stream));
     LB(cudaGetLastError());
