@@ -30,6 +30,14 @@ namespace arv2 {
 
 namespace {
 
+#ifdef ARV2_CONV_TIMING
+__device__ long long g_ct_marks[16];                 // clock64 marks of cluster 0, rank 0, thread 0 (debug build only)
+#define CT_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_ct_marks[i] = clock64(); } while (0)
+#else
+#define CT_MARK(i) do {} while (0)
+#endif
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -270,7 +278,9 @@ __device__ float2* reduce_and_inverse(cg::cluster_group& cluster, float2* part, 
             if (k < block) { part[k] = accL[i]; part[block + k] = accR[i]; }
         }
     }
+    CT_MARK(4);
     cluster.sync();
+    CT_MARK(5);
     {
         const int N = 2 * block;
         const int per = block / C;                       // block is a power of two >= 64, C = 8
@@ -295,9 +305,13 @@ __device__ float2* reduce_and_inverse(cg::cluster_group& cluster, float2* part, 
             }
         }
     }
+    CT_MARK(6);
     cluster.sync();
+    CT_MARK(7);
     if (rank != 0) return nullptr;
-    return fft_smem(bufa, bufb, 2 * block, tw, true);
+    float2* yy = fft_smem(bufa, bufb, 2 * block, tw, true);
+    CT_MARK(8);
+    return yy;
 }
 
 #ifdef ARV2_CONV_TIMING
@@ -368,6 +382,16 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
         hqL[i] = on ? H[(size_t)pq * 2 * block + k] : make_float2(0.f, 0.f);
         hqR[i] = on ? H[((size_t)pq * 2 + 1) * block + k] : make_float2(0.f, 0.f);
     }
+    if (rank == 0 && threadIdx.x < kConvThreads) {
+        // the newest input block and the tails are read after the wait; a prefetch into L2 (the point of coherence:
+        // a line fetched early still sees what the previous step or the producer of `in` writes later) takes part of
+        // their round trip off the chain that follows the wait
+        const char* pin = (const char*)(a.in + (size_t)src * block);
+        const char* ptl = (const char*)(a.tail + (size_t)src * 2 * block);
+        const int t128 = threadIdx.x * 128;
+        if (t128 < block * 4) prefetch_l2(pin + t128);
+        if (t128 < block * 8) prefetch_l2(ptl + t128);
+    }
     {
         int s0 = a.slot - first; if (s0 < 0) s0 += a.P;
         MacRows r;
@@ -392,9 +416,12 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
         // newest block: forward FFT, publish into the frequency-domain delay line, multiply by partition 0
         const float* in = a.in + (size_t)src * block;
         float2* slot = fdl + (size_t)a.slot * block;
+        CT_MARK(0);
         for (int t = threadIdx.x; t < N; t += blockDim.x) bufa[t] = make_float2(t < block ? in[t] : 0.f, 0.f);
         __syncthreads();
+        CT_MARK(1);
         const float2* F = fft_smem(bufa, bufb, N, stw, false);
+        CT_MARK(2);
         if (threadIdx.x < kConvThreads) {
 #pragma unroll
             for (int i = 0; i < BPT; ++i) {
@@ -407,6 +434,7 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
             }
         }
         __syncthreads();                                  // F (bufa or bufb) is read above; part and bufa are written next
+        CT_MARK(3);
     }
     if (rank == C - 1 && a.P > 1 && threadIdx.x < kConvThreads) {
         // the previous block: its spectrum was published by the step this one waited for
@@ -422,6 +450,10 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
     float2* y = reduce_and_inverse<BPT>(cluster, part, bufa, bufb, block, stw, accL, accR);
     CT_STAMP();
 #ifdef ARV2_CONV_TIMING
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.slot == 100)
+        printf("rank 0 cycles: in-load %lld fwd-fft %lld publish+p0 %lld | part-store %lld sync1 %lld dsmem-reduce %lld sync2 %lld inv-fft %lld\n",
+               g_ct_marks[1] - g_ct_marks[0], g_ct_marks[2] - g_ct_marks[1], g_ct_marks[3] - g_ct_marks[2], g_ct_marks[4] - g_ct_marks[3],
+               g_ct_marks[5] - g_ct_marks[4], g_ct_marks[6] - g_ct_marks[5], g_ct_marks[7] - g_ct_marks[6], g_ct_marks[8] - g_ct_marks[7]);
     if ((blockIdx.x == 0 || blockIdx.x == 7) && threadIdx.x == 0 && a.slot == 100)
         printf("cta %d: mac %llu wait %llu fft+p01 %llu reduce+ifft %llu ns (start %llu); mac %lld cycles, whole %lld cycles / %llu ns\n", blockIdx.x,
                ct_[1] - ct_[0], ct_[2] - ct_[1], ct_[3] - ct_[2], ct_[4] - ct_[3], ct_[0] % 1000000ull, cc_[1] - cc_[0], cc_[4] - cc_[0], ct_[4] - ct_[0]);
