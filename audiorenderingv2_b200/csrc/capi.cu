@@ -588,8 +588,8 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     }
 
     // scene BVH (built once; OR/AudioRenderer.cpp:95-218 rebuilds on every move): binary tree
-    // from the host binned-SAH builder or the GPU LBVH builder (K1), then quantised to the
-    // 32 B node the kernels traverse
+    // from the host binned-SAH builder or the GPU LBVH builder (K1), laid out as the 64 B
+    // nodes the kernels traverse (arv2_internal.h)
     const int64_t n_recv = c->n_left + c->n_right;
     c->n_recv_nodes = (int32_t)std::max<int64_t>(1, n_recv);
     const bool gpu_build = desc->bvh_builder == 1 && c->n_scene > kMaxLeafTris;
@@ -633,7 +633,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
         offset_nodes(scene2, 1, 0, nodes.data());
         const BvhNode top = make_top_node(c, false);
         CKC(cudaMemcpy(c->d_nodes, &top, sizeof top, cudaMemcpyHostToDevice));
-        CKC(cudaMemcpy(c->d_nodes + 4, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));      // quantises + uploads the scene nodes and the top node
+        CKC(cudaMemcpy(c->d_nodes + 4, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));      // scene nodes behind the top node
         std::vector<float> recs((size_t)c->n_scene * 16);
         for (int64_t s = 0; s < c->n_scene; ++s) {
             const int32_t src = scene2.order[s];
