@@ -65,6 +65,12 @@ inline float bvh_pad(float extent) { return extent * 1e-5f + 1e-6f; }
 //   (P1, id) (P2, material) (P3, Ng.x) (Ng.y, Ng.z, 0, 0)
 // material >= 0 = mesh index into keep[mesh][band], -1 / -2 = receiver ears; Ng = the unit
 // normal of the arithmetic contract, precomputed once on the host.
+// 4-wide node (experiment, host/bvh4.cpp): 128 B = 8 x float4: lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4],
+// child codes[4] (>= 0: kWideBit | wide node index, < 0: leaf as above), packed split axes (a0 | aL << 2 | aR << 4).
+struct Bvh4Node { float q[32]; };
+constexpr int32_t kWideBit = 1 << 29;
+// returns the depth of the wide tree (0 for an empty input)
+int collapse_bvh4(const HostBvh& bvh2, std::vector<Bvh4Node>* out);
 constexpr int kTraversalStack = 64;      // per-lane stack entries of the kernels (trace.cu)
 int bvh2_depth(const HostBvh& bvh2);
 void make_tri_record(const float* v9, int32_t id, int32_t material, float* out16);

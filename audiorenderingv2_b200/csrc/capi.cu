@@ -72,6 +72,8 @@ struct arv2_ctx {
 
     // device
     float4* d_nodes = nullptr; float4* d_tris = nullptr;
+    float4* d_nodes4 = nullptr;      // optional 4-wide scene tree (ARV2_BVH4=1, host/bvh4.cpp)
+    int32_t scene_root_code = 1;     // node the scene tree is entered at: 1 (binary) or kWideBit | 0
     float* d_keep = nullptr; float* d_scatter = nullptr;
     double* d_hist = nullptr; float* d_ir_l = nullptr; float* d_ir_r = nullptr;
     unsigned long long* d_counters = nullptr;
@@ -135,7 +137,7 @@ BvhNode make_top_node(const arv2_ctx* c, bool with_receiver)
     if (c->n_scene > 0) {
         n.q[0] = c->scene_bvh.lo[0]; n.q[1] = c->scene_bvh.hi[0]; n.q[2] = c->scene_bvh.lo[1]; n.q[3] = c->scene_bvh.hi[1];
         n.q[8] = c->scene_bvh.lo[2]; n.q[9] = c->scene_bvh.hi[2];
-        ch[0] = 1;
+        ch[0] = c->scene_root_code;
     }
     if (with_receiver) {
         n.q[4] = c->recv_bvh.lo[0]; n.q[5] = c->recv_bvh.hi[0]; n.q[6] = c->recv_bvh.lo[1]; n.q[7] = c->recv_bvh.hi[1];
@@ -219,7 +221,8 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     p->delay = (int)((double)c->desc.sample_rate * 0.00044);   // :125
     p->ir_len = c->ir_len; p->mono = c->mono;
     p->root = 0;
-    p->scene_root = c->n_scene > 0 ? 1 : -1;
+    p->scene_root = c->n_scene > 0 ? c->scene_root_code : -1;
+    p->nodes4 = c->d_nodes4;
     p->recv_root = c->has_receiver ? 1 + c->n_scene_nodes : -1;
     p->any_scatter = c->any_scatter;
     // a warp tops up its free lanes only once at least 9 are free, 16 rays per claim: the rays it
@@ -631,6 +634,14 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
         if (bvh2_depth(scene2) + 3 > kTraversalStack) { set_error("scene BVH too deep for the traversal stack"); return fail(ARV2_ERR_INVALID); }
         std::vector<BvhNode> nodes(scene2.nodes.size());
         offset_nodes(scene2, 1, 0, nodes.data());
+        if (getenv("ARV2_BVH4") && trace_supports_wide_nodes() && c->n_scene > kMaxLeafTris) {      // experiment (r07 section 18, slower): 4-wide scene tree next to the binary one
+            std::vector<Bvh4Node> wide;
+            const int depth4 = collapse_bvh4(scene2, &wide);
+            if (3 * depth4 + 3 > kTraversalStack) { set_error("wide scene BVH too deep for the traversal stack"); return fail(ARV2_ERR_INVALID); }
+            CKC(cudaMalloc(&c->d_nodes4, wide.size() * sizeof(Bvh4Node)));
+            CKC(cudaMemcpy(c->d_nodes4, wide.data(), wide.size() * sizeof(Bvh4Node), cudaMemcpyHostToDevice));
+            c->scene_root_code = kWideBit | 0;
+        }
         const BvhNode top = make_top_node(c, false);
         CKC(cudaMemcpy(c->d_nodes, &top, sizeof top, cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(c->d_nodes + 4, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));      // scene nodes behind the top node
@@ -671,7 +682,7 @@ void arv2_destroy(arv2_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_nodes); cudaFree(c->d_tris); cudaFree(c->d_keep); cudaFree(c->d_scatter);
+    cudaFree(c->d_nodes); cudaFree(c->d_nodes4); cudaFree(c->d_tris); cudaFree(c->d_keep); cudaFree(c->d_scatter);
     cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_ir_r); cudaFree(c->d_counters);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
     cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg); cudaFree(c->d_ray_order); cudaFree(c->d_wave_paths);

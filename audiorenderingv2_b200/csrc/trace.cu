@@ -65,6 +65,9 @@ __device__ __forceinline__ F8 ldg256(const float4* p)
 #ifndef ARV2_TRI_POLICY
 #define ARV2_TRI_POLICY 1
 #endif
+#ifndef ARV2_WIDE
+#define ARV2_WIDE 0                  // 1: the kernels also walk 4-wide nodes (TraceParams::nodes4, experiment r07 section 18)
+#endif
 #ifndef ARV2_NODE_POLICY
 #define ARV2_NODE_POLICY 0           // 1 = L1::evict_last
 #endif
@@ -129,12 +132,15 @@ __device__ __forceinline__ float safe_rcp(float d)
 // Per-segment ray constants of the slab test: t(plane) = plane * (1/dir) - org/dir.
 struct RayGrid {
     float ix, iy, iz, ox, oy, oz;
+    unsigned sgn;                    // bit a: the ray travels towards smaller coordinates along axis a (wide nodes)
     __device__ __forceinline__ void setup(F3 org, F3 dir)
     {
         ix = safe_rcp(dir.x); iy = safe_rcp(dir.y); iz = safe_rcp(dir.z);
         ox = org.x * ix; oy = org.y * iy; oz = org.z * iz;
+        sgn = (ix < 0.f ? 1u : 0u) | (iy < 0.f ? 2u : 0u) | (iz < 0.f ? 4u : 0u);
     }
 };
+constexpr int kNone = INT_MIN + 1;   // "this child is not entered" (never a node, a leaf code or the sentinel)
 
 // Traversal of one tree.  Closest hit = min (t, global triangle id) over all triangles
 // whose exact test accepts; the tree only prunes (boxes are padded and quantised outwards,
@@ -152,8 +158,48 @@ struct Traversal {
 
     // one binary node (64 B = two 256-bit loads, both child boxes in the parent): slab tests,
     // descend into the nearer hit child, push the other
-    __device__ __forceinline__ void step_inner(int* stack, const float4* __restrict__ nodes, const RayGrid& g)
+    // one 4-wide node (128 B = four 256-bit loads): four slab tests, the slots ordered front to back from the signs
+    // of the ray direction and the node's three split axes (no sorting network), the first entered child next, the
+    // others pushed
+    __device__ __forceinline__ void step_wide(int* stack, const float4* __restrict__ nodes4, const RayGrid& g)
     {
+        const float4* n = nodes4 + (size_t)(cur & (kWideBit - 1)) * 8;
+        const F8 X = ldg256_node(n), Y = ldg256_node(n + 2), Z = ldg256_node(n + 4), W = ldg256_node(n + 6);
+#define ARV2_SLAB(LOX, HIX, LOY, HIY, LOZ, HIZ, CODE, OUT)                                                                  \
+        {                                                                                                                  \
+            const float ax = fmaf(LOX, g.ix, -g.ox), bx = fmaf(HIX, g.ix, -g.ox);                                           \
+            const float ay = fmaf(LOY, g.iy, -g.oy), by = fmaf(HIY, g.iy, -g.oy);                                           \
+            const float az = fmaf(LOZ, g.iz, -g.oz), bz = fmaf(HIZ, g.iz, -g.oz);                                           \
+            const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));                       \
+            const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), h.t));                       \
+            OUT = tmin <= tmax ? __float_as_int(CODE) : kNone;                                                              \
+        }
+        int c0, c1, c2, c3;
+        ARV2_SLAB(X.lo.x, X.hi.x, Y.lo.x, Y.hi.x, Z.lo.x, Z.hi.x, W.lo.x, c0)
+        ARV2_SLAB(X.lo.y, X.hi.y, Y.lo.y, Y.hi.y, Z.lo.y, Z.hi.y, W.lo.y, c1)
+        ARV2_SLAB(X.lo.z, X.hi.z, Y.lo.z, Y.hi.z, Z.lo.z, Z.hi.z, W.lo.z, c2)
+        ARV2_SLAB(X.lo.w, X.hi.w, Y.lo.w, Y.hi.w, Z.lo.w, Z.hi.w, W.lo.w, c3)
+#undef ARV2_SLAB
+        const int axes = __float_as_int(W.hi.x);
+        const bool n0 = (g.sgn >> (axes & 3)) & 1u, nl = (g.sgn >> ((axes >> 2) & 3)) & 1u, nr = (g.sgn >> ((axes >> 4) & 3)) & 1u;
+        int t;
+        if (nl) { t = c0; c0 = c1; c1 = t; }
+        if (nr) { t = c2; c2 = c3; c3 = t; }
+        if (n0) { t = c0; c0 = c2; c2 = t; t = c1; c1 = c3; c3 = t; }
+        const bool v0 = c0 != kNone, v1 = c1 != kNone, v2 = c2 != kNone, v3 = c3 != kNone;
+        if (v3 && (v0 || v1 || v2)) stack[sp++] = c3;
+        if (v2 && (v0 || v1)) stack[sp++] = c2;
+        if (v1 && v0) stack[sp++] = c1;
+        int next = v0 ? c0 : (v1 ? c1 : (v2 ? c2 : c3));
+        if (!(v0 || v1 || v2 || v3)) next = stack[--sp];
+        cur = next;
+    }
+
+    __device__ __forceinline__ void step_inner(int* stack, const float4* __restrict__ nodes, const float4* __restrict__ nodes4, const RayGrid& g)
+    {
+#if ARV2_WIDE
+        if (cur & kWideBit) { step_wide(stack, nodes4, g); return; }
+#endif
         const F8 na = ldg256_node(nodes + cur * 4), nb = ldg256_node(nodes + cur * 4 + 2);
 #ifdef ARV2_EXTRA_NODE_LOAD
         {   // sensitivity probe: one more 256-bit load of the same line per visit (result unused but kept alive)
@@ -207,12 +253,12 @@ struct Traversal {
         cur = stack[--sp];
     }
 
-    __device__ __forceinline__ void walk(int* stack, const float4* __restrict__ nodes, const float4* __restrict__ tris, int root,
-                                         const RayGrid& g, F3 org, F3 dir)
+    __device__ __forceinline__ void walk(int* stack, const float4* __restrict__ nodes, const float4* __restrict__ nodes4,
+                                         const float4* __restrict__ tris, int root, const RayGrid& g, F3 org, F3 dir)
     {
         enter(stack, root);
         while (!finished()) {
-            while (at_inner()) step_inner(stack, nodes, g);
+            while (at_inner()) step_inner(stack, nodes, nodes4, g);
             if (finished()) break;
             step_leaf(stack, tris, org, dir);
         }
@@ -241,7 +287,7 @@ __device__ __forceinline__ void closest_hit(const TraceParams& p, int* stack, Tr
     if (root < 0) return;
     RayGrid g;
     g.setup(org, dir);
-    tr.walk(stack, p.nodes, p.tris, root, g, org, dir);
+    tr.walk(stack, p.nodes, p.nodes4, p.tris, root, g, org, dir);
 }
 
 // Warp-aggregated deposit into the fp64 histogram (OR/devicePrograms.cu:128-170).
@@ -764,7 +810,7 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
     Traversal tr;
     tr.reset(1e20f);
     RayGrid g;
-    g.ix = g.iy = g.iz = g.ox = g.oy = g.oz = 0.f;
+    g.ix = g.iy = g.iz = g.ox = g.oy = g.oz = 0.f; g.sgn = 0u;
     int stack[kStack];
 
     for (;;) {
@@ -811,7 +857,7 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
             // ---- phase I
 #pragma unroll 1
             for (int k = 0; k < ARV2_BURST; ++k)
-                if (tr.at_inner()) tr.step_inner(stack, p.nodes, g);
+                if (tr.at_inner()) tr.step_inner(stack, p.nodes, p.nodes4, g);
         }
     }
 #pragma unroll
@@ -1203,6 +1249,8 @@ cudaError_t launch_trace_t(const TraceParams& p, int sm_count, cudaStream_t stre
 }
 
 } // namespace
+
+bool trace_supports_wide_nodes() { return ARV2_WIDE != 0; }
 
 cudaError_t launch_trace(const TraceParams& p, int bands, int mode, int sm_count, cudaStream_t stream)
 {
