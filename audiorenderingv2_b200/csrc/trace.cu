@@ -68,6 +68,9 @@ __device__ __forceinline__ F8 ldg256(const float4* p)
 #ifndef ARV2_WIDE
 #define ARV2_WIDE 0                  // 1: the kernels also walk 4-wide nodes (TraceParams::nodes4, experiment r07 section 18)
 #endif
+#ifndef ARV2_SHADE_NOALLOC
+#define ARV2_SHADE_NOALLOC 1           // the shading re-read of the hit record does not allocate in L1 either (+1 %, r07 section 9)
+#endif
 #ifndef ARV2_NODE_POLICY
 #define ARV2_NODE_POLICY 0           // 1 = L1::evict_last
 #endif
@@ -382,7 +385,11 @@ __device__ __forceinline__ bool shade_segment(const TraceParams& p, Path<NB>& s,
         for (int b = 0; b < NB; ++b) p.pc_energy[ci * NB + b] = s.energy[b];
     }
     if (h.slot < 0) return true;                                                     // miss :186-190
+#if ARV2_SHADE_NOALLOC
+    const F8 A = ldg256_tri(p.tris + h.slot * 4), B = ldg256_tri(p.tris + h.slot * 4 + 2);
+#else
     const F8 A = ldg256(p.tris + h.slot * 4), B = ldg256(p.tris + h.slot * 4 + 2);
+#endif
     const F3 p1 = f3(A.lo.x, A.lo.y, A.lo.z), p2 = f3(A.hi.x, A.hi.y, A.hi.z), p3 = f3(B.lo.x, B.lo.y, B.lo.z);
     const int mat = __float_as_int(A.hi.w);
     const F3 pt = hit_point(p1, p2, p3, h.u, h.v);
