@@ -10,7 +10,8 @@ __device__ __forceinline__ F8 ld256(const void* p) {
         : "=f"(r.a[0]),"=f"(r.a[1]),"=f"(r.a[2]),"=f"(r.a[3]),"=f"(r.a[4]),"=f"(r.a[5]),"=f"(r.a[6]),"=f"(r.a[7]) : "l"(p));
     return r;
 }
-// MODE 0: 4 x LDG.128 per 64 B record, 1: 2 x LDG.256, 2: 1 x LDG.128 (16 B), 3: 1 x LDG.32, 4: 2 x LDG.128 (32 B), 5: 3 x LDG.128 (48 B)
+// MODE 0: 4 x LDG.128 per 64 B record, 1: 2 x LDG.256, 2: 1 x LDG.128 (16 B), 3: 1 x LDG.32, 4: 2 x LDG.128 (32 B), 5: 3 x LDG.128 (48 B),
+//      6: 1 x LDG.256 (32 B, one sector)
 template <int MODE>
 __global__ void gather(const float4* __restrict__ tab, unsigned n_rec, int iters, float* out)
 {
@@ -25,6 +26,7 @@ __global__ void gather(const float4* __restrict__ tab, unsigned n_rec, int iters
         if (MODE == 2) { float4 a = __ldg(p); acc += a.x + a.w; }
         if (MODE == 3) { acc += __ldg((const float*)p); }
         if (MODE == 4) { float4 a = __ldg(p), b = __ldg(p + 1); acc += a.x + b.y; }
+        if (MODE == 6) { F8 a = ld256(p); acc += a.a[0] + a.a[7]; }
         if (MODE == 5) { float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2); acc += a.x + b.y + c.z; }
         s += __float_as_uint(acc) & 1u;    // dependent chain like a traversal
     }
@@ -53,6 +55,7 @@ int main()
         run<0>("64B: 4 x LDG.128", tab, n_rec, out);
         run<1>("64B: 2 x LDG.256", tab, n_rec, out);
         run<5>("48B: 3 x LDG.128", tab, n_rec, out);
+        run<6>("32B: 1 x LDG.256", tab, n_rec, out);
         run<4>("32B: 2 x LDG.128", tab, n_rec, out);
         run<2>("16B: 1 x LDG.128", tab, n_rec, out);
         run<3>(" 4B: 1 x LDG.32", tab, n_rec, out);
