@@ -71,6 +71,10 @@ struct Bvh4Node { float q[32]; };
 constexpr int32_t kWideBit = 1 << 29;
 // returns the depth of the wide tree (0 for an empty input)
 int collapse_bvh4(const HostBvh& bvh2, std::vector<Bvh4Node>* out);
+// Quantised binary node (experiment, -DARV2_QNODES=1): 32 B = one sector.  w[3*child + axis] = lo | hi << 16, two 15-bit
+// planes on a scene-wide grid (plane = qc + (2^23 + 256 q) * qk); child codes as in Bvh4Node.  Node i mirrors binary node i.
+struct Q16Node { uint32_t w[6]; int32_t child[2]; };
+void quantise_bvh2(const HostBvh& bvh2, std::vector<Q16Node>* out, float qk[3], float qinvk[3], float qc[3]);
 constexpr int kTraversalStack = 64;      // per-lane stack entries of the kernels (trace.cu)
 int bvh2_depth(const HostBvh& bvh2);
 void make_tri_record(const float* v9, int32_t id, int32_t material, float* out16);

@@ -74,6 +74,7 @@ struct arv2_ctx {
     float4* d_nodes = nullptr; float4* d_tris = nullptr;
     float4* d_nodes4 = nullptr;      // optional 4-wide scene tree (ARV2_BVH4=1, host/bvh4.cpp)
     int32_t scene_root_code = 1;     // node the scene tree is entered at: 1 (binary) or kWideBit | 0
+    float qk[3] = {1.f, 1.f, 1.f}, qinvk[3] = {1.f, 1.f, 1.f}, qc[3] = {0.f, 0.f, 0.f};   // grid of the quantised nodes (any grid serves the float nodes)
     float* d_keep = nullptr; float* d_scatter = nullptr;
     double* d_hist = nullptr; float* d_ir_l = nullptr; float* d_ir_r = nullptr;
     unsigned long long* d_counters = nullptr;
@@ -223,6 +224,7 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     p->root = 0;
     p->scene_root = c->n_scene > 0 ? c->scene_root_code : -1;
     p->nodes4 = c->d_nodes4;
+    for (int a = 0; a < 3; ++a) { p->qk[a] = c->qk[a]; p->qinvk[a] = c->qinvk[a]; p->qc[a] = c->qc[a]; }
     p->recv_root = c->has_receiver ? 1 + c->n_scene_nodes : -1;
     p->any_scatter = c->any_scatter;
     // a warp tops up its free lanes only once at least 9 are free, 16 rays per claim: the rays it
@@ -634,12 +636,19 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
         if (bvh2_depth(scene2) + 3 > kTraversalStack) { set_error("scene BVH too deep for the traversal stack"); return fail(ARV2_ERR_INVALID); }
         std::vector<BvhNode> nodes(scene2.nodes.size());
         offset_nodes(scene2, 1, 0, nodes.data());
-        if (getenv("ARV2_BVH4") && trace_supports_wide_nodes() && c->n_scene > kMaxLeafTris) {      // experiment (r07 section 18, slower): 4-wide scene tree next to the binary one
+        if (getenv("ARV2_BVH4") && trace_supports_wide_nodes() == 1 && c->n_scene > kMaxLeafTris) {      // experiment (r07 section 18, slower): 4-wide scene tree next to the binary one
             std::vector<Bvh4Node> wide;
             const int depth4 = collapse_bvh4(scene2, &wide);
             if (3 * depth4 + 3 > kTraversalStack) { set_error("wide scene BVH too deep for the traversal stack"); return fail(ARV2_ERR_INVALID); }
             CKC(cudaMalloc(&c->d_nodes4, wide.size() * sizeof(Bvh4Node)));
             CKC(cudaMemcpy(c->d_nodes4, wide.data(), wide.size() * sizeof(Bvh4Node), cudaMemcpyHostToDevice));
+            c->scene_root_code = kWideBit | 0;
+        }
+        if (getenv("ARV2_QNODES") && trace_supports_wide_nodes() == 2 && c->n_scene > kMaxLeafTris) {    // experiment (r07 section 22): 32 B quantised scene nodes
+            std::vector<Q16Node> qn;
+            quantise_bvh2(scene2, &qn, c->qk, c->qinvk, c->qc);
+            CKC(cudaMalloc(&c->d_nodes4, qn.size() * sizeof(Q16Node)));
+            CKC(cudaMemcpy(c->d_nodes4, qn.data(), qn.size() * sizeof(Q16Node), cudaMemcpyHostToDevice));
             c->scene_root_code = kWideBit | 0;
         }
         const BvhNode top = make_top_node(c, false);

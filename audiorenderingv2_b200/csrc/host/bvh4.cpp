@@ -7,6 +7,7 @@
 // axis that separates the two children, half 1 = the other; inside a half the same rule), and the node records the
 // three axes: the kernel orders the slots front to back from the signs of the ray direction alone, without a
 // sorting network.  The tree only prunes; results cannot change.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -98,6 +99,44 @@ struct Collapser {
 };
 
 } // namespace
+
+// 15-bit planes, rounded outwards and widened by one more cell (the device decodes a plane with a few ulp of error
+// relative to the scene extent, far below a cell)
+void quantise_bvh2(const HostBvh& b, std::vector<Q16Node>* out, float qk[3], float qinvk[3], float qc[3])
+{
+    double glo[3], cell[3];
+    for (int a = 0; a < 3; ++a) {
+        const double ext = std::max((double)b.hi[a] - (double)b.lo[a], 1e-6);
+        glo[a] = b.lo[a];
+        cell[a] = ext / 32760.0;                       // a few cells of headroom at the top
+        qk[a] = (float)(cell[a] / 256.0);
+        qinvk[a] = (float)(256.0 / cell[a]);
+        qc[a] = (float)(glo[a] - 32768.0 * cell[a]);
+    }
+    out->assign(b.nodes.size(), Q16Node{});
+    for (size_t i = 0; i < b.nodes.size(); ++i) {
+        const BvhNode& n = b.nodes[i];
+        Q16Node q{};
+        int32_t ch[4];
+        std::memcpy(ch, &n.q[12], sizeof ch);
+        for (int w = 0; w < 2; ++w) {
+            const float lo[3] = {n.q[w * 4 + 0], n.q[w * 4 + 2], n.q[8 + w * 2]}, hi[3] = {n.q[w * 4 + 1], n.q[w * 4 + 3], n.q[8 + w * 2 + 1]};
+            for (int a = 0; a < 3; ++a) {
+                long ql, qh;
+                if (lo[0] == kEmptyBox) { ql = qh = 32767; }          // absent child: a point in the far corner of the grid
+                else {
+                    ql = (long)std::floor(((double)lo[a] - glo[a]) / cell[a]) - 1;
+                    qh = (long)std::ceil(((double)hi[a] - glo[a]) / cell[a]) + 1;
+                    ql = std::min<long>(32767, std::max<long>(0, ql));
+                    qh = std::min<long>(32767, std::max<long>(0, qh));
+                }
+                q.w[3 * w + a] = (uint32_t)ql | ((uint32_t)qh << 16);
+            }
+            q.child[w] = ch[w] >= 0 ? (kWideBit | ch[w]) : ch[w];
+        }
+        (*out)[i] = q;
+    }
+}
 
 int collapse_bvh4(const HostBvh& bvh2, std::vector<Bvh4Node>* out)
 {

@@ -133,16 +133,36 @@ __device__ __forceinline__ float safe_rcp(float d)
 }
 
 // Per-segment ray constants of the slab test: t(plane) = plane * (1/dir) - org/dir.
+#ifndef ARV2_QNODES
+#define ARV2_QNODES 0                // 1: the scene tree is walked through 32 B quantised nodes (TraceParams::nodes4, r07 section 22)
+#endif
+#if ARV2_QNODES
+// Quantised nodes: a plane is stored as a 15-bit integer q on a scene-wide grid; PRMT turns it into the float
+// f = 2^23 + 256 q without a conversion, and t(plane) = f * s + b with s = qk / dir and b = qc / dir - org / dir per axis.
+// The float nodes of the top level and of the receiver tree recover 1 / dir as s * qinvk.
+struct RayGrid {
+    float sx, sy, sz, bx, by, bz;
+    unsigned sgn;
+    __device__ __forceinline__ void setup(const TraceParams& p, F3 org, F3 dir)
+    {
+        const float ix = safe_rcp(dir.x), iy = safe_rcp(dir.y), iz = safe_rcp(dir.z);
+        sx = ix * p.qk[0]; sy = iy * p.qk[1]; sz = iz * p.qk[2];
+        bx = fmaf(p.qc[0], ix, -(org.x * ix)); by = fmaf(p.qc[1], iy, -(org.y * iy)); bz = fmaf(p.qc[2], iz, -(org.z * iz));
+        sgn = 0u;
+    }
+};
+#else
 struct RayGrid {
     float ix, iy, iz, ox, oy, oz;
     unsigned sgn;                    // bit a: the ray travels towards smaller coordinates along axis a (wide nodes)
-    __device__ __forceinline__ void setup(F3 org, F3 dir)
+    __device__ __forceinline__ void setup(const TraceParams&, F3 org, F3 dir)
     {
         ix = safe_rcp(dir.x); iy = safe_rcp(dir.y); iz = safe_rcp(dir.z);
         ox = org.x * ix; oy = org.y * iy; oz = org.z * iz;
         sgn = (ix < 0.f ? 1u : 0u) | (iy < 0.f ? 2u : 0u) | (iz < 0.f ? 4u : 0u);
     }
 };
+#endif
 constexpr int kNone = INT_MIN + 1;   // "this child is not entered" (never a node, a leaf code or the sentinel)
 
 // Traversal of one tree.  Closest hit = min (t, global triangle id) over all triangles
@@ -161,6 +181,7 @@ struct Traversal {
 
     // one binary node (64 B = two 256-bit loads, both child boxes in the parent): slab tests,
     // descend into the nearer hit child, push the other
+#if ARV2_WIDE
     // one 4-wide node (128 B = four 256-bit loads): four slab tests, the slots ordered front to back from the signs
     // of the ray direction and the node's three split axes (no sorting network), the first entered child next, the
     // others pushed
@@ -198,34 +219,18 @@ struct Traversal {
         cur = next;
     }
 
-    __device__ __forceinline__ void step_inner(int* stack, const float4* __restrict__ nodes, const float4* __restrict__ nodes4, const RayGrid& g)
+#endif
+
+    // the part of a binary node step that follows the twelve plane distances: slab intervals, descend into the nearer
+    // entered child, push the other, or pop
+    __device__ __forceinline__ void descend(int* stack, float c0lox, float c0hix, float c0loy, float c0hiy, float c0loz, float c0hiz,
+                                            float c1lox, float c1hix, float c1loy, float c1hiy, float c1loz, float c1hiz, int i0, int i1)
     {
-#if ARV2_WIDE
-        if (cur & kWideBit) { step_wide(stack, nodes4, g); return; }
-#endif
-        const F8 na = ldg256_node(nodes + cur * 4), nb = ldg256_node(nodes + cur * 4 + 2);
-#ifdef ARV2_EXTRA_NODE_LOAD
-        {   // sensitivity probe: one more 256-bit load of the same line per visit (result unused but kept alive)
-            F8 nx;
-            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                : "=f"(nx.lo.x), "=f"(nx.lo.y), "=f"(nx.lo.z), "=f"(nx.lo.w), "=f"(nx.hi.x), "=f"(nx.hi.y), "=f"(nx.hi.z), "=f"(nx.hi.w)
-                : "l"(nodes + cur * 4));
-            if (nx.lo.x == 1.2345e-30f) h.u = nx.hi.w;
-        }
-#endif
-        const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
-        const float c0lox = fmaf(n0.x, g.ix, -g.ox), c0hix = fmaf(n0.y, g.ix, -g.ox);
-        const float c0loy = fmaf(n0.z, g.iy, -g.oy), c0hiy = fmaf(n0.w, g.iy, -g.oy);
-        const float c0loz = fmaf(n2.x, g.iz, -g.oz), c0hiz = fmaf(n2.y, g.iz, -g.oz);
-        const float c1lox = fmaf(n1.x, g.ix, -g.ox), c1hix = fmaf(n1.y, g.ix, -g.ox);
-        const float c1loy = fmaf(n1.z, g.iy, -g.oy), c1hiy = fmaf(n1.w, g.iy, -g.oy);
-        const float c1loz = fmaf(n2.z, g.iz, -g.oz), c1hiz = fmaf(n2.w, g.iz, -g.oz);
         const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.f));
         const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
         const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.f));
         const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
         const bool go0 = c0min <= c0max, go1 = c1min <= c1max;
-        const int i0 = __float_as_int(n3.x), i1 = __float_as_int(n3.y);
         // predicated push / pop instead of a divergent if-else: lanes that pop and lanes that descend share the
         // same instructions
         const bool both = go0 && go1;
@@ -235,6 +240,48 @@ struct Traversal {
         sp += both ? 1 : 0;
         if (!(go0 || go1)) next = stack[--sp];
         cur = next;
+    }
+
+#if ARV2_QNODES
+    // one quantised binary node (32 B = one sector, one 256-bit load): six words of two 15-bit planes (lo | hi << 16) for
+    // (child, axis) = (0,x) (0,y) (0,z) (1,x) (1,y) (1,z), then the two child codes
+    __device__ __forceinline__ void step_q(int* stack, const float4* __restrict__ nodesq, const RayGrid& g)
+    {
+        const F8 n = ldg256_node(nodesq + (size_t)(cur & (kWideBit - 1)) * 2);
+#define ARV2_QLO(w) __uint_as_float(__byte_perm(__float_as_uint(w), 0x4B000000u, 0x7104))
+#define ARV2_QHI(w) __uint_as_float(__byte_perm(__float_as_uint(w), 0x4B000000u, 0x7324))
+        descend(stack,
+                fmaf(ARV2_QLO(n.lo.x), g.sx, g.bx), fmaf(ARV2_QHI(n.lo.x), g.sx, g.bx), fmaf(ARV2_QLO(n.lo.y), g.sy, g.by), fmaf(ARV2_QHI(n.lo.y), g.sy, g.by),
+                fmaf(ARV2_QLO(n.lo.z), g.sz, g.bz), fmaf(ARV2_QHI(n.lo.z), g.sz, g.bz),
+                fmaf(ARV2_QLO(n.lo.w), g.sx, g.bx), fmaf(ARV2_QHI(n.lo.w), g.sx, g.bx), fmaf(ARV2_QLO(n.hi.x), g.sy, g.by), fmaf(ARV2_QHI(n.hi.x), g.sy, g.by),
+                fmaf(ARV2_QLO(n.hi.y), g.sz, g.bz), fmaf(ARV2_QHI(n.hi.y), g.sz, g.bz), __float_as_int(n.hi.z), __float_as_int(n.hi.w));
+#undef ARV2_QLO
+#undef ARV2_QHI
+    }
+#endif
+
+    // one binary node (64 B = two 256-bit loads, both child boxes in the parent): slab tests,
+    // descend into the nearer hit child, push the other
+    __device__ __forceinline__ void step_inner(int* stack, const TraceParams& p, const RayGrid& g, F3 org)
+    {
+#if ARV2_WIDE
+        if (cur & kWideBit) { step_wide(stack, p.nodes4, g); return; }
+#endif
+#if ARV2_QNODES
+        if (cur & kWideBit) { step_q(stack, p.nodes4, g); return; }
+        const float ix = g.sx * p.qinvk[0], iy = g.sy * p.qinvk[1], iz = g.sz * p.qinvk[2];
+        const float ox = org.x * ix, oy = org.y * iy, oz = org.z * iz;
+#else
+        (void)org;
+        const float ix = g.ix, iy = g.iy, iz = g.iz, ox = g.ox, oy = g.oy, oz = g.oz;
+#endif
+        const float4* __restrict__ nodes = p.nodes;
+        const F8 na = ldg256_node(nodes + cur * 4), nb = ldg256_node(nodes + cur * 4 + 2);
+        const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
+        descend(stack,
+                fmaf(n0.x, ix, -ox), fmaf(n0.y, ix, -ox), fmaf(n0.z, iy, -oy), fmaf(n0.w, iy, -oy), fmaf(n2.x, iz, -oz), fmaf(n2.y, iz, -oz),
+                fmaf(n1.x, ix, -ox), fmaf(n1.y, ix, -ox), fmaf(n1.z, iy, -oy), fmaf(n1.w, iy, -oy), fmaf(n2.z, iz, -oz), fmaf(n2.w, iz, -oz),
+                __float_as_int(n3.x), __float_as_int(n3.y));
     }
 
     // one leaf: exact tests of its <= 8 triangles; the test needs the first 48 B of a record (P1, id, P2, material, P3)
@@ -256,12 +303,12 @@ struct Traversal {
         cur = stack[--sp];
     }
 
-    __device__ __forceinline__ void walk(int* stack, const float4* __restrict__ nodes, const float4* __restrict__ nodes4,
-                                         const float4* __restrict__ tris, int root, const RayGrid& g, F3 org, F3 dir)
+    __device__ __forceinline__ void walk(int* stack, const TraceParams& p, int root, const RayGrid& g, F3 org, F3 dir)
     {
+        const float4* __restrict__ tris = p.tris;
         enter(stack, root);
         while (!finished()) {
-            while (at_inner()) step_inner(stack, nodes, nodes4, g);
+            while (at_inner()) step_inner(stack, p, g, org);
             if (finished()) break;
             step_leaf(stack, tris, org, dir);
         }
@@ -289,8 +336,8 @@ __device__ __forceinline__ void closest_hit(const TraceParams& p, int* stack, Tr
     tr.reset(tmax);
     if (root < 0) return;
     RayGrid g;
-    g.setup(org, dir);
-    tr.walk(stack, p.nodes, p.nodes4, p.tris, root, g, org, dir);
+    g.setup(p, org, dir);
+    tr.walk(stack, p, root, g, org, dir);
 }
 
 // Warp-aggregated deposit into the fp64 histogram (OR/devicePrograms.cu:128-170).
@@ -817,7 +864,7 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
     Traversal tr;
     tr.reset(1e20f);
     RayGrid g;
-    g.ix = g.iy = g.iz = g.ox = g.oy = g.oz = 0.f; g.sgn = 0u;
+    g.setup(p, f3(0.f, 0.f, 0.f), f3(1.f, 1.f, 1.f));
     int stack[kStack];
 
     for (;;) {
@@ -853,7 +900,7 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
                 const bool to_recv = MODE == 0 && p.recv_root >= 0 && enters_receiver_ball(p, s.org, s.dir, 1e20f);
                 const int root = to_recv ? p.root : p.scene_root;
                 if (root >= 0) {
-                    g.setup(s.org, s.dir);
+                    g.setup(p, s.org, s.dir);
                     tr.enter(stack, root);
                 }
             }
@@ -864,7 +911,7 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
             // ---- phase I
 #pragma unroll 1
             for (int k = 0; k < ARV2_BURST; ++k)
-                if (tr.at_inner()) tr.step_inner(stack, p.nodes, p.nodes4, g);
+                if (tr.at_inner()) tr.step_inner(stack, p, g, s.org);
         }
     }
 #pragma unroll
@@ -1257,7 +1304,7 @@ cudaError_t launch_trace_t(const TraceParams& p, int sm_count, cudaStream_t stre
 
 } // namespace
 
-bool trace_supports_wide_nodes() { return ARV2_WIDE != 0; }
+int trace_supports_wide_nodes() { return ARV2_WIDE ? 1 : (ARV2_QNODES ? 2 : 0); }
 
 cudaError_t launch_trace(const TraceParams& p, int bands, int mode, int sm_count, cudaStream_t stream)
 {

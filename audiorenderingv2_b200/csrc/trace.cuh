@@ -10,7 +10,9 @@ namespace arv2 {
 // (the role of LaunchParams, OR/LaunchParams.h:20-43).
 struct TraceParams {
     const float4* nodes;        // 64 B binary nodes: [top][scene tree][receiver tree] (arv2_internal.h)
-    const float4* nodes4;       // optional 128 B 4-wide nodes of the scene tree (arv2_internal.h); node codes carry kWideBit
+    const float4* nodes4;       // optional alternative nodes of the scene tree (arv2_internal.h), their codes carry kWideBit:
+                                // 128 B 4-wide nodes (-DARV2_WIDE=1) or 32 B quantised binary nodes (-DARV2_QNODES=1)
+    float qk[3], qinvk[3], qc[3];   // quantised nodes: plane = qc + (2^23 + 256 q) * qk per axis, qinvk = 1 / qk
     const float4* tris;         // 64 B triangle records, leaf order
     const float* keep;          // [n_mats][bands]  1 - mat_absorption
     const float* scattering;    // [n_mats]
@@ -52,8 +54,9 @@ constexpr int kWaveQueues = 64;               // most per-depth queues of wave_k
 constexpr int kCounters = 16;                 // unsigned long long counters per context
 __host__ __device__ constexpr int cont_f4(int bands) { return bands == 1 ? 3 : 5; }   // float4 per queued path
 
-// true when the kernels were compiled with -DARV2_WIDE=1 and can walk TraceParams::nodes4
-bool trace_supports_wide_nodes();
+// 1 when the kernels were compiled with -DARV2_WIDE=1 (4-wide nodes in TraceParams::nodes4), 2 with -DARV2_QNODES=1
+// (quantised binary nodes there), 0 otherwise
+int trace_supports_wide_nodes();
 // mode 0: full trace (scene + receiver), deposits into hist.
 // mode 1: scene-only trace that fills the path cache (no deposits).
 cudaError_t launch_trace(const TraceParams& p, int bands, int mode, int sm_count, cudaStream_t stream);
