@@ -105,7 +105,7 @@ SYMBOLS = {
     "arv2_hist_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "arv2_last_segments": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "arv2_last_upload_bytes": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
-    "arv2_get_records": (C.c_int, [_vp, _ip, _ip, _fp, _ip]),
+    "arv2_get_records": (C.c_int, [_vp, C.c_int64, _ip, _ip, _fp, _ip, C.POINTER(C.c_int64)]),
     "arv2_write_ir_text": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
     "arv2_convolve_file": (C.c_int, [_vp, _fp, C.c_size_t, _fp, _fp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "arv2_stream_open": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
@@ -404,10 +404,13 @@ class AudioRenderer:
         return b.value
 
     def records(self, n_rays=None):
-        n = self.n_rays if n_rays is None else n_rays
+        """Per-ray records of the range last traced (sized by the library, not by the caller)."""
+        last = C.c_int64()
+        _check(lib().arv2_get_records(self._h, 0, None, None, None, None, C.byref(last)))
+        n = last.value if n_rays is None else min(int(n_rays), last.value)
         b = np.empty(n, np.int32); e = np.empty(n, np.int32); s = np.empty(n, np.int32)
         en = np.empty((n, self.bands), np.float32)
-        _check(lib().arv2_get_records(self._h, _i(b), _i(e), _f(en), _i(s)))
+        _check(lib().arv2_get_records(self._h, n, _i(b), _i(e), _f(en), _i(s), None))
         return dict(bin=b, ear=e, energy=en, nseg=s)
 
     def write_ir_text(self, left_path, right_path):

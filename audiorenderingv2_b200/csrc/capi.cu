@@ -88,7 +88,9 @@ struct arv2_ctx {
     // breadth-first tracer: per-depth path queues, grown on demand
     float4* d_wave_paths = nullptr; size_t wave_slots = 0;
     bool wave = true;
-    int* d_ray_order = nullptr; long long order_begin = -1, order_n = -1; unsigned long long order_seed = 0;
+    // direction-sorted start orders, cached per (seed, ray range); two slots so that alternating ranges do not re-sort
+    struct RayOrder { int* d = nullptr; long long begin = -1, n = -1; unsigned long long seed = 0, stamp = 0; } order[2];
+    unsigned long long order_clock = 0;
     bool coherent_order = true;
     // pinned staging for the receiver sub-tree
     float4* h_stage = nullptr; size_t stage_f4 = 0;
@@ -233,7 +235,9 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     p->refill_below = c->coherent_order ? 24 : 33;
     if (const char* e = getenv("ARV2_CHUNK")) p->chunk = atoi(e) > 0 ? atoi(e) : p->chunk;
     if (const char* e = getenv("ARV2_REFILL_BELOW")) p->refill_below = atoi(e) > 0 ? atoi(e) : p->refill_below;
-    p->ray_order = (c->d_ray_order && c->order_begin == ray_begin && c->order_n == n_rays && c->order_seed == c->seed) ? c->d_ray_order : nullptr;
+    p->ray_order = nullptr;
+    for (const auto& o : c->order)
+        if (o.d && o.begin == ray_begin && o.n == n_rays && o.seed == c->seed) p->ray_order = o.d;
 }
 
 // Coherent ray order: the rays of a launch are started in the order of their emission direction
@@ -243,8 +247,12 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
 int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
 {
     if (!c->coherent_order || n_rays <= 0 || n_rays > 0x7fffffffLL) return ARV2_OK;
-    if (c->d_ray_order && c->order_begin == ray_begin && c->order_n == n_rays && c->order_seed == c->seed) return ARV2_OK;
-    cudaFree(c->d_ray_order); c->d_ray_order = nullptr; c->order_n = -1;
+    arv2_ctx::RayOrder* slot = &c->order[0];
+    for (auto& o : c->order) {
+        if (o.d && o.begin == ray_begin && o.n == n_rays && o.seed == c->seed) { o.stamp = ++c->order_clock; return ARV2_OK; }
+        if (o.stamp < slot->stamp) slot = &o;                     // least recently used
+    }
+    cudaFree(slot->d); slot->d = nullptr; slot->n = -1;
     unsigned* keys[2] = {nullptr, nullptr};
     int* vals[2] = {nullptr, nullptr};
     auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); };
@@ -257,9 +265,25 @@ int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
     if (e == cudaSuccess) e = launch_direction_keys(c->seed, ray_begin, n_rays, keys[0], vals[0], c->stream);
     if (e == cudaSuccess) e = radix_sort_pairs(keys, vals, (int)n_rays, 8, 32, &res, c->stream);
     if (e != cudaSuccess) { cleanup(); set_error(std::string("ray order: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
-    c->d_ray_order = vals[res]; vals[res] = nullptr;
+    slot->d = vals[res]; vals[res] = nullptr;
     cleanup();
-    c->order_begin = ray_begin; c->order_n = n_rays; c->order_seed = c->seed;
+    slot->begin = ray_begin; slot->n = n_rays; slot->seed = c->seed; slot->stamp = ++c->order_clock;
+    return ARV2_OK;
+}
+
+// Per-ray records (desc.record_rays) are indexed by the ray's position in the launch: sized for the largest range
+// rendered so far, not for the whole seeded set (a 200k-ray shard of a 100M-ray set needs 200k entries).
+int ensure_records(arv2_ctx* c, long long n_rays)
+{
+    if (!c->desc.record_rays || n_rays <= c->rec_capacity) return ARV2_OK;
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
+    c->d_rec_bin = nullptr; c->d_rec_ear = nullptr; c->d_rec_nseg = nullptr; c->d_rec_energy = nullptr; c->rec_capacity = 0;
+    CK(cudaMalloc(&c->d_rec_bin, (size_t)n_rays * sizeof(int)));
+    CK(cudaMalloc(&c->d_rec_ear, (size_t)n_rays * sizeof(int)));
+    CK(cudaMalloc(&c->d_rec_nseg, (size_t)n_rays * sizeof(int)));
+    CK(cudaMalloc(&c->d_rec_energy, (size_t)n_rays * c->bands * sizeof(float)));
+    c->rec_capacity = n_rays;
     return ARV2_OK;
 }
 
@@ -274,9 +298,11 @@ int ensure_wave(arv2_ctx* c, TraceParams* p, long long n_rays)
     // +1.2 % over 4 at 8M rays on the SAH-leaf tree and halve the queue memory)
     int per = 8;
     if (const char* e = getenv("ARV2_WAVE_SEGMENTS")) per = atoi(e) > 0 ? atoi(e) : per;      // tuning aid
-    const unsigned mb = c->max_bounces < 1 ? 1u : c->max_bounces;
-    while ((mb + per - 1) / per > (unsigned)kWaveQueues) ++per;
+    // segments per task so that ceil(max_bounces / per) per-depth queues fit (64-bit: max_bounces may be UINT_MAX)
+    const long long mb = c->max_bounces < 1 ? 1LL : (long long)c->max_bounces;
+    per = (int)std::max<long long>(per, (mb + kWaveQueues - 1) / kWaveQueues);
     const int nq = (int)((mb + per - 1) / per);
+    if (nq < 1 || nq > kWaveQueues || mb > (1LL << 24)) return ARV2_OK;      // absurd depth: depth-first kernel
     long long cap = 2048;
     if (const char* e = getenv("ARV2_WAVE_CAP")) cap = atoll(e) >= 64 ? atoll(e) : cap;       // tuning aid
     const long long share = (2 * n_rays / c->sm_count + 95) / 32 * 32;
@@ -329,7 +355,7 @@ int ensure_cache(arv2_ctx* c)
 
 int finish_timed(arv2_ctx* c, double* ms)
 {
-    CK(cudaMemcpyAsync(c->h_counters, c->d_counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_counters, c->d_counters, kCounters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));                    // CUDA_SYNC_CHECK, OR/AudioRenderer.cpp:511
     c->last_segments = (long long)c->h_counters[1];
     if (c->h_counters[7] != 0) { set_error("trace: path-queue watchdog tripped (a warp waited too long for a queued path)"); return ARV2_ERR_CUDA; }
@@ -337,7 +363,7 @@ int finish_timed(arv2_ctx* c, double* ms)
                                                                 (double)c->h_counters[12] / (double)c->h_counters[13] * 1e-6, c->h_counters[13]);
     if (getenv("ARV2_TAILSTAT")) fprintf(stderr, "tail: pool empty -> first warp exit %.3f ms, -> last warp exit %.3f ms\n",
                                          ((double)c->h_counters[6] - (double)c->h_counters[4]) * 1e-6, ((double)c->h_counters[5] - (double)c->h_counters[4]) * 1e-6);
-    if (getenv("ARV2_PRINT_STATS")) { for (int i = 0; i < 16; ++i) fprintf(stderr, "%llu ", c->h_counters[i]); fprintf(stderr, "\n"); }
+    if (getenv("ARV2_PRINT_STATS")) { for (int i = 0; i < kCounters; ++i) fprintf(stderr, "%llu ", c->h_counters[i]); fprintf(stderr, "\n"); }
     if (ms) { float t = 0.f; CK(cudaEventElapsedTime(&t, c->ev0, c->ev1)); *ms = t; }
     return ARV2_OK;
 }
@@ -581,6 +607,14 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     std::vector<float> keep((size_t)std::max(1, n_mesh) * c->bands, 0.5f), scat((size_t)std::max(1, n_mesh), 0.f);
     for (int m = 0; m < n_mesh; ++m) {
         const std::string& name = c->scene.mesh_material[m];
+        // getMaterialAbsorption (OR/AudioRenderer.cpp:34-56) turns a mesh named receiver_left / receiver_right, or one
+        // with a negative configured absorption, into a receiver (mat_absorption < 0, OR/devicePrograms.cu:91).  Here
+        // receivers are their own object (arv2_receiver: refit per move, left out of the path cache), so such a scene
+        // is rejected instead of silently tracing those meshes as walls with 1 - a > 1.
+        if (material_absorption(name, desc->materials, desc->n_materials) < 0.f) {
+            set_error("scene mesh '" + name + "' resolves to a receiver material (name receiver_left/right or absorption < 0): pass receivers through arv2_receiver");
+            return fail(ARV2_ERR_INVALID);
+        }
         const arv2_material* hit = nullptr;
         for (int i = 0; i < desc->n_materials && !hit; ++i)
             if (desc->materials[i].name && name == desc->materials[i].name) hit = &desc->materials[i];
@@ -663,7 +697,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     }
     c->stage_f4 = 4 + 4 * (size_t)c->n_recv_nodes + 4 * (size_t)std::max<int64_t>(1, n_recv);
     CKC(cudaMallocHost(&c->h_stage, c->stage_f4 * sizeof(float4)));
-    CKC(cudaMallocHost(&c->h_counters, 16 * sizeof(unsigned long long)));
+    CKC(cudaMallocHost(&c->h_counters, kCounters * sizeof(unsigned long long)));
 
     // IR buffers (OR/AudioRenderer.cpp:81-85) and the fp64 accumulation histogram
     const size_t irn = (size_t)c->bands * c->ir_len;
@@ -674,13 +708,6 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     CKC(cudaMemset(c->d_ir_l, 0, irn * sizeof(float)));
     CKC(cudaMemset(c->d_ir_r, 0, irn * sizeof(float)));
     CKC(cudaMalloc(&c->d_counters, kCounters * sizeof(unsigned long long)));
-    if (desc->record_rays) {
-        c->rec_capacity = n_total;
-        CKC(cudaMalloc(&c->d_rec_bin, (size_t)n_total * sizeof(int)));
-        CKC(cudaMalloc(&c->d_rec_ear, (size_t)n_total * sizeof(int)));
-        CKC(cudaMalloc(&c->d_rec_nseg, (size_t)n_total * sizeof(int)));
-        CKC(cudaMalloc(&c->d_rec_energy, (size_t)n_total * c->bands * sizeof(float)));
-    }
 #undef CKC
     (void)rc;
     *out = c;
@@ -694,7 +721,7 @@ void arv2_destroy(arv2_ctx* c)
     cudaFree(c->d_nodes); cudaFree(c->d_nodes4); cudaFree(c->d_tris); cudaFree(c->d_keep); cudaFree(c->d_scatter);
     cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_ir_r); cudaFree(c->d_counters);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
-    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg); cudaFree(c->d_ray_order); cudaFree(c->d_wave_paths);
+    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg); cudaFree(c->order[0].d); cudaFree(c->order[1].d); cudaFree(c->d_wave_paths);
     cudaFree(c->d_rr_cand); cudaFree(c->d_rr_res); cudaFree(c->d_rr_energy); cudaFree(c->d_rr_first);
     cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -748,6 +775,8 @@ int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t ze
     if (getenv("ARV2_TAILSTAT")) { CK(cudaMemsetAsync(c->d_counters + 4, 0xFF, 8, c->stream)); CK(cudaMemsetAsync(c->d_counters + 6, 0xFF, 8, c->stream)); CK(cudaMemsetAsync(c->d_counters + 14, 0xFF, 8, c->stream)); }
     rc = ensure_ray_order(c, ray_begin, n_rays);
     if (rc != ARV2_OK) return rc;
+    rc = ensure_records(c, n_rays);
+    if (rc != ARV2_OK) return rc;
     TraceParams p;
     fill_params(c, &p, ray_begin, n_rays);
     rc = ensure_wave(c, &p, n_rays);
@@ -776,11 +805,13 @@ int arv2_rerender(arv2_ctx* c, double* ms)
     int rc = upload_receiver(c);
     if (rc != ARV2_OK) return rc;
     const size_t irn = (size_t)c->bands * c->ir_len;
+    rc = ensure_records(c, c->n_rays_total);
+    if (rc != ARV2_OK) return rc;
     TraceParams p;
     fill_params(c, &p, 0, c->n_rays_total);
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));
-    CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->d_counters, 0, kCounters * sizeof(unsigned long long), c->stream));
     const bool parallel = c->rr_cap > 0;
     if (parallel) {
         CK(cudaMemsetAsync(c->d_rr_first, 0x7f, (size_t)c->n_rays_total * sizeof(int), c->stream));     // kRrNoHit
@@ -796,7 +827,7 @@ int arv2_rerender(arv2_ctx* c, double* ms)
     // more ball-entering segments than the candidate list holds (a receiver that fills the room): the per-ray kernel
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));
-    CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->d_counters, 0, kCounters * sizeof(unsigned long long), c->stream));
     CK(launch_rerender(p, c->bands, c->sm_count, c->stream));
     CK(launch_finalize(c->d_hist, c->bands, c->ir_len, c->mono, c->d_ir_l, c->d_ir_r, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -900,13 +931,15 @@ int arv2_last_segments(arv2_ctx* c, int64_t* segs)
     return ARV2_OK;
 }
 
-int arv2_get_records(arv2_ctx* c, int32_t* bin, int32_t* ear, float* energy, int32_t* nseg)
+int arv2_get_records(arv2_ctx* c, int64_t capacity, int32_t* bin, int32_t* ear, float* energy, int32_t* nseg, int64_t* n_rays)
 {
-    REQUIRE(c, "null ctx");
+    REQUIRE(c && capacity >= 0, "arv2_get_records: bad argument");
     if (!c->desc.record_rays) { set_error("records not enabled (desc.record_rays)"); return ARV2_ERR_STATE; }
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    const size_t n = (size_t)c->last_range_rays;
+    if (n_rays) *n_rays = c->last_range_rays;
+    const size_t n = (size_t)std::min<long long>(capacity, std::min<long long>(c->last_range_rays, c->rec_capacity));
+    if (n == 0) return ARV2_OK;
     if (bin) CK(cudaMemcpy(bin, c->d_rec_bin, n * sizeof(int), cudaMemcpyDeviceToHost));
     if (ear) CK(cudaMemcpy(ear, c->d_rec_ear, n * sizeof(int), cudaMemcpyDeviceToHost));
     if (nseg) CK(cudaMemcpy(nseg, c->d_rec_nseg, n * sizeof(int), cudaMemcpyDeviceToHost));

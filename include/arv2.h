@@ -137,7 +137,7 @@ typedef struct {
     uint32_t ir_length_in_seconds;  /* AudioRenderer ctor arg                        */
     int32_t  sample_rate;           /* AudioRenderer ctor arg                        */
     int32_t  rays_x, rays_y, rays_z;/* rays_per_dimension: N = x*y*z                 */
-    int32_t  bands;                 /* 1 = reference; <= ARV2_MAX_BANDS              */
+    int32_t  bands;                 /* 1 = reference, or ARV2_MAX_BANDS (8)          */
     int32_t  device;                /* CUDA ordinal (reference hard-wires 0)         */
     int32_t  record_rays;           /* keep per-ray (bin, ear, energy, nseg) records */
     int32_t  path_cache;            /* keep receiver-independent paths for rerender  */
@@ -201,9 +201,12 @@ int arv2_hist_device(arv2_ctx* ctx, double** d_hist, int64_t* count);
 int arv2_last_upload_bytes(arv2_ctx* ctx, int64_t* bytes);
 /* Segments (closest-hit queries) traced by the last render on this context. */
 int arv2_last_segments(arv2_ctx* ctx, int64_t* segments);
-/* Per-ray records of the last render (desc.record_rays): arrays of n_rays entries
- * for the range last traced; energy is float[n_rays][bands]. Any may be NULL. */
-int arv2_get_records(arv2_ctx* ctx, int32_t* bin, int32_t* ear, float* energy, int32_t* nseg);
+/* Per-ray records of the last render (desc.record_rays), indexed by the ray's position in the
+ * range last traced: *n_rays (may be NULL) = rays in that range; at most `capacity` entries are
+ * copied into each non-NULL array (energy is float[capacity][bands]).  Call with capacity 0 to
+ * learn the size. */
+int arv2_get_records(arv2_ctx* ctx, int64_t capacity, int32_t* bin, int32_t* ear, float* energy,
+                     int32_t* nseg, int64_t* n_rays);
 /* Text dump of AudioRenderer::render's write_ir_to_file branch
  * (OR/AudioRenderer.cpp:525-567): one value per line, ostream default format. */
 int arv2_write_ir_text(arv2_ctx* ctx, const char* left_path, const char* right_path);

@@ -54,6 +54,7 @@ def lib():
         L.oracle_closest_hit.argtypes = [fp, C.c_int64, fp, fp, fp, fp, fp]
         L.oracle_finalize_ir.argtypes = [dp, C.c_int32, C.c_int32, C.c_int32, fp, fp]
         L.oracle_direct_conv.argtypes = [fp, C.c_int64, fp, C.c_int64, dp, C.c_int32]
+        L.oracle_direct_conv_window.argtypes = [fp, C.c_int64, fp, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int32]
         L.oracle_reference_file_conv.argtypes = [fp, C.c_int64, fp, C.c_int32, C.c_int32, dp, C.c_int32]
         L.oracle_reference_live_conv.argtypes = [dp, C.c_int64, fp, fp, C.c_int32, dp]
         L.oracle_upola.restype = C.c_double
@@ -146,6 +147,18 @@ class PreparedScene:
             raise RuntimeError("oracle_trace_scene failed")
         return int(segs), hist
 
+    def trace_records(self, p: Params, ray_begin, n_rays, n_threads=None):
+        """Same, with the per-ray records: dict(hist, bin, ear, energy, nseg, segments) like oracle.trace."""
+        n_rays = int(n_rays)
+        hist = np.zeros((2, p.bands, p.ir_length), np.float64)
+        rb = np.empty(n_rays, np.int32); re_ = np.empty(n_rays, np.int32); rn = np.empty(n_rays, np.int32)
+        en = np.empty((n_rays, p.bands), np.float32)
+        segs = lib().oracle_trace_scene(self._h, C.byref(p), int(ray_begin), n_rays, n_threads or (os.cpu_count() or 1),
+                                        _dp(hist), _ip(rb), _ip(re_), _fp(en), _ip(rn))
+        if segs < 0:
+            raise RuntimeError("oracle_trace_scene failed")
+        return dict(hist=hist, bin=rb, ear=re_, energy=en, nseg=rn, segments=int(segs))
+
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.oracle_scene_destroy(self._h)
@@ -188,6 +201,16 @@ def direct_conv(x, h, n_threads=None):
     h = np.ascontiguousarray(h, dtype=np.float32)
     y = np.zeros(len(x) + len(h) - 1, np.float64)
     lib().oracle_direct_conv(_fp(x), len(x), _fp(h), len(h), _dp(y), n_threads or (os.cpu_count() or 1))
+    return y
+
+
+def direct_conv_window(x, h, begin, count, n_threads=None):
+    """Outputs [begin, begin+count) of direct_conv(x, h)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    h = np.ascontiguousarray(h, dtype=np.float32)
+    assert 0 <= begin and count > 0 and begin + count <= len(x) + len(h) - 1
+    y = np.zeros(count, np.float64)
+    lib().oracle_direct_conv_window(_fp(x), len(x), _fp(h), len(h), int(begin), int(count), _dp(y), n_threads or (os.cpu_count() or 1))
     return y
 
 

@@ -104,6 +104,10 @@ void oracle_finalize_ir(const double* hist, int32_t bands, int32_t ir_length,
 void oracle_direct_conv(const float* x, int64_t n, const float* h, int64_t m,
                         double* y, int32_t n_threads);
 
+/* Outputs [begin, begin+count) of the same convolution (y has count entries). */
+void oracle_direct_conv_window(const float* x, int64_t n, const float* h, int64_t m,
+                               int64_t begin, int64_t count, double* y, int32_t n_threads);
+
 /* Reference file convolver, restated exactly (OR/kernels.cu:382-438 +
  * OR/AudioRenderer.cpp:702-711): whole seconds only, FFT size == ir_len
  * (circular), overlap-add at second*fs truncated to n, gain 1/(ir_len/2) after

@@ -86,6 +86,23 @@ void oracle_direct_conv(const float* x, int64_t n, const float* h, int64_t m, do
     });
 }
 
+/* outputs [begin, begin+count) of the same fp64 direct convolution (full-size checks: a few blocks of a long stream) */
+void oracle_direct_conv_window(const float* x, int64_t n, const float* h, int64_t m, int64_t begin, int64_t count,
+                               double* y, int32_t n_threads)
+{
+    const int64_t L = n + m - 1;
+    if (n <= 0 || m <= 0 || begin < 0 || count <= 0 || begin + count > L) return;
+    parallel_for(count, n_threads, [=](int64_t b, int64_t e) {
+        for (int64_t k = b; k < e; ++k) {
+            const int64_t i = begin + k;
+            const int64_t j0 = std::max<int64_t>(0, i - (n - 1)), j1 = std::min<int64_t>(m - 1, i);
+            double acc = 0.0;
+            for (int64_t j = j0; j <= j1; ++j) acc += (double)h[j] * (double)x[i - j];
+            y[k] = acc;
+        }
+    });
+}
+
 void oracle_reference_file_conv(const float* x, int64_t n, const float* h, int32_t ir_len, int32_t sample_rate,
                                 double* y, int32_t n_threads)
 {

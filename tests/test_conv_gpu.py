@@ -246,3 +246,34 @@ def test_live_callback_fills_ring_like_the_reference():
     got = ring.get_and_reset(2 * 4096)
     ref = oracle.reference_live_conv(x, hl, hr)[: 2 * 4096]
     assert rel_l2(got, ref) <= TOL
+
+
+def test_c5_sixteen_sources_two_second_ir():
+    """BASELINE configs[4] at its full size: 16 sources x 96 000-tap stereo IR (2 s @48 kHz, 188 partitions of 512),
+    400 blocks through arv2_stream_process_device_blocks, against the fp64 direct convolution: source 0 in full (both
+    ears, 204 800 outputs x 96 000 taps), every other source on windows that cover the first blocks, the first trip
+    around the frequency-domain delay line (blocks 186..190) and the last blocks."""
+    import torch
+    n_src, block, ir_len, nb, fs = 16, 512, 96000, 400, 48000
+    st = arv.ConvStream(n_src, block, ir_len)
+    irs = [(decaying_ir(ir_len, 200 + i, 1.2, fs), decaying_ir(ir_len, 300 + i, 1.2, fs)) for i in range(n_src)]
+    for i, (a, b) in enumerate(irs):
+        st.set_ir(i, a, b)
+    rng = np.random.default_rng(100)
+    x = (0.1 * rng.standard_normal((n_src, nb * block))).astype(np.float32)
+    xb = torch.from_numpy(np.ascontiguousarray(x.reshape(n_src, nb, block).transpose(1, 0, 2))).cuda()     # [nb][src][block]
+    yb = torch.empty(nb, n_src, 2, block, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        st.process_device_blocks(xb.data_ptr(), yb.data_ptr(), nb, s.cuda_stream)
+    torch.cuda.synchronize()
+    out = yb.cpu().numpy().transpose(1, 2, 0, 3).reshape(n_src, 2, nb * block)
+    for ear in (0, 1):
+        assert rel_l2(out[0, ear], oracle.direct_conv(x[0], irs[0][ear])[: nb * block]) <= TOL
+    windows = [(0, 2 * block), (186 * block, 5 * block), ((nb - 2) * block, 2 * block)]
+    for i in range(1, n_src):
+        for ear in (0, 1):
+            got = np.concatenate([out[i, ear, b:b + n] for b, n in windows])
+            ref = np.concatenate([oracle.direct_conv_window(x[i], irs[i][ear], b, n) for b, n in windows])
+            assert rel_l2(got, ref) <= TOL, (i, ear)
+    st.close()

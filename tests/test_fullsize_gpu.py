@@ -1,10 +1,15 @@
-"""BASELINE.json's full sizes (C2: 331k-triangle room, 1M rays, 50 bounces, 2 s IR @48 kHz), checked through
-properties that do not need the CPU oracle at that size: the result must not depend on how the rays are
-scheduled (breadth-first tasks vs depth-first lanes, direction-sorted vs id order, one launch vs ranges), and a
-re-render from the path cache must equal a fresh trace.  Plus the long-path case of the per-depth queues."""
+"""BASELINE.json's configurations at their real sizes against the CPU oracle (tolerances of north_star: >= 99.99 % of rays
+in the same receiver-hit bin, per-bin energy 1e-4, total energy 1e-5):
+  C2  conference-scale room, the full 1M rays, 50 bounces, 2 s IR @48 kHz        (restates OR/devicePrograms.cu:62-254)
+  C3  a 200k-ray shard deep inside the 100M-ray set (global ray ids beyond 2^26, ray_begin offsets)
+  C4  1M-triangle hall, 8 frequency bands, seed 11, 300k rays + interactive receiver moves through the path cache
+plus size-independent properties at the full size: the result must not depend on how the rays are scheduled
+(breadth-first tasks vs depth-first lanes, direction-sorted vs id order, one launch vs ranges), and a re-render from
+the path cache must equal a fresh trace.  Plus the long-path case of the per-depth queues."""
 import numpy as np
 import pytest
 
+import oracle
 from audiorenderingv2_b200 import scenes
 from util import Case, check_parity
 
@@ -25,6 +30,73 @@ def _render(r):
     r.render()
     l, rr = r.get_ir()
     return l, rr, r.last_segments(), r.records()
+
+
+def test_c2_fullsize_parity_with_oracle(c2):
+    """BASELINE configs[1] at its full size: every one of the 1M rays against the oracle."""
+    r = c2.renderer(record_rays=True)
+    l, rr, segs, rec = _render(r)
+    o = c2.oracle_run()
+    match = check_parity(rec, l, rr, segs, o, case=c2)
+    assert match >= 0.9999
+    # the rays both sides agree on took the same number of segments and arrive with the same energy
+    same = rec["bin"] == o["bin"]
+    assert np.mean(rec["nseg"][same] == o["nseg"][same]) >= 0.9999
+    assert abs(segs - o["segments"]) <= 1e-4 * o["segments"]
+    assert (rec["ear"] > 0).mean() > 0.2                  # a fifth of the rays reach the receiver in this room
+
+
+def test_c3_shard_deep_in_the_100m_ray_set(c2):
+    """BASELINE configs[2]: 100M rays sharded over ranks.  One 200k-ray shard that starts at ray 87 500 000 (the slice
+    of rank 7 of 8) against the oracle on the same global ray ids: directions are f(seed, global id), the energy per
+    ray is base_power / (1e8 * 4pi/3), records are indexed by the position in the shard."""
+    n_total, begin, n = 100_000_000, 87_500_000, 200_000
+    case = Case(c2.tv, c2.tm, c2.names, c2.receiver, rays=(n_total, 1, 1), emitter=c2.emitter, center=c2.center, yaw=c2.yaw,
+                materials=c2.materials, base_power=100.0, max_bounces=50, sample_rate=48000, ir_seconds=2, hrtf=0.9, seed=7)
+    r = case.renderer(record_rays=True)
+    r.render_range(begin, n, zero_first=True)
+    r.finalize()
+    l, rr = r.get_ir()
+    rec = r.records()
+    assert len(rec["bin"]) == n
+    o = oracle.trace(case.params(), case.flat(), ray_begin=begin, n_rays=n)
+    o["ir_left"], o["ir_right"] = oracle.finalize_ir(o["hist"])
+    assert check_parity(rec, l, rr, r.last_segments(), o, case=case) >= 0.9999
+    # and the shard is not the first 200k rays of the set
+    o0 = oracle.trace(case.params(), case.flat(), ray_begin=0, n_rays=2000)
+    assert not np.array_equal(o0["bin"], o["bin"][:2000])
+
+
+@pytest.fixture(scope="module")
+def c4(golden_receiver):
+    """BASELINE configs[3]: synthetic 1M-triangle hall, 8 frequency bands (bench.py --workload c4 geometry)."""
+    tv, tm, names = scenes.atrium()
+    return Case(tv, tm, names, golden_receiver, rays=(300_000, 1, 1), emitter=(8.0, 1.6, 15.0), center=(30.0, 1.6, 15.0),
+                yaw=30.0, materials=scenes.materials(bands=8), base_power=100.0, max_bounces=50, sample_rate=48000,
+                ir_seconds=2, hrtf=0.9, bands=8, seed=11)
+
+
+def test_c4_million_triangle_hall_parity_and_receiver_moves(c4):
+    assert len(c4.tv) >= 1_000_000
+    r = c4.renderer(record_rays=True, path_cache=True)
+    r.render()                                    # builds the path cache, then deposits from it
+    l, rr = r.get_ir()
+    o = c4.oracle_run()
+    assert check_parity(r.records(), l, rr, r.last_segments(), o, case=c4) >= 0.9999
+    assert l.shape == (8, 96000) and (l.sum(axis=1) > 0).all()
+    # a fresh full trace (no cache) gives the same IR
+    f = c4.renderer(record_rays=True)
+    f.render()
+    lf, rf = f.get_ir()
+    assert check_parity(f.records(), lf, rf, f.last_segments(), o, case=c4) >= 0.9999
+    # interactive receiver moves: re-deposit from the cached paths, against the oracle at the new position
+    for k in (1, 2):
+        pos, yaw = (30.0 - 1.5 * k, 1.6 + 0.2 * k, 15.0 + 2.0 * k), 30.0 + 40.0 * k
+        r.setSphereCenterInOptix(pos, yaw)
+        r.rerender()
+        l, rr = r.get_ir()
+        om = c4.oracle_run(center=pos, yaw=yaw)
+        assert check_parity(r.records(), l, rr, r.last_segments(), om, case=c4) >= 0.9999
 
 
 def test_c2_fullsize_result_is_scheduling_invariant(c2, monkeypatch):

@@ -262,3 +262,46 @@ def test_reference_live_conv_and_upola():
     ol, orr, _ = oracle.upola(xs, hl[:1000], hr[:1000], 64)
     ref = oracle.direct_conv(xs, hl[:1000])[: len(xs)]
     assert np.linalg.norm(ol - ref) / np.linalg.norm(ref) < 1e-5
+
+
+def test_direct_conv_window_equals_full():
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(3000).astype(np.float32); h = rng.standard_normal(700).astype(np.float32)
+    full = oracle.direct_conv(x, h)
+    for b, n in ((0, 10), (650, 900), (3000, 699), (len(full) - 1, 1)):
+        assert np.array_equal(oracle.direct_conv_window(x, h, b, n), full[b:b + n])
+
+
+def test_check_parity_per_bin_rule_with_flipped_rays(golden_scenes, golden_receiver):
+    """tests/util.check_parity on synthetic 'CUDA' outputs derived from the oracle's own records: two rays of 20 000
+    land in another bin (float intersection order) -> the per-bin 1e-4 check still runs on every bin and passes;
+    a 3e-4 error in one bin no flipped ray touches, or a third flipped ray, must fail."""
+    from util import Case, check_parity, deposit_hist
+    case = Case(golden_scenes["test_verts"], golden_scenes["test_mesh"], golden_scenes["test_names"], golden_receiver,
+                rays=(100, 100, 2), emitter=(0, 2, 0), center=(5, 2, 0), hrtf=0.7, sample_rate=16000, ir_seconds=1, seed=1)
+    o = case.oracle_run()
+    ir_len = o["ir_left"].shape[-1]
+    # the deposit rule in numpy reproduces the oracle's histogram from its per-ray records
+    everything = np.ones(len(o["bin"]), bool)
+    assert np.allclose(deposit_hist(case, o, everything, ir_len), o["hist"], rtol=1e-12, atol=0)
+    hits = np.nonzero((o["ear"] > 0) & (o["bin"] < ir_len - 40))[0]
+    assert len(hits) > 100
+
+    def fake(n_flip, spoil=None):
+        rec = {k: v.copy() for k, v in o.items() if k in ("bin", "ear", "energy", "nseg")}
+        for j in hits[:n_flip]:
+            rec["bin"][j] += 3
+        l, r = oracle.finalize_ir(deposit_hist(case, rec, everything, ir_len))
+        if spoil is not None:
+            l = l.copy(); l[0, spoil] *= np.float32(1.0 + 3e-4)
+        return rec, l, r
+
+    rec, l, r = fake(2)
+    assert check_parity(rec, l, r, o["segments"], o, case=case) == 1.0 - 2 / 20000
+    clean = [b for b in np.nonzero(o["ir_left"][0])[0] if b not in set(o["bin"][hits[:2]]) | set(o["bin"][hits[:2]] + 3)]
+    rec, l, r = fake(2, spoil=clean[0])
+    with pytest.raises(AssertionError):
+        check_parity(rec, l, r, o["segments"], o, case=case)
+    rec, l, r = fake(3)
+    with pytest.raises(AssertionError):
+        check_parity(rec, l, r, o["segments"], o, case=case)

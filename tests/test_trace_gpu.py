@@ -63,7 +63,7 @@ def test_torus_box(golden_scenes, golden_receiver):
                 rays=(50, 50, 8), emitter=(0, 5, 0), center=(6, 2, 3), max_bounces=30, sample_rate=48000, ir_seconds=1)
     r, rec, l, rr, segs, _ = run(case)
     o = case.oracle_run()
-    assert check_parity(rec, l, rr, segs, o) >= 0.9999
+    assert check_parity(rec, l, rr, segs, o, case=case) >= 0.9999
 
 
 def test_free_field_energy(golden_receiver):
@@ -95,7 +95,7 @@ def test_eight_bands_and_diffuse(golden_scenes, golden_receiver):
     case = c1(golden_scenes, golden_receiver, rays=(100, 100, 3), materials=mats, bands=bands, hrtf=0.7)
     r, rec, l, rr, segs, _ = run(case)
     o = case.oracle_run()
-    assert check_parity(rec, l, rr, segs, o) >= 0.9999
+    assert check_parity(rec, l, rr, segs, o, case=case) >= 0.9999
     assert l.shape == (bands, 16000)
 
 
@@ -152,7 +152,7 @@ def test_conference_scale_parity(golden_receiver):
                 yaw=30.0, materials=scenes.materials(), max_bounces=50, sample_rate=48000, ir_seconds=2, hrtf=0.9)
     r, rec, l, rr, segs, _ = run(case)
     o = case.oracle_run()
-    assert check_parity(rec, l, rr, segs, o) >= 0.9999
+    assert check_parity(rec, l, rr, segs, o, case=case) >= 0.9999
     assert rec["nseg"].mean() > 5
 
 
@@ -186,4 +186,4 @@ def test_gpu_lbvh_builder_gives_identical_hits(golden_scenes, golden_receiver):
             assert np.array_equal(reca[k], recb[k]), k
         assert np.allclose(la, lb, rtol=1e-6, atol=0) and np.allclose(rra, rrb, rtol=1e-6, atol=0)
     r, rec, l, rr, segs, _ = run(cases[0], bvh_builder=1)
-    assert check_parity(rec, l, rr, segs, cases[0].oracle_run()) >= 0.9999
+    assert check_parity(rec, l, rr, segs, cases[0].oracle_run(), case=cases[0]) >= 0.9999
