@@ -1,4 +1,10 @@
-"""CPU ORACLE -- test infrastructure, NOT the product.  PARITY UNPINNED.
+"""CPU ORACLE -- test infrastructure, NOT the product.
+
+Pin status: the tracer's per-ray arithmetic (raygen, closest-hit, miss: OR/devicePrograms.cu:62-254), loadOBJ and
+placeReceiver are PINNED against the reference's own sources compiled where they lie (oracle/ref.py, oracle/_ref/,
+tests/test_pin_cpu.py, tests/golden/ref_*).  PARITY UNPINNED for what the reference delegates to closed third-party
+code absent from /root/reference: OptiX 7.7's ray-triangle search, cuRAND's clock64()-seeded stream, cuFFT (the
+convolvers are anchored on the fp64 direct convolution instead).
 
 ctypes binding of oracle/_build/liboracle.so (oracle_trace.cpp, oracle_conv.cpp;
 build with `make -C oracle`).  Only tests/, __graft_entry__.smoke() and
@@ -27,8 +33,37 @@ class Params(C.Structure):
     ]
 
 
-def build():
-    subprocess.check_call(["make", "-C", _HERE, "-s"])
+def build(target=None):
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + ([target] if target else []))
+
+
+def _bind(path):
+    L = C.CDLL(path)
+    fp = C.POINTER(C.c_float)
+    dp = C.POINTER(C.c_double)
+    ip = C.POINTER(C.c_int32)
+    L.oracle_trace.restype = C.c_int64
+    L.oracle_trace.argtypes = [C.POINTER(Params), fp, ip, C.c_int64, fp, fp, C.c_int32, C.c_int64,
+                               C.c_int64, C.c_int32, C.c_int32, dp, ip, ip, fp, ip]
+    L.oracle_scene_create.restype = C.c_void_p
+    L.oracle_scene_create.argtypes = [fp, ip, C.c_int64, fp, fp, C.c_int32, C.c_int32, C.c_int32]
+    L.oracle_scene_destroy.argtypes = [C.c_void_p]
+    L.oracle_trace_scene.restype = C.c_int64
+    L.oracle_trace_scene.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_int64, C.c_int32, dp, ip, ip, fp, ip]
+    L.oracle_shade_hit.argtypes = [fp, C.c_float, fp, C.c_float, C.c_float, fp, C.c_int32, C.c_float, C.c_int32, C.c_int32,
+                                   fp, ip, ip, ip, ip, fp]
+    L.oracle_ray_direction.argtypes = [C.c_uint64, C.c_uint64, fp]
+    L.oracle_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.oracle_closest_hit.restype = C.c_int64
+    L.oracle_closest_hit.argtypes = [fp, C.c_int64, fp, fp, fp, fp, fp]
+    L.oracle_finalize_ir.argtypes = [dp, C.c_int32, C.c_int32, C.c_int32, fp, fp]
+    L.oracle_direct_conv.argtypes = [fp, C.c_int64, fp, C.c_int64, dp, C.c_int32]
+    L.oracle_direct_conv_window.argtypes = [fp, C.c_int64, fp, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int32]
+    L.oracle_reference_file_conv.argtypes = [fp, C.c_int64, fp, C.c_int32, C.c_int32, dp, C.c_int32]
+    L.oracle_reference_live_conv.argtypes = [dp, C.c_int64, fp, fp, C.c_int32, dp]
+    L.oracle_upola.restype = C.c_double
+    L.oracle_upola.argtypes = [fp, C.c_int64, C.c_int32, fp, fp, C.c_int32, fp, fp]
+    return L
 
 
 def lib():
@@ -36,30 +71,22 @@ def lib():
     if _lib is None:
         if not os.path.exists(_LIB_PATH):
             build()
-        L = C.CDLL(_LIB_PATH)
-        fp = C.POINTER(C.c_float)
-        dp = C.POINTER(C.c_double)
-        ip = C.POINTER(C.c_int32)
-        L.oracle_trace.restype = C.c_int64
-        L.oracle_trace.argtypes = [C.POINTER(Params), fp, ip, C.c_int64, fp, fp, C.c_int32, C.c_int64,
-                                   C.c_int64, C.c_int32, C.c_int32, dp, ip, ip, fp, ip]
-        L.oracle_scene_create.restype = C.c_void_p
-        L.oracle_scene_create.argtypes = [fp, ip, C.c_int64, fp, fp, C.c_int32, C.c_int32, C.c_int32]
-        L.oracle_scene_destroy.argtypes = [C.c_void_p]
-        L.oracle_trace_scene.restype = C.c_int64
-        L.oracle_trace_scene.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int64, C.c_int64, C.c_int32, dp, ip, ip, fp, ip]
-        L.oracle_ray_direction.argtypes = [C.c_uint64, C.c_uint64, fp]
-        L.oracle_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
-        L.oracle_closest_hit.restype = C.c_int64
-        L.oracle_closest_hit.argtypes = [fp, C.c_int64, fp, fp, fp, fp, fp]
-        L.oracle_finalize_ir.argtypes = [dp, C.c_int32, C.c_int32, C.c_int32, fp, fp]
-        L.oracle_direct_conv.argtypes = [fp, C.c_int64, fp, C.c_int64, dp, C.c_int32]
-        L.oracle_direct_conv_window.argtypes = [fp, C.c_int64, fp, C.c_int64, C.c_int64, C.c_int64, dp, C.c_int32]
-        L.oracle_reference_file_conv.argtypes = [fp, C.c_int64, fp, C.c_int32, C.c_int32, dp, C.c_int32]
-        L.oracle_reference_live_conv.argtypes = [dp, C.c_int64, fp, fp, C.c_int32, dp]
-        L.oracle_upola.restype = C.c_double
-        L.oracle_upola.argtypes = [fp, C.c_int64, C.c_int32, fp, fp, C.c_int32, fp, fp]
-        _lib = L
+        _lib = _bind(_LIB_PATH)
+    return _lib
+
+
+def load_variant(name):
+    """Another build of the same sources (oracle/Makefile): "native" = -O3 -march=native, compiled on this machine;
+    "o2" = -O2.  Returns the bound library without making it the default."""
+    build(name)
+    return _bind(os.path.join(_HERE, "_build", f"liboracle_{name}.so"))
+
+
+def use_native():
+    """Build the oracle with -O3 -march=native ON THIS MACHINE and make it the library every call below uses
+    (bench.py's CPU-baseline legs).  Results are bit-identical to the portable build."""
+    global _lib
+    _lib = load_variant("native")
     return _lib
 
 

@@ -8,12 +8,18 @@
  *   - convolution of the dry signal with that IR
  *                                      (OR/kernels.cu:345-438, OR/AudioRenderer.cpp:593-750)
  *
- * PARITY UNPINNED: the reference ships no tests / golden vectors for this path
- * and cannot be built here (Windows + OptiX 7.7 + cuFFT).  The arithmetic that
- * lives inside OptiX (ray/triangle test), cuRAND (seeded by clock64()) and
- * cuFFT is restated from its published contract.  The only reference-held data
- * the oracle is checked against are the weak fixtures OR/input.txt and
- * OR/output_ir.txt (see tests/golden/README.md).
+ * PIN STATUS.  Pinned against the reference's own sources, compiled where they lie by `make ref` (ref_scene_dump.cpp,
+ * ref_device_shim.cpp, ref_stubs/; vectors in tests/golden/ref_*, checks in tests/test_pin_cpu.py):
+ *   - loadOBJ + placeReceiver (OR/OptixModel.cpp:75-257): bit for bit;
+ *   - __closesthit__radiance (OR/devicePrograms.cu:62-180) on 10^5 hand-made hits: integer outcomes equal, floats to
+ *     fp32 rounding;
+ *   - the whole per-ray loop (__raygen__renderFrame + programs, :186-254) on BASELINE config 1 (100k rays) and the
+ *     closed box (20k rays, 50 bounces): every ray ends in the same ear and bin after the same number of segments.
+ * PARITY UNPINNED for the arithmetic that lives inside closed third-party code absent from /root/reference -- OptiX
+ * 7.7's ray/triangle test, cuRAND XORWOW seeded by clock64(), cuFFT (CUDA 12.1) -- restated from the published
+ * contract (one recipe, used on both sides of the pin); the reference ships no tests or golden vectors for them.
+ * The convolvers are anchored on the fp64 direct convolution and on OR/input.txt / OR/output_ir.txt
+ * (tests/golden/README.md).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library.  The product never links it.
@@ -78,6 +84,13 @@ int64_t oracle_trace_scene(void* scene, const oracle_params* p, int64_t ray_begi
                            int32_t n_threads, double* hist, int32_t* rec_bin, int32_t* rec_ear,
                            float* rec_energy, int32_t* rec_nseg);
 void oracle_scene_destroy(void* scene);
+
+/* One closest-hit invocation (single band), flat form shared with oracle/ref_device_shim.cpp (pin test against the
+ * reference's own __closesthit__radiance).  prd8 = {remaining_factor, distance, prev_position[3], direction[3]}
+ * in/out; *depth in/out; deposits (<= 2): ear 0 = ir_left, 1 = ir_right. */
+void oracle_shade_hit(const float* tri9, float mat_absorption, const float* ray_dir, float u, float v,
+                      const float* sphere_center, int32_t sample_rate, float hrtf, int32_t is_mono, int32_t ir_length,
+                      float* prd8, int32_t* depth, int32_t* n_dep, int32_t* dep_ear, int32_t* dep_idx, float* dep_val);
 
 /* Direction of ray `ray_id` of the seeded set (unit vector, float[3]). */
 void oracle_ray_direction(uint64_t seed, uint64_t ray_id, float* dir3);

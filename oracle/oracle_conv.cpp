@@ -1,6 +1,6 @@
 /*
  * oracle_conv.cpp -- CPU ORACLE (test infrastructure, not the product).
- * PARITY UNPINNED (see arv2_oracle.h).  Restates the reference convolvers:
+ * PARITY UNPINNED for the convolvers (cuFFT is closed; see arv2_oracle.h "PIN STATUS").  Restates:
  *   file mode  OR/kernels.cu:382-438 + OR/AudioRenderer.cpp:663-711
  *   live mode  OR/kernels.cu:345-377 + OR/AudioRenderer.cpp:593-661
  * cuFFT (third-party, CUDA 12.1, absent from /root/reference) is an

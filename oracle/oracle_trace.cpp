@@ -1,8 +1,8 @@
 /*
  * oracle_trace.cpp -- CPU ORACLE (test infrastructure, not the product).
- * PARITY UNPINNED (see arv2_oracle.h): restates OR/devicePrograms.cu:62-254.
+ * Restates OR/devicePrograms.cu:62-254; pinned against that file compiled where it lies (arv2_oracle.h "PIN STATUS").
  *
- * Build: g++ -O2 -std=c++17 -ffp-contract=off -mfma  (see oracle/Makefile).
+ * Build: g++ -O3 -std=c++17 -ffp-contract=off -mavx2 -mfma  (see oracle/Makefile; results do not depend on -O / -march).
  * Every a*b+c that must be fused is an explicit fmaf(); everything else is
  * evaluated exactly as written (no contraction), IEEE sqrt and division.
  *
@@ -347,103 +347,127 @@ struct Scene {
 
 struct RayOut { int32_t bin, ear, nseg; float energy[MAX_BANDS]; };
 
+/* struct PRD (OR/PRD.h:5-14) with one remaining_factor per band */
+struct PathState { float energy[MAX_BANDS]; float distance; V3 prev, dir; int depth; };
+
+/* the atomicAdds of one closest-hit invocation (<= 2 per band): ear 0 = ir_left, 1 = ir_right */
+struct Deposits { int n; int ear[2]; int idx[2]; float val[2][MAX_BANDS]; };
+
+/* __closesthit__radiance (devicePrograms.cu:62-180) for the hit (u, v) on triangle (p1, p2, p3) of material m
+ * (>= 0 wall, -1 receiver_left, -2 receiver_right): updates the path state, lists what it deposits.
+ * keep = the wall's absorption row [nb]; sc = its scattering coefficient (0 = reference). */
+inline void shade_hit(const oracle_params& P, int nb, V3 p1, V3 p2, V3 p3, int m, const float* absorption, float sc,
+                      uint64_t ray, V3 center, float u, float v, int delay, PathState& st, Deposits& dep)
+{
+    dep.n = 0;
+    /* :75-77  Ng = normalize(cross(P2-P1, P3-P1)) */
+    const V3 nc = cross(sub(p2, p1), sub(p3, p1));
+    const float ninv = 1.0f / sqrtf(dot(nc, nc));
+    const V3 ng{nc.x * ninv, nc.y * ninv, nc.z * ninv};
+    /* :81  P = (1-u-v)P1 + uP2 + vP3 */
+    const float w = (1.0f - u) - v;
+    const V3 pt{fmaf(v, p3.x, fmaf(u, p2.x, w * p1.x)), fmaf(v, p3.y, fmaf(u, p2.y, w * p1.y)),
+                fmaf(v, p3.z, fmaf(u, p2.z, w * p1.z))};
+    /* :83  distance += |P - prev_position| */
+    const V3 dp = sub(pt, st.prev);
+    st.distance = st.distance + sqrtf(dot(dp, dp));
+    const V3 dir = st.dir;
+
+    if (m < 0) {
+        /* :91-122  chord of the unit ball around sphere_center along the ray */
+        const float dinv = 1.0f / sqrtf(dot(dir, dir));
+        const V3 nd{dir.x * dinv, dir.y * dinv, dir.z * dinv};
+        const V3 oc = sub(pt, center);
+        const float a = dot(nd, nd);
+        const float bq = 2.0f * dot(oc, nd);
+        const float c = dot(oc, oc) - 1.0f;
+        const float disc = fmaf(bq, bq, -((4.0f * a) * c));
+        float wgt = 0.f;
+        if (disc > 0.f) {
+            const float sq = sqrtf(disc);
+            const float t1 = (-bq - sq) / (2.0f * a);
+            const float t2 = (-bq + sq) / (2.0f * a);
+            const V3 i1{fmaf(t1, nd.x, pt.x), fmaf(t1, nd.y, pt.y), fmaf(t1, nd.z, pt.z)};
+            const V3 i2{fmaf(t2, nd.x, pt.x), fmaf(t2, nd.y, pt.y), fmaf(t2, nd.z, pt.z)};
+            const V3 df = sub(i1, i2);
+            wgt = sqrtf(dot(df, df));
+        }
+        for (int b = 0; b < nb; ++b) st.energy[b] = st.energy[b] * wgt;
+        /* :124-170  deposit */
+        const float elapsed = st.distance / 343.0f;
+        const int bin = (int)roundf(elapsed * (float)P.sample_rate);
+        const float cross_gain = 1.0f - P.hrtf_absorption_rate;
+        const int primary = (m == -1) ? 0 : 1;
+        dep.idx[0] = bin; dep.ear[0] = primary;          /* recorded even when bin >= ir_length (not deposited) */
+        for (int b = 0; b < nb; ++b) dep.val[0][b] = st.energy[b];
+        if (bin < P.ir_length) {
+            dep.n = 1;
+            if (!P.is_mono) {
+                dep.n = 2;
+                dep.ear[1] = 1 - primary;
+                dep.idx[1] = (bin + delay < P.ir_length) ? bin + delay : bin;
+                for (int b = 0; b < nb; ++b) dep.val[1][b] = st.energy[b] * cross_gain;
+            }
+        }
+        st.depth = -1;                                   /* :147,169 */
+        return;
+    }
+    /* :171-176  wall */
+    bool diffuse = false;
+    uint32_t r[4];
+    if (sc > 0.f) {
+        philox(P.seed, ray, (uint32_t)st.depth, 1u, r);
+        diffuse = (float)(r[0] >> 8) * 0x1p-24f < sc;
+    }
+    if (diffuse) {
+        st.dir = lambert_direction(r, dir, ng);
+    } else {
+        const float k = 2.0f * dot(dir, ng);
+        st.dir = {fmaf(-k, ng.x, dir.x), fmaf(-k, ng.y, dir.y), fmaf(-k, ng.z, dir.z)};
+    }
+    for (int b = 0; b < nb; ++b) st.energy[b] = st.energy[b] * (1.0f - absorption[b]);
+    st.depth++;
+    /* :179  prev_position = P + 1e-3 * direction */
+    st.prev = {fmaf(1e-3f, st.dir.x, pt.x), fmaf(1e-3f, st.dir.y, pt.y), fmaf(1e-3f, st.dir.z, pt.z)};
+}
+
 /* One thread of __raygen__renderFrame + its closest-hit/miss programs. */
 void trace_ray(const oracle_params& P, const Scene& S, uint64_t ray, float energy0, float dist_thr, int delay,
                double* hist, RayOut& out)
 {
     const int nb = P.bands;
-    float energy[MAX_BANDS];
-    for (int b = 0; b < nb; ++b) energy[b] = energy0;           /* devicePrograms.cu:208 */
-    float distance = 0.f;                                        /* :209 */
-    V3 prev{P.emitter[0], P.emitter[1], P.emitter[2]};           /* :210 */
-    int depth = 0;                                               /* :211 */
+    PathState st;
+    for (int b = 0; b < nb; ++b) st.energy[b] = energy0;        /* devicePrograms.cu:208 */
+    st.distance = 0.f;                                           /* :209 */
+    st.prev = {P.emitter[0], P.emitter[1], P.emitter[2]};        /* :210 */
+    st.depth = 0;                                                /* :211 */
     const V3 center{P.sphere_center[0], P.sphere_center[1], P.sphere_center[2]};
-    V3 dir = emit_direction(P.seed, ray);                        /* :216-224 */
+    st.dir = emit_direction(P.seed, ray);                        /* :216-224 */
     out.bin = -1; out.ear = 0; out.nseg = 0;
     for (int b = 0; b < nb; ++b) out.energy[b] = 0.f;
-    if (!(dir.x != 0.f || dir.y != 0.f || dir.z != 0.f)) return; /* :230 */
+    if (!(st.dir.x != 0.f || st.dir.y != 0.f || st.dir.z != 0.f)) return; /* :230 */
 
     for (;;) {
-        float emax = energy[0];
-        for (int b = 1; b < nb; ++b) emax = std::max(emax, energy[b]);
-        if (!(distance < dist_thr && emax > P.energy_thres && depth >= 0 && (uint32_t)depth < P.max_bounces))
+        float emax = st.energy[0];
+        for (int b = 1; b < nb; ++b) emax = std::max(emax, st.energy[b]);
+        if (!(st.distance < dist_thr && emax > P.energy_thres && st.depth >= 0 && (uint32_t)st.depth < P.max_bounces))
             break;                                               /* :233-236 */
         out.nseg++;
-        const Hit h = S.use_bvh ? closest_bvh(S.bvh, S.tris, prev, dir) : closest_brute(S.tris, prev, dir);
-        if (h.id < 0) { depth = -1; break; }                     /* __miss__radiance :186-190 */
-
-        const Tri& tr = S.tris[h.id];
-        const V3 p1 = tr.p1, p2 = S.p2[h.id], p3 = S.p3[h.id];
-        /* :75-77  Ng = normalize(cross(P2-P1, P3-P1)) */
-        const V3 nc = cross(tr.e1, tr.e2);
-        const float ninv = 1.0f / sqrtf(dot(nc, nc));
-        const V3 ng{nc.x * ninv, nc.y * ninv, nc.z * ninv};
-        /* :81  P = (1-u-v)P1 + uP2 + vP3 */
-        const float w = (1.0f - h.u) - h.v;
-        const V3 pt{fmaf(h.v, p3.x, fmaf(h.u, p2.x, w * p1.x)), fmaf(h.v, p3.y, fmaf(h.u, p2.y, w * p1.y)),
-                    fmaf(h.v, p3.z, fmaf(h.u, p2.z, w * p1.z))};
-        /* :83  distance += |P - prev_position| */
-        const V3 dp = sub(pt, prev);
-        distance = distance + sqrtf(dot(dp, dp));
-
+        const Hit h = S.use_bvh ? closest_bvh(S.bvh, S.tris, st.prev, st.dir) : closest_brute(S.tris, st.prev, st.dir);
+        if (h.id < 0) { st.depth = -1; break; }                  /* __miss__radiance :186-190 */
         const int m = S.mat[h.id];
+        Deposits dep;
+        shade_hit(P, nb, S.tris[h.id].p1, S.p2[h.id], S.p3[h.id], m, m >= 0 ? S.absorption + (size_t)m * nb : nullptr,
+                  (m >= 0 && S.scattering) ? S.scattering[m] : 0.f, ray, center, h.u, h.v, delay, st, dep);
         if (m < 0) {
-            /* :91-122  chord of the unit ball around sphere_center along the ray */
-            const float dinv = 1.0f / sqrtf(dot(dir, dir));
-            const V3 nd{dir.x * dinv, dir.y * dinv, dir.z * dinv};
-            const V3 oc = sub(pt, center);
-            const float a = dot(nd, nd);
-            const float bq = 2.0f * dot(oc, nd);
-            const float c = dot(oc, oc) - 1.0f;
-            const float disc = fmaf(bq, bq, -((4.0f * a) * c));
-            float wgt = 0.f;
-            if (disc > 0.f) {
-                const float sq = sqrtf(disc);
-                const float t1 = (-bq - sq) / (2.0f * a);
-                const float t2 = (-bq + sq) / (2.0f * a);
-                const V3 i1{fmaf(t1, nd.x, pt.x), fmaf(t1, nd.y, pt.y), fmaf(t1, nd.z, pt.z)};
-                const V3 i2{fmaf(t2, nd.x, pt.x), fmaf(t2, nd.y, pt.y), fmaf(t2, nd.z, pt.z)};
-                const V3 df = sub(i1, i2);
-                wgt = sqrtf(dot(df, df));
-            }
-            for (int b = 0; b < nb; ++b) energy[b] = energy[b] * wgt;
-            /* :124-170  deposit */
-            const float elapsed = distance / 343.0f;
-            const int bin = (int)roundf(elapsed * (float)P.sample_rate);
-            const float cross_gain = 1.0f - P.hrtf_absorption_rate;
-            const int primary = (m == -1) ? 0 : 1;
-            out.bin = bin; out.ear = (m == -1) ? 1 : 2;
-            for (int b = 0; b < nb; ++b) out.energy[b] = energy[b];
-            if (bin >= 0 && bin < P.ir_length && hist) {
-                for (int b = 0; b < nb; ++b) {
-                    hist[((size_t)primary * nb + b) * P.ir_length + bin] += (double)energy[b];
-                    if (!P.is_mono) {
-                        const int ob = (bin + delay < P.ir_length) ? bin + delay : bin;
-                        hist[((size_t)(1 - primary) * nb + b) * P.ir_length + ob] += (double)(energy[b] * cross_gain);
-                    }
-                }
-            }
-            depth = -1;                                          /* :147,169 */
+            out.bin = dep.idx[0]; out.ear = (m == -1) ? 1 : 2;
+            for (int b = 0; b < nb; ++b) out.energy[b] = dep.val[0][b];
+            if (hist && out.bin >= 0)
+                for (int d = 0; d < dep.n; ++d)
+                    for (int b = 0; b < nb; ++b)
+                        hist[((size_t)dep.ear[d] * nb + b) * P.ir_length + dep.idx[d]] += (double)dep.val[d][b];
             break;
         }
-        /* :171-176  wall */
-        const float sc = S.scattering ? S.scattering[m] : 0.f;
-        bool diffuse = false;
-        uint32_t r[4];
-        if (sc > 0.f) {
-            philox(P.seed, ray, (uint32_t)depth, 1u, r);
-            diffuse = (float)(r[0] >> 8) * 0x1p-24f < sc;
-        }
-        if (diffuse) {
-            dir = lambert_direction(r, dir, ng);
-        } else {
-            const float k = 2.0f * dot(dir, ng);
-            dir = {fmaf(-k, ng.x, dir.x), fmaf(-k, ng.y, dir.y), fmaf(-k, ng.z, dir.z)};
-        }
-        for (int b = 0; b < nb; ++b) energy[b] = energy[b] * (1.0f - S.absorption[(size_t)m * nb + b]);
-        depth++;
-        /* :179  prev_position = P + 1e-3 * direction */
-        prev = {fmaf(1e-3f, dir.x, pt.x), fmaf(1e-3f, dir.y, pt.y), fmaf(1e-3f, dir.z, pt.z)};
     }
 }
 
@@ -551,6 +575,34 @@ int64_t oracle_trace(const oracle_params* p, const float* tri_verts, const int32
     const int64_t r = oracle_trace_scene(h, p, ray_begin, n_rays, n_threads, hist, rec_bin, rec_ear, rec_energy, rec_nseg);
     oracle_scene_destroy(h);
     return r;
+}
+
+/* One closest-hit invocation (single band) in the flat form oracle/ref_device_shim.cpp's ref_closesthit uses, for
+ * the pin test against the reference's own __closesthit__radiance: prd8 = {remaining_factor, distance,
+ * prev_position[3], direction[3]} in/out. */
+void oracle_shade_hit(const float* tri9, float mat_absorption, const float* ray_dir, float u, float v,
+                      const float* sphere_center, int32_t sample_rate, float hrtf, int32_t is_mono, int32_t ir_length,
+                      float* prd8, int32_t* depth, int32_t* n_dep, int32_t* dep_ear, int32_t* dep_idx, float* dep_val)
+{
+    oracle_params P{};
+    P.sample_rate = sample_rate; P.hrtf_absorption_rate = hrtf; P.is_mono = is_mono; P.ir_length = ir_length; P.bands = 1;
+    PathState st;
+    st.energy[0] = prd8[0]; st.distance = prd8[1];
+    st.prev = {prd8[2], prd8[3], prd8[4]};
+    st.dir = {ray_dir[0], ray_dir[1], ray_dir[2]};      /* the traced ray's direction is prd.direction (:238,:245) */
+    (void)prd8[5];
+    st.depth = *depth;
+    const int m = mat_absorption == -1.f ? -1 : (mat_absorption == -2.f ? -2 : 0);
+    const int delay = (int)((double)sample_rate * 0.00044);
+    Deposits dep;
+    shade_hit(P, 1, {tri9[0], tri9[1], tri9[2]}, {tri9[3], tri9[4], tri9[5]}, {tri9[6], tri9[7], tri9[8]}, m, &mat_absorption, 0.f,
+              0, {sphere_center[0], sphere_center[1], sphere_center[2]}, u, v, delay, st, dep);
+    prd8[0] = st.energy[0]; prd8[1] = st.distance;
+    prd8[2] = st.prev.x; prd8[3] = st.prev.y; prd8[4] = st.prev.z;
+    prd8[5] = st.dir.x; prd8[6] = st.dir.y; prd8[7] = st.dir.z;
+    *depth = st.depth;
+    *n_dep = (m < 0 && dep.idx[0] >= 0) ? dep.n : 0;
+    for (int i = 0; i < 2; ++i) { dep_ear[i] = dep.ear[i]; dep_idx[i] = dep.idx[i]; dep_val[i] = dep.val[i][0]; }
 }
 
 void oracle_ray_direction(uint64_t seed, uint64_t ray_id, float* dir3)

@@ -1,0 +1,1 @@
+/* oracle/ref_stubs: empty stand-in for the Win32 header OR/kernels.cuh:12 includes */

@@ -305,3 +305,31 @@ def test_check_parity_per_bin_rule_with_flipped_rays(golden_scenes, golden_recei
     rec, l, r = fake(3)
     with pytest.raises(AssertionError):
         check_parity(rec, l, r, o["segments"], o, case=case)
+
+
+def test_oracle_builds_are_bit_identical(golden_scenes, golden_receiver):
+    """BASELINE.md section 5 wants the CPU baseline built -O3 -march=native; the oracle's results must not depend on
+    that: the portable -O3 build, the -O2 build and the native build (compiled on this machine) agree bit for bit
+    (every fused operation is an explicit fmaf, contraction is off)."""
+    from util import Case
+    case = Case(golden_scenes["test_verts"], golden_scenes["test_mesh"], golden_scenes["test_names"], golden_receiver,
+                rays=(100, 50, 2), emitter=(0, 2, 0), center=(5, 2, 0), hrtf=0.7, sample_rate=16000, ir_seconds=1, seed=3)
+    flat, p = case.flat(), case.params()
+    tv = np.ascontiguousarray(flat.tri_verts, np.float32); tm = np.ascontiguousarray(flat.tri_mat, np.int32)
+    ab = np.ascontiguousarray(flat.absorption, np.float32); sc = np.ascontiguousarray(flat.scattering, np.float32)
+    import ctypes as C
+    n = 10_000
+    outs = []
+    for L in (oracle.lib(), oracle.load_variant("o2"), oracle.load_variant("native")):
+        hist = np.zeros((2, 1, 16000)); b = np.empty(n, np.int32); e = np.empty(n, np.int32); s = np.empty(n, np.int32)
+        en = np.empty((n, 1), np.float32)
+        segs = L.oracle_trace(C.byref(p), oracle._fp(tv), oracle._ip(tm), len(tv), oracle._fp(ab), oracle._fp(sc), len(ab), 0, n, 1, 1,
+                              oracle._dp(hist), oracle._ip(b), oracle._ip(e), oracle._fp(en), oracle._ip(s))
+        x = np.random.default_rng(1).standard_normal(3000).astype(np.float32); h = np.random.default_rng(2).standard_normal(500).astype(np.float32)
+        y = np.zeros(3499)
+        L.oracle_direct_conv(oracle._fp(x), 3000, oracle._fp(h), 500, oracle._dp(y), 1)
+        outs.append((segs, hist, b, e, en, s, y))
+    for o in outs[1:]:
+        assert o[0] == outs[0][0]
+        for a, b in zip(o[1:], outs[0][1:]):
+            assert np.array_equal(a, b)
