@@ -103,6 +103,7 @@ SYMBOLS = {
     "arv2_set_ir": (C.c_int, [_vp, _fp, _fp]),
     "arv2_ir_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "arv2_hist_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
+    "arv2_path_cache_info": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "arv2_last_segments": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "arv2_last_upload_bytes": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "arv2_get_records": (C.c_int, [_vp, C.c_int64, _ip, _ip, _fp, _ip, C.POINTER(C.c_int64)]),
@@ -397,6 +398,12 @@ class AudioRenderer:
         s = C.c_int64()
         _check(lib().arv2_last_segments(self._h, C.byref(s)))
         return s.value
+
+    def path_cache_info(self):
+        """(cached segments, device bytes) of the receiver-independent path cache."""
+        a = C.c_int64(); b = C.c_int64()
+        _check(lib().arv2_path_cache_info(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def last_upload_bytes(self):
         b = C.c_int64()

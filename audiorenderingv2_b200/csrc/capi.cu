@@ -80,11 +80,12 @@ struct arv2_ctx {
     unsigned long long* d_counters = nullptr;
     int* d_rec_bin = nullptr; int* d_rec_ear = nullptr; int* d_rec_nseg = nullptr; float* d_rec_energy = nullptr;
     long long rec_capacity = 0, last_range_rays = 0;
-    float4* d_pc_seg = nullptr; float* d_pc_energy = nullptr; int* d_pc_nseg = nullptr;
-    long long pc_rays = 0; unsigned pc_bounces = 0;
-    // data-parallel re-render: candidate list, per-candidate results, per-ray first hit (trace.cuh)
-    int2* d_rr_cand = nullptr; int2* d_rr_res = nullptr; float* d_rr_energy = nullptr; int* d_rr_first = nullptr;
-    long long rr_cap = 0;
+    // receiver-independent path cache, packed (trace.cuh): CSR records + energies, offsets, quantised path vertices, flag bits
+    float4* d_pc_seg = nullptr; float* d_pc_energy = nullptr;
+    unsigned long long* d_pc_off = nullptr; uint2* d_pc_vert = nullptr; unsigned* d_pc_bits = nullptr;
+    long long pc_segs = 0, pc_nvert = 0;
+    float pc_q0[3] = {0.f, 0.f, 0.f}, pc_qs[3] = {1.f, 1.f, 1.f}, pc_eps = 0.f;
+    bool rr_serial = false;
     // breadth-first tracer: per-depth path queues, grown on demand
     float4* d_wave_paths = nullptr; size_t wave_slots = 0;
     bool wave = true;
@@ -205,9 +206,9 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     if (c->desc.record_rays && n_rays <= c->rec_capacity) {
         p->rec_bin = c->d_rec_bin; p->rec_ear = c->d_rec_ear; p->rec_energy = c->d_rec_energy; p->rec_nseg = c->d_rec_nseg;
     }
-    p->pc_seg = c->d_pc_seg; p->pc_energy = c->d_pc_energy; p->pc_nseg = c->d_pc_nseg;
-    p->pc_stride = (long long)c->pc_bounces;
-    p->rr_cand = c->d_rr_cand; p->rr_res = c->d_rr_res; p->rr_energy = c->d_rr_energy; p->rr_first = c->d_rr_first; p->rr_cap = c->rr_cap;
+    p->pc_seg = c->d_pc_seg; p->pc_energy = c->d_pc_energy; p->pc_off = c->d_pc_off; p->pc_vert = c->d_pc_vert; p->pc_bits = c->d_pc_bits;
+    p->pc_nvert = c->pc_nvert; p->pc_eps = c->pc_eps;
+    for (int a = 0; a < 3; ++a) { p->pc_q0[a] = c->pc_q0[a]; p->pc_qs[a] = c->pc_qs[a]; }
     p->seed = c->seed; p->ray_begin = ray_begin; p->n_rays = n_rays;
     for (int a = 0; a < 3; ++a) { p->emitter[a] = c->emitter[a]; p->center[a] = c->center[a]; }
     p->recv_radius = c->recv_radius;
@@ -228,6 +229,8 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
     p->nodes4 = c->d_nodes4;
     for (int a = 0; a < 3; ++a) { p->qk[a] = c->qk[a]; p->qinvk[a] = c->qinvk[a]; p->qc[a] = c->qc[a]; }
     p->recv_root = c->has_receiver ? 1 + c->n_scene_nodes : -1;
+    // rr_walk_kernel keeps the receiver tree's nodes in shared memory when they fit the default 48 KB with room to spare
+    { const size_t nn = c->recv_bvh.nodes.size(); p->recv_nodes_shared = (c->has_receiver && nn > 0 && nn * 64 <= 40 * 1024 && !getenv("ARV2_RR_NO_SHARED")) ? (int)nn : 0; }
     p->any_scatter = c->any_scatter;
     // a warp tops up its free lanes only once at least 9 are free, 16 rays per claim: the rays it
     // starts together are neighbours in the direction order (tuning aids: ARV2_CHUNK, ARV2_REFILL_BELOW)
@@ -322,34 +325,85 @@ int ensure_wave(arv2_ctx* c, TraceParams* p, long long n_rays)
     return ARV2_OK;
 }
 
-int ensure_cache(arv2_ctx* c)
+void free_cache(arv2_ctx* c)
+{
+    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_off); cudaFree(c->d_pc_vert); cudaFree(c->d_pc_bits);
+    c->d_pc_seg = nullptr; c->d_pc_energy = nullptr; c->d_pc_off = nullptr; c->d_pc_vert = nullptr; c->d_pc_bits = nullptr;
+    c->pc_segs = 0; c->pc_nvert = 0; c->cache_valid = false;
+}
+
+int finish_timed(arv2_ctx* c, double* ms);
+
+// Trace the receiver-independent paths of the whole seeded set (scene tree only, wave_kernel mode 1) into a ray-major
+// scratch cache, then pack it: CSR records + energies, and the 8 B path vertices rr_mask_kernel streams.  The scratch
+// (max_bounces records per ray) is freed again; what stays is 36 B + 4 B x bands per traced segment.
+int build_cache(arv2_ctx* c, double* ms)
 {
     const long long n = c->n_rays_total;
-    if (c->max_bounces > 65535u || n > 0x7fffffffLL) { set_error("path cache: max_bounces <= 65535 and at most 2^31 rays"); return ARV2_ERR_INVALID; }
-    if (c->d_pc_seg && c->pc_rays == n && c->pc_bounces >= c->max_bounces) return ARV2_OK;
-    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg);
-    cudaFree(c->d_rr_cand); cudaFree(c->d_rr_res); cudaFree(c->d_rr_energy); cudaFree(c->d_rr_first);
-    c->d_pc_seg = nullptr; c->d_pc_energy = nullptr; c->d_pc_nseg = nullptr;
-    c->d_rr_cand = nullptr; c->d_rr_res = nullptr; c->d_rr_energy = nullptr; c->d_rr_first = nullptr; c->rr_cap = 0;
-    const size_t segs = (size_t)n * c->max_bounces;
-    CK(cudaMalloc(&c->d_pc_seg, segs * 2 * sizeof(float4)));
-    CK(cudaMalloc(&c->d_pc_energy, segs * sizeof(float) * c->bands));
-    CK(cudaMalloc(&c->d_pc_nseg, (size_t)n * sizeof(int)));
-    // data-parallel re-render (experiment, ARV2_RR_PARALLEL=1; 1.2 ms against 0.61 ms for the persistent per-ray
-    // kernel on C2, profiles/r07_trace_experiments.md section 8): room for 4 ball-entering segments per ray; more
-    // than that, or no memory for the lists, and the re-render takes the per-ray kernel
-    long long cap = std::max<long long>(1 << 16, std::min<long long>(4 * n, (long long)segs));
-    if (const char* e = getenv("ARV2_RR_CAP")) cap = atoll(e) > 0 ? atoll(e) : cap;     // tests: force the overflow fallback
-    if (getenv("ARV2_RR_PARALLEL") &&
-        cudaMalloc(&c->d_rr_cand, (size_t)cap * sizeof(int2)) == cudaSuccess && cudaMalloc(&c->d_rr_res, (size_t)cap * sizeof(int2)) == cudaSuccess &&
-        cudaMalloc(&c->d_rr_energy, (size_t)cap * sizeof(float) * c->bands) == cudaSuccess && cudaMalloc(&c->d_rr_first, (size_t)n * sizeof(int)) == cudaSuccess) {
-        c->rr_cap = cap;
-    } else {
-        cudaGetLastError();
-        cudaFree(c->d_rr_cand); cudaFree(c->d_rr_res); cudaFree(c->d_rr_energy); cudaFree(c->d_rr_first);
-        c->d_rr_cand = nullptr; c->d_rr_res = nullptr; c->d_rr_energy = nullptr; c->d_rr_first = nullptr; c->rr_cap = 0;
+    if (c->max_bounces > 65535u || n > 0x7fffffffLL || (double)n * (c->max_bounces + 1.0) >= 4.0e9) {
+        set_error("path cache: max_bounces <= 65535, at most 2^31 rays and fewer than 4e9 path vertices"); return ARV2_ERR_INVALID;
     }
-    c->pc_rays = n; c->pc_bounces = c->max_bounces; c->cache_valid = false;
+    free_cache(c);
+    int rc = upload_receiver(c);
+    if (rc != ARV2_OK) return rc;
+    rc = ensure_ray_order(c, 0, n);
+    if (rc != ARV2_OK) return rc;
+    const size_t slots = (size_t)n * std::max(1u, c->max_bounces);
+    float4* t_seg = nullptr; float* t_energy = nullptr; int* t_nseg = nullptr; unsigned long long* scratch = nullptr;
+    auto drop = [&]() { cudaFree(t_seg); cudaFree(t_energy); cudaFree(t_nseg); cudaFree(scratch); };
+#define CKB(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); drop(); free_cache(c); return ARV2_ERR_CUDA; } } while (0)
+    CKB(cudaMalloc(&t_seg, slots * 2 * sizeof(float4)));
+    CKB(cudaMalloc(&t_energy, slots * sizeof(float) * c->bands));
+    CKB(cudaMalloc(&t_nseg, (size_t)n * sizeof(int)));
+    CKB(cudaMalloc(&c->d_pc_off, ((size_t)n + 1) * sizeof(unsigned long long)));
+    const long long tiles = (n + 2047) / 2048;
+    CKB(cudaMalloc(&scratch, ((size_t)tiles + 1) * sizeof(unsigned long long)));
+    CKB(cudaMemsetAsync(c->d_counters, 0, kCounters * sizeof(unsigned long long), c->stream));
+    TraceParams p;
+    fill_params(c, &p, 0, n);
+    p.rec_bin = nullptr; p.rec_ear = nullptr; p.rec_energy = nullptr; p.rec_nseg = nullptr;
+    p.pc_seg = t_seg; p.pc_energy = t_energy; p.pc_nseg = t_nseg; p.pc_stride = (long long)std::max(1u, c->max_bounces);
+    rc = ensure_wave(c, &p, n);
+    if (rc != ARV2_OK) { drop(); return rc; }
+    CKB(cudaEventRecord(c->ev0, c->stream));
+    CKB(launch_trace(p, c->bands, 1, c->sm_count, c->stream));
+    CKB(launch_cache_offsets(t_nseg, n, c->d_pc_off, scratch, c->stream));
+    unsigned long long total = 0;
+    CKB(cudaMemcpyAsync(&total, c->d_pc_off + n, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+    CKB(cudaStreamSynchronize(c->stream));
+    c->pc_segs = (long long)total; c->pc_nvert = (long long)total + n;
+    // records and energies share the vertices' index space (one unused slot per ray): a flagged vertex is its own record index
+    CKB(cudaMalloc(&c->d_pc_seg, (size_t)c->pc_nvert * 2 * sizeof(float4)));
+    CKB(cudaMalloc(&c->d_pc_energy, (size_t)c->pc_nvert * sizeof(float) * c->bands));
+    // vertices padded to whole 128-vertex tiles plus one (rr_mask_kernel reads tile by tile and one vertex beyond)
+    const size_t vert_padded = ((size_t)c->pc_nvert + 127) / 128 * 128 + 128;
+    CKB(cudaMalloc(&c->d_pc_vert, vert_padded * sizeof(uint2)));
+    CKB(cudaMemsetAsync(c->d_pc_vert + c->pc_nvert, 0, (vert_padded - (size_t)c->pc_nvert) * sizeof(uint2), c->stream));
+    CKB(cudaMalloc(&c->d_pc_bits, vert_padded / 32 * sizeof(unsigned)));
+    // vertex grid: 16 bits per axis over the scene's bounds and the emitter (every path vertex lies on the scene or at the
+    // emitter).  pc_eps = how far a true segment may be from the line through its two quantised vertices: a segment starts
+    // 1 mm (x |dir|) off the wall the previous one ended on, each vertex moves by at most half a grid diagonal, float slop.
+    float qmax = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        float lo = c->emitter[a], hi = c->emitter[a];
+        if (c->n_scene > 0) { lo = std::min(lo, c->scene_bvh.lo[a]); hi = std::max(hi, c->scene_bvh.hi[a]); }
+        const float pad = std::max(0.01f, 1e-3f * (hi - lo));
+        c->pc_q0[a] = lo - pad;
+        c->pc_qs[a] = (hi - lo + 2.f * pad) / 65535.f;
+        qmax = std::max(qmax, c->pc_qs[a]);
+    }
+    // (rr_mask_kernel folds the grid origin, the centre and 2^23 grid steps into one constant per axis: its rounding moves
+    // every vertex by up to one grid step per axis, the same way)
+    c->pc_eps = 1.2e-3f + (0.87f + 1.8f) * qmax + 1e-4f + 1e-5f * (65535.f * qmax);
+    fill_params(c, &p, 0, n);
+    p.pc_stride = (long long)std::max(1u, c->max_bounces);
+    CKB(launch_cache_compact(p, t_seg, t_energy, c->d_pc_vert, c->bands, c->stream));
+    CKB(cudaEventRecord(c->ev1, c->stream));
+    rc = finish_timed(c, ms);
+    drop();
+#undef CKB
+    if (rc != ARV2_OK) { free_cache(c); return rc; }
+    c->cache_valid = true;
     return ARV2_OK;
 }
 
@@ -581,6 +635,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     auto* c = new arv2_ctx;
     if (getenv("ARV2_NO_SORT")) c->coherent_order = false;   // tuning aids (A/B)
     if (getenv("ARV2_NO_WAVE")) c->wave = false;
+    if (getenv("ARV2_RR_SERIAL")) c->rr_serial = true;
     c->desc = *desc; c->desc.materials = nullptr; c->desc.n_materials = 0;
     c->device = desc->device;
     c->bands = desc->bands;
@@ -721,8 +776,7 @@ void arv2_destroy(arv2_ctx* c)
     cudaFree(c->d_nodes); cudaFree(c->d_nodes4); cudaFree(c->d_tris); cudaFree(c->d_keep); cudaFree(c->d_scatter);
     cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_ir_r); cudaFree(c->d_counters);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
-    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_nseg); cudaFree(c->order[0].d); cudaFree(c->order[1].d); cudaFree(c->d_wave_paths);
-    cudaFree(c->d_rr_cand); cudaFree(c->d_rr_res); cudaFree(c->d_rr_energy); cudaFree(c->d_rr_first);
+    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_off); cudaFree(c->d_pc_vert); cudaFree(c->d_pc_bits); cudaFree(c->order[0].d); cudaFree(c->order[1].d); cudaFree(c->d_wave_paths);
     cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -812,25 +866,14 @@ int arv2_rerender(arv2_ctx* c, double* ms)
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->d_counters, 0, kCounters * sizeof(unsigned long long), c->stream));
-    const bool parallel = c->rr_cap > 0;
-    if (parallel) {
-        CK(cudaMemsetAsync(c->d_rr_first, 0x7f, (size_t)c->n_rays_total * sizeof(int), c->stream));     // kRrNoHit
-        CK(launch_rerender_parallel(p, c->bands, c->sm_count, c->stream));
-    } else {
+    if (c->rr_serial) CK(launch_rerender_serial(p, c->bands, c->sm_count, c->stream));
+    else {
+        CK(cudaMemsetAsync(c->d_pc_bits, 0, ((size_t)c->pc_nvert + 127) / 128 * 128 / 32 * sizeof(unsigned) + 128 / 32 * sizeof(unsigned), c->stream));
         CK(launch_rerender(p, c->bands, c->sm_count, c->stream));
     }
     CK(launch_finalize(c->d_hist, c->bands, c->ir_len, c->mono, c->d_ir_l, c->d_ir_r, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
     c->last_range_rays = c->n_rays_total;
-    rc = finish_timed(c, ms);
-    if (rc != ARV2_OK || !parallel || c->h_counters[2] <= (unsigned long long)c->rr_cap) return rc;
-    // more ball-entering segments than the candidate list holds (a receiver that fills the room): the per-ray kernel
-    CK(cudaEventRecord(c->ev0, c->stream));
-    CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));
-    CK(cudaMemsetAsync(c->d_counters, 0, kCounters * sizeof(unsigned long long), c->stream));
-    CK(launch_rerender(p, c->bands, c->sm_count, c->stream));
-    CK(launch_finalize(c->d_hist, c->bands, c->ir_len, c->mono, c->d_ir_l, c->d_ir_r, c->stream));
-    CK(cudaEventRecord(c->ev1, c->stream));
     return finish_timed(c, ms);
 }
 
@@ -842,31 +885,15 @@ int arv2_render(arv2_ctx* c, double* ms)
         if (rc != ARV2_OK) return rc;
         return arv2_finalize(c);
     }
-    // path-cache mode: trace the receiver-independent paths once, then scan them
+    // path-cache mode: trace the receiver-independent paths once, then re-deposit from them
     CK(cudaSetDevice(c->device));
-    int rc = ensure_cache(c);
-    if (rc != ARV2_OK) return rc;
     double ms_build = 0.0;
     if (!c->cache_valid) {
-        rc = upload_receiver(c);
+        const int rc = build_cache(c, &ms_build);
         if (rc != ARV2_OK) return rc;
-        rc = ensure_ray_order(c, 0, c->n_rays_total);
-        if (rc != ARV2_OK) return rc;
-        CK(cudaMemsetAsync(c->d_counters, 0, kCounters * sizeof(unsigned long long), c->stream));
-        TraceParams p;
-        fill_params(c, &p, 0, c->n_rays_total);
-        p.rec_bin = nullptr; p.rec_ear = nullptr; p.rec_energy = nullptr; p.rec_nseg = nullptr;
-        rc = ensure_wave(c, &p, c->n_rays_total);
-        if (rc != ARV2_OK) return rc;
-        CK(cudaEventRecord(c->ev0, c->stream));
-        CK(launch_trace(p, c->bands, 1, c->sm_count, c->stream));
-        CK(cudaEventRecord(c->ev1, c->stream));
-        rc = finish_timed(c, &ms_build);
-        if (rc != ARV2_OK) return rc;
-        c->cache_valid = true;
     }
     double ms_scan = 0.0;
-    rc = arv2_rerender(c, &ms_scan);
+    const int rc = arv2_rerender(c, &ms_scan);
     if (ms) *ms = ms_build + ms_scan;
     return rc;
 }
@@ -921,6 +948,16 @@ int arv2_last_upload_bytes(arv2_ctx* c, int64_t* bytes)
 {
     REQUIRE(c && bytes, "null argument");
     *bytes = (int64_t)c->upload_bytes;
+    return ARV2_OK;
+}
+
+int arv2_path_cache_info(arv2_ctx* c, int64_t* segments, int64_t* bytes)
+{
+    REQUIRE(c, "null ctx");
+    if (!c->desc.path_cache || !c->cache_valid) { set_error("no valid path cache"); return ARV2_ERR_STATE; }
+    if (segments) *segments = c->pc_segs;
+    if (bytes) *bytes = c->pc_nvert * (int64_t)(2 * sizeof(float4) + sizeof(float) * c->bands + sizeof(uint2)) + (c->n_rays_total + 1) * (int64_t)sizeof(unsigned long long)
+                        + (c->pc_nvert + 31) / 32 * (int64_t)sizeof(unsigned);
     return ARV2_OK;
 }
 

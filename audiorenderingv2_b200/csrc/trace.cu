@@ -284,7 +284,25 @@ struct Traversal {
                 __float_as_int(n3.x), __float_as_int(n3.y));
     }
 
+    // the same step on a copy of a (small) tree in shared memory: `nodes` points at the copy of node `first`
+    __device__ __forceinline__ void step_inner_shared(int* stack, const float4* nodes, int first, const RayGrid& g)
+    {
+#if ARV2_QNODES
+        (void)stack; (void)nodes; (void)first; (void)g;
+#else
+        const float ix = g.ix, iy = g.iy, iz = g.iz, ox = g.ox, oy = g.oy, oz = g.oz;
+        const float4* n = nodes + (cur - first) * 4;
+        const float4 n0 = n[0], n1 = n[1], n2 = n[2], n3 = n[3];
+        descend(stack,
+                fmaf(n0.x, ix, -ox), fmaf(n0.y, ix, -ox), fmaf(n0.z, iy, -oy), fmaf(n0.w, iy, -oy), fmaf(n2.x, iz, -oz), fmaf(n2.y, iz, -oz),
+                fmaf(n1.x, ix, -ox), fmaf(n1.y, ix, -ox), fmaf(n1.z, iy, -oy), fmaf(n1.w, iy, -oy), fmaf(n2.z, iz, -oz), fmaf(n2.w, iz, -oz),
+                __float_as_int(n3.x), __float_as_int(n3.y));
+#endif
+    }
+
     // one leaf: exact tests of its <= 8 triangles; the test needs the first 48 B of a record (P1, id, P2, material, P3)
+    // (CACHED: the records stay in L1 -- the 1020 receiver triangles of a re-render; the scene's are read once per visit)
+    template <bool CACHED = false>
     __device__ __forceinline__ void step_leaf(int* stack, const float4* __restrict__ tris, F3 org, F3 dir)
     {
         const int code = ~cur;
@@ -292,8 +310,8 @@ struct Traversal {
         const int cnt = (code & 7) + 1;
         for (int i = 0; i < cnt; ++i) {
             const int slot = first + i;
-            const F8 A = ldg256_tri(tris + slot * 4);
-            const float4 B = ldg128_tri(tris + slot * 4 + 2);
+            const F8 A = CACHED ? ldg256(tris + slot * 4) : ldg256_tri(tris + slot * 4);
+            const float4 B = CACHED ? __ldg(tris + slot * 4 + 2) : ldg128_tri(tris + slot * 4 + 2);
             float t, u, v;
             if (tri_test(f3(A.lo.x, A.lo.y, A.lo.z), f3(A.hi.x, A.hi.y, A.hi.z), f3(B.x, B.y, B.z), org, dir, &t, &u, &v)) {
                 const int id = __float_as_int(A.lo.w);
@@ -920,19 +938,341 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
 }
 
 // ---------------------------------------------------------------------------------------
-// Receiver move: walk each ray's cached receiver-independent segments in order and deposit at
-// the first one the receiver intercepts before the wall (t_recv < t_wall; ties go to the scene
-// because scene triangle ids are lower).
-// The cache is ray-major (a ray's records are consecutive 32 B sectors), a lane streams its ray four
-// records (one 128 B line) at a time and prefetches the next two lines into L2.  A segment is first tested against the receiver's
-// bounding ball (a few FMAs, exact-conservative).  Two things keep the warp full (r04 profile of
-// the version that walked the receiver tree as soon as 12 lanes held a candidate: 6.8 of 32
-// lanes per instruction, 446 M warp instructions):
-//   * a lane whose segment enters the ball PARKS (ray, k) in the warp's candidate buffer and takes
-//     the next ray, so 32 lanes keep scanning;
-//   * the receiver tree is walked only when 32 candidates are parked -- a full warp of walks; a
-//     candidate that misses the mesh goes to the warp's resume buffer and is scanned on from k+1.
-// A warp admits new rays only while it holds at most 32 parked ones, so 64 slots per buffer suffice.
+// Receiver move.  The cached paths do not depend on the receiver; it only ends them (OR/devicePrograms.cu:147,169), so a
+// move re-deposits: per ray, the first cached segment the receiver intercepts before the wall (t_recv < t_wall; ties go
+// to the scene because scene triangle ids are lower) deposits, exactly as a fresh trace would.
+//
+// Two data-parallel passes over the packed (CSR) cache (profiles/r08_rerender.md):
+//   rr_mask_kernel  streams the path vertices: the segment between two consecutive 8 B vertices (16-bit grid) against
+//                   the receiver's bounding ball, padded by what a true segment may stray from the quantised one --
+//                   8 B per segment instead of the 32 B record, coalesced, no dependence between rays (the r06 kernel
+//                   scanned each ray serially: a chain of dependent DRAM round trips, 10 of 32 lanes).  The flagged few
+//                   per cent are parked per warp and refined 32 at a time with their exact record (first step of the
+//                   walk: the root boxes of the receiver tree); what passes sets its bit in the bit array.
+//   rr_walk_kernel  one lane per ray: its flagged segments, in order, are walked through the receiver tree with the exact
+//                   32 B record until the first hit, which ends the ray (warp-aggregated fp64 deposit); the lane then
+//                   takes the next ray.  Walks behind a ray's first hit never happen (the r07 data-parallel experiment
+//                   walked every flagged segment).  A first version that packed the offers of 256 rays into full warps
+//                   through a shared-memory queue spent its time in the CTA barriers between rounds (r08).
+// Conservative flags + exact walks: per-ray results are bit-identical to the serial kernel and to a fresh trace.
+constexpr int kRrThreads = 256;
+#ifndef ARV2_RRW_MINB
+#define ARV2_RRW_MINB 3               // CTAs of rr_walk_kernel per SM
+#endif
+
+__device__ __forceinline__ F3 vert_pos(const TraceParams& p, uint2 v)
+{
+    return f3(fmaf((float)(v.x & 0xffffu), p.pc_qs[0], p.pc_q0[0]), fmaf((float)(v.x >> 16), p.pc_qs[1], p.pc_q0[1]),
+              fmaf((float)(v.y & 0xffffu), p.pc_qs[2], p.pc_q0[2]));
+}
+constexpr unsigned kVertSegment = 1u << 16, kVertEscapes = 2u << 16;      // flags in the top half of uint2::y
+
+// A vertex's coordinate without an integer-to-float conversion (I2F issues at a fraction of the FMA rate): the 16-bit
+// grid index is dropped into the mantissa of 2^23, so that fmaf(as_float(0x4B000000 | q), qs, q0 - c - 2^23 qs) is the
+// coordinate relative to the ball's centre.
+__device__ __forceinline__ float grid_coord(unsigned q16, float qs, float bias) { return fmaf(__uint_as_float(0x4B000000u | q16), qs, bias); }
+
+// The first step of a walk of the receiver tree, on its own: does the segment (org + t dir, 0 <= t <= tmax) enter either
+// child box of the tree's root?  Same arithmetic as Traversal::step_inner / descend, so skipping a segment that fails
+// it is exactly what the walk would have concluded.
+__device__ __forceinline__ bool enters_receiver_root(const TraceParams& p, F3 org, F3 dir, float tmax)
+{
+    const float ix = safe_rcp(dir.x), iy = safe_rcp(dir.y), iz = safe_rcp(dir.z);
+    const float ox = org.x * ix, oy = org.y * iy, oz = org.z * iz;
+    const F8 na = ldg256(p.nodes + p.recv_root * 4), nb = ldg256(p.nodes + p.recv_root * 4 + 2);
+    const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo;
+    const float c0lox = fmaf(n0.x, ix, -ox), c0hix = fmaf(n0.y, ix, -ox), c0loy = fmaf(n0.z, iy, -oy), c0hiy = fmaf(n0.w, iy, -oy);
+    const float c0loz = fmaf(n2.x, iz, -oz), c0hiz = fmaf(n2.y, iz, -oz);
+    const float c1lox = fmaf(n1.x, ix, -ox), c1hix = fmaf(n1.y, ix, -ox), c1loy = fmaf(n1.z, iy, -oy), c1hiy = fmaf(n1.w, iy, -oy);
+    const float c1loz = fmaf(n2.z, iz, -oz), c1hiz = fmaf(n2.w, iz, -oz);
+    const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.f));
+    const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
+    const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.f));
+    const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
+    return c0min <= c0max || c1min <= c1max;
+}
+
+// A warp takes 128 consecutive vertices per trip, lane l the four vertices 4l .. 4l+3 (one 256-bit load; the array is
+// padded to whole tiles + 1): three of a lane's four segments end on its own vertices, the fourth on the next lane's first.
+constexpr int kMaskTile = 128;
+
+__global__ void __launch_bounds__(kRrThreads) rr_mask_kernel(const TraceParams p)
+{
+    const long long n = p.pc_nvert;
+    const float r = p.recv_radius + p.pc_eps, r2 = r * r * 1.0001f;
+    const float qx = p.pc_qs[0], qy = p.pc_qs[1], qz = p.pc_qs[2];
+    const float bx = p.pc_q0[0] - p.center[0] - 8388608.f * qx, by = p.pc_q0[1] - p.center[1] - 8388608.f * qy, bz = p.pc_q0[2] - p.center[2] - 8388608.f * qz;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    // Second stage, on the flagged segments only (a few per cent): the first step of the walk of the receiver tree --
+    // does the exact segment enter a root box before it ends on its wall?  Most flagged segments end on geometry next
+    // to the receiver or only cross the rim of the ball; what passes sets its bit in the (zeroed) bit array.  The
+    // record of segment i is stored at index i, like its vertex.
+    __shared__ unsigned sh_buf[kRrThreads / 32][32 + kMaskTile];
+    unsigned* const buf = sh_buf[threadIdx.x >> 5];
+    int n_buf = 0;                                 // warp-uniform
+    auto refine = [&](unsigned idx) {
+        const F8 rec = ldg256_tri(p.pc_seg + 2 * (size_t)idx);
+        if (enters_receiver_root(p, f3(rec.lo.x, rec.lo.y, rec.lo.z), f3(rec.hi.x, rec.hi.y, rec.hi.z), rec.lo.w))
+            atomicOr(p.pc_bits + (idx >> 5), 1u << (idx & 31));
+    };
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp0 * kMaskTile; base < n; base += n_warps * kMaskTile) {
+        const uint2* src = p.pc_vert + base + lane * 4;
+        uint4 lo, hi;
+        asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(src));
+        // the vertex after this lane's four: the next lane's first, or (lane 31) the first of the next tile
+        unsigned nx = __shfl_down_sync(FULL, lo.x, 1), ny = __shfl_down_sync(FULL, lo.y, 1);
+        if (lane == 31) { const uint2 w = __ldg(p.pc_vert + base + kMaskTile); nx = w.x; ny = w.y; }
+        const unsigned wx[5] = {lo.x, lo.z, hi.x, hi.z, nx}, wy[5] = {lo.y, lo.w, hi.y, hi.w, ny};
+        float x[5], y[5], z[5], qq[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            x[j] = grid_coord(wx[j] & 0xffffu, qx, bx); y[j] = grid_coord(wx[j] >> 16, qy, by); z[j] = grid_coord(wy[j] & 0xffffu, qz, bz);
+            qq[j] = x[j] * x[j] + y[j] * y[j] + z[j] * z[j];                  // squared distance from the centre
+        }
+        unsigned nib = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // closest point of the segment (a = vertex j, e = vertex j+1, relative to the centre) to the origin, division-free
+            const float dx = x[j + 1] - x[j], dy = y[j + 1] - y[j], dz = z[j + 1] - z[j];
+            const float dd = dx * dx + dy * dy + dz * dz;
+            const float ad = -(x[j] * dx + y[j] * dy + z[j] * dz);            // (centre - a) . d
+            const bool inside = ad <= 0.f ? qq[j] <= r2 : (ad >= dd ? qq[j + 1] <= r2 : (qq[j] - r2) * dd <= ad * ad * 1.0001f);
+            const bool cand = (wy[j] & kVertSegment) && (inside || (wy[j] & kVertEscapes));       // no end point: always walked
+            nib |= cand ? (1u << j) : 0u;
+        }
+        // ---- park the flagged segments of this trip in the warp's buffer ...
+        if (__any_sync(FULL, nib != 0u)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned c = __ballot_sync(FULL, (nib >> j) & 1u);
+                if ((nib >> j) & 1u) buf[n_buf + __popc(c & lt)] = (unsigned)(base + lane * 4 + j);
+                n_buf += __popc(c);
+            }
+            __syncwarp();
+        }
+        // ... and refine them 32 at a time
+        while (n_buf >= 32) { n_buf -= 32; refine(buf[n_buf + lane]); __syncwarp(); }
+    }
+    if (lane < n_buf) refine(buf[lane]);
+}
+
+// first set bit of the bit array in [a, b), or -1
+__device__ __forceinline__ long long next_flag(const unsigned* __restrict__ bits, long long a, long long b)
+{
+    while (a < b) {
+        unsigned w = __ldg(bits + (a >> 5)) & (0xffffffffu << (a & 31));
+        const long long word_end = (a | 31) + 1;
+        if (b < word_end) w &= 0xffffffffu >> (word_end - b);
+        if (w) return (a & ~31LL) + (__ffs(w) - 1);
+        a = word_end;
+    }
+    return -1;
+}
+
+// One lane = one ray at a time, and the lanes of a warp are decoupled: a walk of the receiver tree takes 5 to 80 node
+// visits, so a warp that starts 32 walks together and waits for the longest runs at 6.5 of 32 lanes (r08 capture of that
+// version).  Here a lane whose walk has finished parks; once kRrAcquire lanes are parked (or nothing else is left to do)
+// the warp resolves them -- a hit deposits and ends the ray, a miss moves on -- and hands each its next offer: the ray's
+// next flagged segment that also enters the root boxes of the receiver tree, from the next ray of the warp's chunk
+// when the ray is used up (ballot / popc refill).  In between, the warp takes single steps: inner nodes for the lanes
+// that stand at one, a leaf for the lanes that stand at one once kRrLeaf of them do.
+#ifndef ARV2_RR_ACQUIRE
+#define ARV2_RR_ACQUIRE 12
+#endif
+#ifndef ARV2_RR_LEAF
+#define ARV2_RR_LEAF 6
+#endif
+#ifndef ARV2_RR_BURST
+#define ARV2_RR_BURST 4
+#endif
+
+template <int NB>
+__global__ void __launch_bounds__(kRrThreads, ARV2_RRW_MINB) rr_walk_kernel(const TraceParams p)
+{
+    // the receiver tree's nodes (a few hundred, 64 B each) in shared memory: a node visit is a dependent load, and most
+    // of this kernel's time was spent waiting for those from L1 / L2 (r08 capture: 6.9 warps per issue on long_scoreboard)
+    extern __shared__ float4 sh_nodes[];
+    const bool in_shared = p.recv_nodes_shared > 0;
+    for (int i = threadIdx.x; i < p.recv_nodes_shared * 4; i += blockDim.x) sh_nodes[i] = __ldg(p.nodes + (size_t)p.recv_root * 4 + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    long long chunk_base = 0;                     // warp-uniform: first ray of the warp's chunk of kChunk rays
+    unsigned pend[4] = {0u, 0u, 0u, 0u};          // warp-uniform: rays of the chunk that have a flagged segment and no lane yet
+    bool pool_empty = false;                      // warp-uniform
+    long long ray = -1, vbase = 0;
+    unsigned long long off0 = 0;
+    int n = 0, cursor = 0, k = -1;
+    bool walking = false;                         // a walk of segment k is under way (or has just finished)
+    F3 org = f3(0.f, 0.f, 0.f), dir = f3(1.f, 1.f, 1.f);
+    float t_wall = 0.f, dist0 = 0.f;
+    unsigned long long segs = 0;
+    Traversal tr;
+    tr.reset(1e20f);
+    RayGrid g;
+    g.setup(p, org, dir);
+    int stack[kStack];
+    float energy[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) energy[b] = 0.f;
+
+    for (;;) {
+        const unsigned inner_m = __ballot_sync(FULL, walking && tr.at_inner());
+        const unsigned leaf_m = __ballot_sync(FULL, walking && tr.at_leaf());
+        const unsigned busy = inner_m | leaf_m;
+        const int parked = __popc(__ballot_sync(FULL, walking && tr.finished()));      // walks waiting to be resolved
+        // (after a service phase every lane walks or, once the pool is empty, is out of rays for good)
+        if (busy == 0 || parked >= ARV2_RR_ACQUIRE || (pool_empty && 2 * parked >= __popc(busy) + parked)) {
+            // ---- resolve the finished walks
+            bool dep = false;
+            int bin = -1, primary = 0;
+            if (walking && tr.finished()) {
+                walking = false;
+                const Hit& h = tr.h;
+                if (h.slot >= 0 && h.t < t_wall) {
+                    const size_t ci = (size_t)(vbase + k);
+                    const F8 A = ldg256(p.tris + h.slot * 4), B = ldg256(p.tris + h.slot * 4 + 2);
+                    const int mat = __float_as_int(A.hi.w);
+                    const F3 pt = hit_point(f3(A.lo.x, A.lo.y, A.lo.z), f3(A.hi.x, A.hi.y, A.hi.z), f3(B.lo.x, B.lo.y, B.lo.z), h.u, h.v);
+                    const F3 dp = sub3(pt, org);
+                    const float dist = __fadd_rn(dist0, __fsqrt_rn(dot3(dp, dp)));
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) energy[b] = __ldg(p.pc_energy + ci * NB + b);
+                    bin = receiver_hit<NB>(p, pt, dir, dist, energy);
+                    primary = (mat == -1) ? 0 : 1;
+                    dep = bin >= 0 && bin < p.ir_len;
+                    if (p.rec_bin) p.rec_bin[ray] = bin;
+                    if (p.rec_ear) p.rec_ear[ray] = (mat == -1) ? 1 : 2;
+                    if (p.rec_nseg) p.rec_nseg[ray] = k + 1;
+                    if (p.rec_energy) {
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) p.rec_energy[(size_t)ray * NB + b] = energy[b];
+                    }
+                    segs += (unsigned long long)(k + 1);
+                    ray = -1;                                // the path ends on the receiver (OR/devicePrograms.cu:147,169)
+                } else {
+                    cursor = k + 1;
+                }
+            }
+            deposit_warp<NB>(p, dep, bin, primary, energy);
+
+            // ---- every parked lane gets its next offer, or the pool runs dry
+            bool offer = false;
+            for (;;) {
+                if (!walking && !offer && ray >= 0) {
+                    // the ray's next flagged segment (one that only grazes the bounding ball ends its walk at the root
+                    // of the receiver tree: one step of one lane, now that the lanes are decoupled)
+                    const long long f = next_flag(p.pc_bits, vbase + cursor, vbase + n);
+                    if (f >= 0) {
+                        k = (int)(f - vbase); offer = true;
+                        const F8 rec = ldg256(p.pc_seg + 2 * (size_t)(vbase + k));
+                        org = f3(rec.lo.x, rec.lo.y, rec.lo.z); dir = f3(rec.hi.x, rec.hi.y, rec.hi.z); t_wall = rec.lo.w; dist0 = rec.hi.w;
+                    }
+                    if (!offer) {                            // every cached segment passed: a miss
+                        if (p.rec_bin) p.rec_bin[ray] = -1;
+                        if (p.rec_ear) p.rec_ear[ray] = 0;
+                        if (p.rec_nseg) p.rec_nseg[ray] = n;
+                        if (p.rec_energy) {
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) p.rec_energy[(size_t)ray * NB + b] = 0.f;
+                        }
+                        segs += (unsigned long long)n;
+                        ray = -1;
+                    }
+                }
+                const unsigned need = __ballot_sync(FULL, ray < 0);
+                if (need == 0) break;
+                int pending = __popc(pend[0]) + __popc(pend[1]) + __popc(pend[2]) + __popc(pend[3]);
+                if (pending == 0) {
+                    if (pool_empty) break;
+                    // the warp's next 128 rays, looked at by all lanes first: a ray without a flagged segment (in a large
+                    // hall: nearly all of them) is closed here and now, the others wait in `pend` for a free lane
+                    unsigned long long b = 0;
+                    if (lane == 0) b = atomicAdd(p.counters, (unsigned long long)kChunk);
+                    chunk_base = (long long)__shfl_sync(FULL, b, 0);
+                    if (chunk_base >= p.n_rays) { pool_empty = true; break; }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const long long r = chunk_base + q * 32 + lane;
+                        bool open = false;
+                        if (r < p.n_rays) {
+                            const unsigned long long o0 = __ldg(p.pc_off + r);
+                            const int rn = (int)(__ldg(p.pc_off + r + 1) - o0);
+                            const long long vb = (long long)o0 + r;
+                            open = next_flag(p.pc_bits, vb, vb + rn) >= 0;
+                            if (!open) {                     // every cached segment passes: a miss
+                                if (p.rec_bin) p.rec_bin[r] = -1;
+                                if (p.rec_ear) p.rec_ear[r] = 0;
+                                if (p.rec_nseg) p.rec_nseg[r] = rn;
+                                if (p.rec_energy) {
+#pragma unroll
+                                    for (int bb = 0; bb < NB; ++bb) p.rec_energy[(size_t)r * NB + bb] = 0.f;
+                                }
+                                segs += (unsigned long long)rn;
+                            }
+                        }
+                        pend[q] = __ballot_sync(FULL, open);
+                    }
+                    continue;
+                }
+                // hand the first popc(need) pending rays to the lanes in need, in order
+                int rank = __popc(need & lt);
+                if (ray < 0 && rank < pending) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cq = __popc(pend[q]);
+                        if (rank >= 0 && rank < cq) { ray = chunk_base + q * 32 + (int)__fns(pend[q], 0, rank + 1); rank = -1; }
+                        else if (rank >= 0) rank -= cq;
+                    }
+                    off0 = __ldg(p.pc_off + ray);
+                    n = (int)(__ldg(p.pc_off + ray + 1) - off0);
+                    vbase = (long long)off0 + ray;
+                    cursor = 0;
+                }
+                int take = min(__popc(need), pending);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cq = __popc(pend[q]);
+                    const int t = min(take, cq);
+                    if (t == cq) pend[q] = 0u;
+                    else if (t > 0) pend[q] &= ~((2u << __fns(pend[q], 0, t)) - 1u);
+                    take -= t;
+                }
+            }
+            if (offer) {
+                walking = true;
+                tr.reset(t_wall);
+                g.setup(p, org, dir);
+                tr.enter(stack, p.recv_root);
+            }
+            if (!__any_sync(FULL, walking)) break;           // the pool is empty and no ray is open
+            continue;
+        }
+        // ---- single steps
+        if (leaf_m != 0 && (__popc(leaf_m) >= ARV2_RR_LEAF || inner_m == 0)) {
+            if (walking && tr.at_leaf()) tr.step_leaf<true>(stack, p.tris, org, dir);
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < ARV2_RR_BURST; ++s)
+                if (walking && tr.at_inner()) {
+                    if (in_shared) tr.step_inner_shared(stack, sh_nodes, p.recv_root, g);
+                    else tr.step_inner(stack, p, g, org);
+                }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
+    if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+}
+
+// ---------------------------------------------------------------------------------------
+// The r06 kernel on the packed cache (A/B: ARV2_RR_SERIAL=1): every lane scans its ray's 32 B records in order (four
+// records = one 128 B line per step, the next two lines prefetched into L2), tests them against the bounding ball,
+// parks candidates per warp in shared memory and walks them through the receiver tree 32 at a time; misses resume from
+// a warp-local buffer.  0.62 ms on C2 against the two passes above (profiles/r08_rerender.md).
 #ifndef ARV2_RR_MINB
 #define ARV2_RR_MINB 4
 #endif
@@ -952,6 +1292,7 @@ __global__ void __launch_bounds__(kRerenderThreads, ARV2_RR_MINB) rerender_kerne
     bool pool_empty = false;                      // warp-uniform
     bool have = false;
     int ray = 0, k = 0, n = 0;
+    size_t base = 0;                              // first record of `ray`
     float energy[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) energy[b] = 0.f;
@@ -980,6 +1321,7 @@ __global__ void __launch_bounds__(kRerenderThreads, ARV2_RR_MINB) rerender_kerne
             if (!have && rank < take) {
                 const int2 e = res[n_res - 1 - rank];
                 ray = e.x; k = e.y & 0xffff; n = (int)((unsigned)e.y >> 16); have = true;
+                base = (size_t)__ldg(p.pc_off + ray) + (size_t)ray;
             }
             n_res -= take;
             __syncwarp();
@@ -998,7 +1340,9 @@ __global__ void __launch_bounds__(kRerenderThreads, ARV2_RR_MINB) rerender_kerne
             const int rank = __popc(need & lt);
             if (!have && rank < avail) {
                 ray = (int)(chunk_next + rank);
-                n = p.pc_nseg[ray];
+                base = (size_t)__ldg(p.pc_off + ray);
+                n = (int)(__ldg(p.pc_off + ray + 1) - base);
+                base += (size_t)ray;
                 k = 0;
                 have = n > 0;
                 if (n == 0) finish(ray, -1, 0, 0);
@@ -1022,7 +1366,7 @@ __global__ void __launch_bounds__(kRerenderThreads, ARV2_RR_MINB) rerender_kerne
             if (lane < m) {
                 const int2 e = cand[n_cand - m + lane];
                 c_ray = e.x; c_k = e.y & 0xffff; c_n = (int)((unsigned)e.y >> 16);
-                const size_t ci = (size_t)c_ray * (size_t)p.pc_stride + (size_t)c_k;
+                const size_t ci = (size_t)__ldg(p.pc_off + c_ray) + (size_t)c_ray + (size_t)c_k;
                 const F8 rec = ldg256(p.pc_seg + 2 * ci);
                 const float4 ot = rec.lo, dd = rec.hi;
                 const F3 org = f3(ot.x, ot.y, ot.z), dir = f3(dd.x, dd.y, dd.z);
@@ -1060,7 +1404,7 @@ __global__ void __launch_bounds__(kRerenderThreads, ARV2_RR_MINB) rerender_kerne
         if (have) {
 #pragma unroll 1
             for (int burst = 0; burst < 2 && have && !found; ++burst) {
-                const float4* rec = p.pc_seg + 2 * ((size_t)ray * (size_t)p.pc_stride + (size_t)k);
+                const float4* rec = p.pc_seg + 2 * (base + (size_t)k);
                 if (k + 4 < n) prefetch_l2(rec + 8);                 // the next lines of this ray: the scan is otherwise a
                 if (k + 8 < n) prefetch_l2(rec + 16);                // chain of dependent DRAM round trips
                 const F8 r0 = ldg256(rec);
@@ -1090,159 +1434,82 @@ __global__ void __launch_bounds__(kRerenderThreads, ARV2_RR_MINB) rerender_kerne
 }
 
 // ---------------------------------------------------------------------------------------
-// Data-parallel re-render (experiment, ARV2_RR_PARALLEL=1; measured SLOWER than the persistent kernel, which stays
-// the default: 1.2 ms against 0.61 ms on C2, profiles/r07_trace_experiments.md section 8).  The persistent kernel
-// above walks every ray's cached segments in order: a chain of dependent DRAM round trips per lane (0.61 ms for
-// 27 M segments, 4x the HBM time of the cache).  Here the order is restored afterwards instead:
-//   rr_scan     one warp per ray, lane k tests cached segment k against the receiver's bounding ball (coalesced
-//               1 KB reads, no dependence between rays) and appends the candidates (ray, k) to a global list;
-//   rr_walk     one lane per candidate walks the receiver tree; a hit stores (bin, ear, weighted energy) and lowers
-//               rr_first[ray] to its k with atomicMin;
-//   rr_resolve  the candidate whose k equals rr_first[ray] deposits (the trace would have ended that ray there);
-//               rays without a hit are closed as misses.
-// The scan does run at 4.5 TB/s (0.36 ms cold, reading all 50 slots of every ray), but the walks behind a ray's
-// first hit are not "a few": 473 M warp instructions at 7 lanes for the walk pass alone, more than the whole
-// persistent kernel (330 M).
-constexpr int kRrThreads = 256;
+// Packing the freshly traced cache: exclusive scan of the per-ray segment counts (three small kernels), then one warp
+// per ray moves its records and energies to their CSR place and writes the quantised path vertices.
+constexpr int kScanBlock = 256, kScanPerThread = 8, kScanTile = kScanBlock * kScanPerThread;
+
+__global__ void __launch_bounds__(kScanBlock) pc_tile_sums_kernel(const int* __restrict__ nseg, long long n, unsigned long long* __restrict__ sums)
+{
+    __shared__ unsigned long long sh[kScanBlock / 32];
+    const long long t0 = (long long)blockIdx.x * kScanTile;
+    unsigned long long s = 0;
+    for (int j = 0; j < kScanPerThread; ++j) { const long long i = t0 + (long long)j * kScanBlock + threadIdx.x; if (i < n) s += (unsigned)nseg[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long t = 0; for (int w = 0; w < kScanBlock / 32; ++w) t += sh[w]; sums[blockIdx.x] = t; }
+}
+
+__global__ void pc_scan_sums_kernel(unsigned long long* sums, long long n_tiles)      // one thread: a few thousand tiles
+{
+    unsigned long long run = 0;
+    for (long long i = 0; i < n_tiles; ++i) { const unsigned long long v = sums[i]; sums[i] = run; run += v; }
+    sums[n_tiles] = run;
+}
+
+__global__ void __launch_bounds__(kScanBlock) pc_offsets_kernel(const int* __restrict__ nseg, long long n, const unsigned long long* __restrict__ sums,
+                                                                unsigned long long* __restrict__ off)
+{
+    __shared__ unsigned long long sh[kScanBlock];
+    const long long i0 = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanPerThread;     // 8 consecutive rays per thread
+    unsigned v[kScanPerThread];
+    unsigned long long s = 0;
+    for (int j = 0; j < kScanPerThread; ++j) { v[j] = i0 + j < n ? (unsigned)nseg[i0 + j] : 0u; s += v[j]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < kScanBlock; d <<= 1) {            // Hillis-Steele inclusive scan of the thread totals
+        const unsigned long long add = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    unsigned long long run = sums[blockIdx.x] + sh[threadIdx.x] - s;
+    for (int j = 0; j < kScanPerThread; ++j) { if (i0 + j < n) off[i0 + j] = run; run += v[j]; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) off[n] = sums[gridDim.x];
+}
+
+__device__ __forceinline__ uint2 quantise_vertex(const TraceParams& p, float x, float y, float z, unsigned flags)
+{
+    const unsigned qx = (unsigned)fminf(fmaxf(rintf((x - p.pc_q0[0]) / p.pc_qs[0]), 0.f), 65535.f);
+    const unsigned qy = (unsigned)fminf(fmaxf(rintf((y - p.pc_q0[1]) / p.pc_qs[1]), 0.f), 65535.f);
+    const unsigned qz = (unsigned)fminf(fmaxf(rintf((z - p.pc_q0[2]) / p.pc_qs[2]), 0.f), 65535.f);
+    return make_uint2(qx | (qy << 16), qz | flags);
+}
 
 template <int NB>
-__global__ void __launch_bounds__(kRrThreads) rr_scan_kernel(const TraceParams p)
+__global__ void __launch_bounds__(256) pc_compact_kernel(const TraceParams p, const float4* __restrict__ src_seg, const float* __restrict__ src_energy,
+                                                         uint2* __restrict__ vert)
 {
-    // candidates are collected per warp and appended 32 at a time: one atomic per 32 candidates on the list's
-    // counter (one per ray with a candidate serialised the kernel on that address: 2 ms, r07)
-    __shared__ int2 sh_buf[kRrThreads / 32][64];
-    int2* const buf = sh_buf[threadIdx.x >> 5];
-    int n_buf = 0;                                            // warp-uniform
     const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int stride = (int)p.pc_stride;
-    auto flush = [&](int count) {                             // the first `count` (<= 32) buffered candidates
-        unsigned long long b = 0;
-        if (lane == 0) b = atomicAdd(p.counters + 2, (unsigned long long)count);
-        b = __shfl_sync(FULL, b, 0);
-        const long long idx = (long long)b + lane;
-        if (lane < count && idx < p.rr_cap) p.rr_cand[idx] = buf[lane];
-        __syncwarp();
-        if (lane + 32 < n_buf) buf[lane] = buf[lane + 32];    // n_buf <= 64: what is left moves to the front
-        n_buf -= count;
-        __syncwarp();
-    };
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long ray = warp0; ray < p.n_rays; ray += n_warps) {
-        const float4* base = p.pc_seg + 2 * (size_t)ray * (size_t)stride;
-        // the first 32 records are fetched together with the ray's segment count (no dependent round trip)
-        const int n = __ldg(p.pc_nseg + ray);
-        F8 rec;
-        rec.lo = make_float4(0.f, 0.f, 0.f, 0.f); rec.hi = rec.lo;
-        if (lane < stride) rec = ldg256(base + 2 * lane);
-        for (int k0 = 0; k0 < n; k0 += 32) {
-            const int k = k0 + lane;
-            if (k0 > 0 && k < n) rec = ldg256(base + 2 * k);
-            const bool cand = k < n && enters_receiver_ball(p, f3(rec.lo.x, rec.lo.y, rec.lo.z), f3(rec.hi.x, rec.hi.y, rec.hi.z), rec.lo.w);
-            const unsigned m = __ballot_sync(FULL, cand);
-            if (m) {
-                if (cand) buf[n_buf + __popc(m & lt)] = make_int2((int)ray, k);
-                n_buf += __popc(m);
-                __syncwarp();
-                if (n_buf >= 32) flush(32);
-            }
+        const int n = (int)(p.pc_off[ray + 1] - p.pc_off[ray]);
+        const unsigned long long o0 = p.pc_off[ray] + (unsigned long long)ray;      // records share the vertices' index space
+        const size_t src = (size_t)ray * (size_t)p.pc_stride;
+        uint2* const v = vert + o0;
+        if (n == 0 && lane == 0) v[0] = quantise_vertex(p, p.emitter[0], p.emitter[1], p.emitter[2], 0u);
+        for (int k = lane; k < n; k += 32) {
+            const F8 rec = ldg256(src_seg + 2 * (src + k));
+            stg256(p.pc_seg + 2 * (o0 + k), rec.lo, rec.hi);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) p.pc_energy[(o0 + k) * NB + b] = src_energy[(src + k) * NB + b];
+            const bool escapes = !(rec.lo.w < 1e20f);
+            v[k] = quantise_vertex(p, rec.lo.x, rec.lo.y, rec.lo.z, kVertSegment | (escapes ? kVertEscapes : 0u));
+            // the end point of the ray's last segment (every other segment ends where the next one starts, 1 mm off the wall)
+            if (k == n - 1) v[n] = escapes ? make_uint2(0u, 0u) : quantise_vertex(p, fmaf(rec.lo.w, rec.hi.x, rec.lo.x), fmaf(rec.lo.w, rec.hi.y, rec.lo.y), fmaf(rec.lo.w, rec.hi.z, rec.lo.z), 0u);
         }
     }
-    if (n_buf > 0) flush(n_buf);
-}
-
-template <int NB>
-__global__ void __launch_bounds__(kRrThreads) rr_walk_kernel(const TraceParams p)
-{
-    const unsigned long long found = p.counters[2];
-    const long long n_cand = (long long)(found < (unsigned long long)p.rr_cap ? found : (unsigned long long)p.rr_cap);
-    Traversal tr;
-    int stack[kStack];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (long long)gridDim.x * blockDim.x) {
-        const int2 c = p.rr_cand[i];
-        const size_t ci = (size_t)c.x * (size_t)p.pc_stride + (size_t)c.y;
-        const F8 rec = ldg256(p.pc_seg + 2 * ci);
-        const float4 ot = rec.lo, dd = rec.hi;
-        const F3 org = f3(ot.x, ot.y, ot.z), dir = f3(dd.x, dd.y, dd.z);
-        closest_hit(p, stack, tr, p.recv_root, org, dir, ot.w);
-        const Hit& h = tr.h;
-        int2 res = make_int2(-1, 0);
-        if (h.slot >= 0 && h.t < ot.w) {
-            const F8 A = ldg256(p.tris + h.slot * 4), B = ldg256(p.tris + h.slot * 4 + 2);
-            const int mat = __float_as_int(A.hi.w);
-            const F3 pt = hit_point(f3(A.lo.x, A.lo.y, A.lo.z), f3(A.hi.x, A.hi.y, A.hi.z), f3(B.lo.x, B.lo.y, B.lo.z), h.u, h.v);
-            const F3 dp = sub3(pt, org);
-            const float dist = __fadd_rn(dd.w, __fsqrt_rn(dot3(dp, dp)));
-            float energy[NB];
-#pragma unroll
-            for (int b = 0; b < NB; ++b) energy[b] = p.pc_energy[ci * NB + b];
-            res.x = receiver_hit<NB>(p, pt, dir, dist, energy);
-            res.y = (mat == -1) ? 1 : 2;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) p.rr_energy[(size_t)i * NB + b] = energy[b];
-            atomicMin(p.rr_first + c.x, c.y);
-        }
-        p.rr_res[i] = res;
-    }
-}
-
-template <int NB>
-__global__ void __launch_bounds__(kRrThreads) rr_resolve_kernel(const TraceParams p)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned long long found = p.counters[2];
-    const long long n_cand = (long long)(found < (unsigned long long)p.rr_cap ? found : (unsigned long long)p.rr_cap);
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n_thr = (long long)gridDim.x * blockDim.x;
-    unsigned long long segs = 0;
-    // hits: only a ray's first one counts (warp-uniform trip count: deposit_warp is a warp collective)
-    for (long long i0 = tid - lane; i0 < n_cand; i0 += n_thr) {
-        const long long i = i0 + lane;
-        bool dep = false;
-        int bin = -1, primary = 0;
-        float energy[NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) energy[b] = 0.f;
-        if (i < n_cand) {
-            const int2 res = p.rr_res[i];
-            if (res.y != 0) {
-                const int2 c = p.rr_cand[i];
-                if (p.rr_first[c.x] == c.y) {
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) energy[b] = p.rr_energy[(size_t)i * NB + b];
-                    bin = res.x; primary = res.y - 1;
-                    dep = bin >= 0 && bin < p.ir_len;
-                    if (p.rec_bin) p.rec_bin[c.x] = bin;
-                    if (p.rec_ear) p.rec_ear[c.x] = res.y;
-                    if (p.rec_nseg) p.rec_nseg[c.x] = c.y + 1;
-                    if (p.rec_energy) {
-#pragma unroll
-                        for (int b = 0; b < NB; ++b) p.rec_energy[(size_t)c.x * NB + b] = energy[b];
-                    }
-                    segs += (unsigned long long)(c.y + 1);
-                }
-            }
-        }
-        deposit_warp<NB>(p, dep, bin, primary, energy);
-    }
-    // misses: every cached segment passed
-    for (long long r = tid; r < p.n_rays; r += n_thr) {
-        if (p.rr_first[r] == kRrNoHit) {
-            const int n = p.pc_nseg[r];
-            if (p.rec_bin) p.rec_bin[r] = -1;
-            if (p.rec_ear) p.rec_ear[r] = 0;
-            if (p.rec_nseg) p.rec_nseg[r] = n;
-            if (p.rec_energy) {
-#pragma unroll
-                for (int b = 0; b < NB; ++b) p.rec_energy[(size_t)r * NB + b] = 0.f;
-            }
-            segs += (unsigned long long)n;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
-    if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
 }
 
 __device__ __forceinline__ unsigned spread16(unsigned v)
@@ -1317,6 +1584,26 @@ cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaS
 {
     if (p.n_rays == 0) return cudaSuccess;
     if (bands != 1 && bands != 8) return cudaErrorInvalidValue;
+    if (!p.pc_vert || !p.pc_bits || !p.pc_off) return cudaErrorInvalidValue;
+    const long long tiles = (p.pc_nvert + kMaskTile - 1) / kMaskTile;      // one warp per tile and trip
+    long long grid = (tiles + kRrThreads / 32 - 1) / (kRrThreads / 32);
+    const long long cap = (long long)sm_count * (2048 / kRrThreads) * 2;
+    if (grid > cap) grid = cap;
+    rr_mask_kernel<<<(unsigned)grid, kRrThreads, 0, stream>>>(p);
+    long long wgrid = (p.n_rays + kRrThreads - 1) / kRrThreads;
+    long long wcap = (long long)sm_count * ARV2_RRW_MINB;
+    if (const char* e = getenv("ARV2_RRW_CTAS")) wcap = (long long)sm_count * (atoi(e) > 0 ? atoi(e) : ARV2_RRW_MINB);      // tuning aid
+    if (wgrid > wcap) wgrid = wcap;
+    const size_t smem = (size_t)p.recv_nodes_shared * 64;
+    if (bands == 1) rr_walk_kernel<1><<<(unsigned)wgrid, kRrThreads, smem, stream>>>(p);
+    else rr_walk_kernel<8><<<(unsigned)wgrid, kRrThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rerender_serial(const TraceParams& p, int bands, int sm_count, cudaStream_t stream)
+{
+    if (p.n_rays == 0) return cudaSuccess;
+    if (bands != 1 && bands != 8) return cudaErrorInvalidValue;
     int per_sm = 0;
     cudaError_t e = bands == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rerender_kernel<1>, kRerenderThreads, 0)
                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rerender_kernel<8>, kRerenderThreads, 0);
@@ -1329,23 +1616,25 @@ cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaS
     return cudaGetLastError();
 }
 
-template <int NB>
-static cudaError_t launch_rerender_parallel_t(const TraceParams& p, int sm_count, cudaStream_t stream)
+cudaError_t launch_cache_offsets(const int* nseg, long long n_rays, unsigned long long* off, unsigned long long* scratch, cudaStream_t stream)
 {
-    const unsigned grid = (unsigned)(sm_count * (2048 / kRrThreads));
-    rr_scan_kernel<NB><<<grid, kRrThreads, 0, stream>>>(p);
-    rr_walk_kernel<NB><<<grid, kRrThreads, 0, stream>>>(p);
-    rr_resolve_kernel<NB><<<grid, kRrThreads, 0, stream>>>(p);
+    if (n_rays <= 0) return cudaSuccess;
+    const long long tiles = (n_rays + kScanTile - 1) / kScanTile;
+    pc_tile_sums_kernel<<<(unsigned)tiles, kScanBlock, 0, stream>>>(nseg, n_rays, scratch);
+    pc_scan_sums_kernel<<<1, 1, 0, stream>>>(scratch, tiles);
+    pc_offsets_kernel<<<(unsigned)tiles, kScanBlock, 0, stream>>>(nseg, n_rays, scratch, off);
     return cudaGetLastError();
 }
 
-cudaError_t launch_rerender_parallel(const TraceParams& p, int bands, int sm_count, cudaStream_t stream)
+cudaError_t launch_cache_compact(const TraceParams& p, const float4* src_seg, const float* src_energy, uint2* vert, int bands, cudaStream_t stream)
 {
-    if (p.n_rays == 0) return cudaSuccess;
-    if (!p.rr_cand || !p.rr_res || !p.rr_energy || !p.rr_first) return cudaErrorInvalidValue;
-    if (bands == 1) return launch_rerender_parallel_t<1>(p, sm_count, stream);
-    if (bands == 8) return launch_rerender_parallel_t<8>(p, sm_count, stream);
-    return cudaErrorInvalidValue;
+    if (p.n_rays <= 0) return cudaSuccess;
+    long long grid = (p.n_rays * 32 + 255) / 256;
+    if (grid > 148LL * 64) grid = 148LL * 64;
+    if (bands == 1) pc_compact_kernel<1><<<(unsigned)grid, 256, 0, stream>>>(p, src_seg, src_energy, vert);
+    else if (bands == 8) pc_compact_kernel<8><<<(unsigned)grid, 256, 0, stream>>>(p, src_seg, src_energy, vert);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_direction_keys(unsigned long long seed, long long ray_begin, long long n, unsigned* keys, int* vals, cudaStream_t stream)

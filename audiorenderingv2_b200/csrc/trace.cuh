@@ -19,11 +19,22 @@ struct TraceParams {
     double* hist;               // [2][bands][ir_len] fp64 accumulation
     unsigned long long* counters; // [0] next ray chunk, [1] segments traced, [7] watchdog
     int* rec_bin; int* rec_ear; float* rec_energy; int* rec_nseg;   // optional per-ray records
-    // receiver-independent path cache (optional), ray-major: segment k of ray r at [r*stride + k]
+    // receiver-independent path cache (optional).  While it is being filled (launch_trace mode 1) it is ray-major with
+    // a fixed stride: segment k of ray r at [r*pc_stride + k].  launch_cache_compact then packs it (CSR): the segments
+    // of ray r are [pc_off[r], pc_off[r+1]), and adds the quantised path vertices the re-render scans.
     float4* pc_seg;             // 32 B per cached segment: (origin.xyz, t_wall or 1e20 on miss), (dir.xyz, distance before)
-    float* pc_energy;           // [r*stride + k][bands]
-    int* pc_nseg;               // [r] segments cached
-    long long pc_stride;        // records per ray (>= max_bounces)
+    float* pc_energy;           // [segment][bands] energy the segment starts with
+    int* pc_nseg;               // [r] segments cached (filling only)
+    long long pc_stride;        // records per ray while filling (>= max_bounces)
+    const unsigned long long* pc_off;   // [n_rays + 1] CSR offsets
+    // path vertices, 8 B each = (x, y, z) on a 16-bit grid over the scene bounds + flags; ray r owns vertices
+    // [pc_off[r] + r, pc_off[r+1] + r + 1): the origins of its segments and the end point of the last one.
+    // flags bit 0: a segment starts at this vertex; bit 1: that segment leaves the scene (no end point).
+    const uint2* pc_vert;
+    unsigned* pc_bits;          // one bit per vertex: its segment may enter the receiver's bounding ball
+    long long pc_nvert;
+    float pc_q0[3], pc_qs[3];   // vertex = pc_q0 + q * pc_qs per axis
+    float pc_eps;               // what a true segment may stray from the line through its two quantised vertices
     unsigned long long seed;
     long long ray_begin, n_rays;
     float emitter[3], center[3];
@@ -33,18 +44,13 @@ struct TraceParams {
     int delay, ir_len, mono;
     int root;                   // node the full trace starts at (0 = two-level top node)
     int scene_root, recv_root;  // roots of the two sub-trees (-1: absent)
+    int recv_nodes_shared;      // rr_walk_kernel: nodes of the receiver tree (from recv_root on) to keep in shared memory, 0 = none
     int any_scatter;            // 0: skip the diffuse-bounce RNG entirely
     // breadth-first tracer (wave_kernel; optional): per-SM, per-depth queues of path states
     float4* wave_paths;         // [sm][wave_queues][wave_cap][cont_f4(bands)]
     long long wave_cap;         // ring slots per queue = most paths alive per SM
     int wave_queues;            // queue j holds paths of depth (j + 1) * wave_segments
     int wave_segments;          // segments per task
-    // data-parallel re-render (rr_scan / rr_walk / rr_resolve kernels; optional): candidate list and per-ray first hit
-    int2* rr_cand;              // [rr_cap] (ray, k) of every cached segment that enters the receiver's bounding ball
-    int2* rr_res;               // [rr_cap] (bin, ear) of the candidate's receiver hit, ear 0 = the walk missed
-    float* rr_energy;           // [rr_cap][bands] chord-weighted energy of the hit
-    int* rr_first;              // [n_rays] smallest k with a receiver hit (pre-set to 0x7f7f7f7f)
-    long long rr_cap;           // counters[2] = candidates found (may exceed rr_cap: the caller then falls back)
     const int* ray_order;       // optional: the order in which the launch's rays [0, n_rays) are started (direction-sorted)
     int chunk;                  // rays a warp claims per global atomic
     int refill_below;           // lanes of a warp are refilled only while fewer than this many hold a path (32 = always)
@@ -60,11 +66,18 @@ int trace_supports_wide_nodes();
 // mode 0: full trace (scene + receiver), deposits into hist.
 // mode 1: scene-only trace that fills the path cache (no deposits).
 cudaError_t launch_trace(const TraceParams& p, int bands, int mode, int sm_count, cudaStream_t stream);
-// Re-deposit from the path cache against the current receiver sub-tree: persistent per-ray scan (fallback) ...
+// Pack the freshly filled ray-major cache (src_*; stride p.pc_stride, counts p.pc_nseg) into the CSR arrays
+// (p.pc_seg / p.pc_energy as destinations, p.pc_off already scanned) and write the quantised path vertices.
+cudaError_t launch_cache_offsets(const int* nseg, long long n_rays, unsigned long long* off, unsigned long long* scratch, cudaStream_t stream);
+cudaError_t launch_cache_compact(const TraceParams& p, const float4* src_seg, const float* src_energy, uint2* vert, int bands, cudaStream_t stream);
+// Re-deposit from the packed path cache against the current receiver sub-tree:
+//   rr_mask_kernel   streams the 8 B path vertices (coalesced, no dependence between rays) and writes one bit per
+//                    segment: "may enter the receiver's bounding ball" (conservative);
+//   rr_walk_kernel   per ray, in order: the flagged segments are walked through the receiver tree with their exact
+//                    32 B record until the first hit (t_recv < t_wall), which deposits -- what a fresh trace does.
 cudaError_t launch_rerender(const TraceParams& p, int bands, int sm_count, cudaStream_t stream);
-// ... and the data-parallel version (needs p.rr_*; rr_first pre-set to 0x7f bytes, counters zeroed).
-cudaError_t launch_rerender_parallel(const TraceParams& p, int bands, int sm_count, cudaStream_t stream);
-constexpr int kRrNoHit = 0x7f7f7f7f;
+// the r06 persistent per-ray scan of the 32 B records on the same CSR arrays (A/B: ARV2_RR_SERIAL=1)
+cudaError_t launch_rerender_serial(const TraceParams& p, int bands, int sm_count, cudaStream_t stream);
 // hist (fp64) -> ir_left / ir_right (fp32); mono: L = R = L + R (OR/kernels.cu:519-527).
 cudaError_t launch_finalize(const double* hist, int bands, int ir_len, int mono, float* ir_left, float* ir_right,
                             cudaStream_t stream);

@@ -199,6 +199,9 @@ int arv2_ir_device(arv2_ctx* ctx, float** d_left, float** d_right);
 int arv2_hist_device(arv2_ctx* ctx, double** d_hist, int64_t* count);
 /* Host->device bytes of the last receiver placement (top node + receiver tree + triangles). */
 int arv2_last_upload_bytes(arv2_ctx* ctx, int64_t* bytes);
+/* The receiver-independent path cache arv2_rerender scans (desc.path_cache, after one arv2_render): cached segments
+ * of the whole ray set and the device bytes they occupy (32 B record + 4 B x bands energy + 8 B scan vertex each). */
+int arv2_path_cache_info(arv2_ctx* ctx, int64_t* segments, int64_t* bytes);
 /* Segments (closest-hit queries) traced by the last render on this context. */
 int arv2_last_segments(arv2_ctx* ctx, int64_t* segments);
 /* Per-ray records of the last render (desc.record_rays), indexed by the ray's position in the

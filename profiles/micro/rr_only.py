@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT)
 import torch, bench
 import audiorenderingv2_b200 as arv
 torch.cuda.set_device(0)
+bench.select_workload(os.environ.get("RR_WORKLOAD", "c2"))
 tv, tm, names, mats = bench.scene_case()
 recv = bench.load_receiver()
 scene = arv.Scene.from_triangles(tv, tm, names)

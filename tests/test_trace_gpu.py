@@ -120,12 +120,11 @@ def test_sharded_ranges_equal_full(golden_scenes, golden_receiver):
     assert np.allclose(l2, l, rtol=1e-6, atol=0) and np.allclose(rr2, rr, rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize("env", [{}, {"ARV2_RR_PARALLEL": "1"}, {"ARV2_RR_PARALLEL": "1", "ARV2_RR_CAP": "64"}],
-                         ids=["per-ray", "parallel", "parallel-overflow-fallback"])
+@pytest.mark.parametrize("env", [{}, {"ARV2_RR_SERIAL": "1"}], ids=["mask+walk", "serial-scan"])
 def test_path_cache_rerender_equals_render(golden_scenes, golden_receiver, monkeypatch, env):
-    """Receiver moves re-deposit from cached receiver-independent paths; the result must
-    equal a fresh full trace ray for ray -- through the persistent per-ray kernel (default), the data-parallel
-    kernels (scan / walk / resolve, opt-in), and the fallback from those when the candidate list overflows."""
+    """Receiver moves re-deposit from cached receiver-independent paths; the result must equal a fresh full trace ray
+    for ray -- through the two data-parallel passes (8 B vertex stream -> flag bits, then ordered exact walks; default)
+    and through the serial per-ray scan of the 32 B records (A/B switch)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     case = Case(golden_scenes["caja_verts"], golden_scenes["caja_mesh"], golden_scenes["caja_names"], golden_receiver,
