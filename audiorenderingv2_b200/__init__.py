@@ -98,16 +98,29 @@ SYMBOLS = {
     "arv2_render_range": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
     "arv2_finalize": (C.c_int, [_vp]),
     "arv2_rerender": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "arv2_comm_unique_id": (C.c_int, [_vp]),
+    "arv2_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _vp, C.POINTER(_vp)]),
+    "arv2_comm_info": (C.c_int, [_vp, _ip, _ip, _ip]),
+    "arv2_comm_destroy": (None, [_vp]),
+    "arv2_shard_range": (None, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "arv2_render_sharded": (C.c_int, [_vp, _vp, C.POINTER(C.c_double)]),
+    "arv2_multi_create": (C.c_int, [_vp, _vp, C.POINTER(RendererDesc), _ip, C.c_int32, C.POINTER(_vp)]),
+    "arv2_multi_size": (C.c_int32, [_vp]),
+    "arv2_multi_ctx": (_vp, [_vp, C.c_int32]),
+    "arv2_multi_render": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "arv2_multi_destroy": (None, [_vp]),
     "arv2_ir_length": (C.c_int, [_vp, _ip, _ip]),
     "arv2_get_ir": (C.c_int, [_vp, _fp, _fp]),
     "arv2_set_ir": (C.c_int, [_vp, _fp, _fp]),
     "arv2_ir_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "arv2_hist_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "arv2_path_cache_info": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "arv2_last_counters": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int32]),
     "arv2_last_segments": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "arv2_last_upload_bytes": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "arv2_get_records": (C.c_int, [_vp, C.c_int64, _ip, _ip, _fp, _ip, C.POINTER(C.c_int64)]),
     "arv2_write_ir_text": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    "arv2_write_convolved_text": (C.c_int, [C.c_char_p, C.c_char_p, _fp, _fp, C.c_size_t]),
     "arv2_convolve_file": (C.c_int, [_vp, _fp, C.c_size_t, _fp, _fp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "arv2_stream_open": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
     "arv2_stream_set_ir": (C.c_int, [_vp, C.c_int32, _fp, _fp]),
@@ -289,37 +302,88 @@ def config_materials(cfg: Config):
     return [(cfg.material_names[i].value.decode(), cfg.material_absorption[i]) for i in range(cfg.n_materials)]
 
 
+COMM_ID_BYTES = 128
+
+
+def _make_desc(ir_length_in_seconds, sample_rate, materials, rays_per_dimension, bands, device, record_rays, path_cache, bvh_builder):
+    """arv2_renderer_desc + the byte strings / array it points into (keep them alive while it is used)."""
+    d = RendererDesc()
+    d.ir_length_in_seconds = int(ir_length_in_seconds)
+    d.sample_rate = int(sample_rate)
+    d.rays_x, d.rays_y, d.rays_z = (int(v) for v in rays_per_dimension)
+    d.bands = bands; d.device = device
+    d.record_rays = 1 if record_rays else 0
+    d.path_cache = 1 if path_cache else 0
+    d.bvh_builder = bvh_builder
+    arr = (Material * max(1, len(materials)))()
+    keep = [arr]
+    for i, m in enumerate(materials):
+        name, a = m[0], m[1]
+        b = name.encode(); keep.append(b)
+        arr[i].name = b
+        vals = list(a) if isinstance(a, (list, tuple, np.ndarray)) else [a] * MAX_BANDS
+        for k in range(MAX_BANDS):
+            arr[i].mat_absorption[k] = float(vals[min(k, len(vals) - 1)])
+        arr[i].scattering = float(m[2]) if len(m) > 2 else 0.0
+    d.materials = arr; d.n_materials = len(materials)
+    return d, keep
+
+
+def shard_range(n_rays, rank, n_ranks):
+    """The contiguous slice (begin, count) of the seeded ray set rank `rank` of `n_ranks` traces."""
+    b = C.c_int64(); c = C.c_int64()
+    lib().arv2_shard_range(int(n_rays), int(rank), int(n_ranks), C.byref(b), C.byref(c))
+    return b.value, c.value
+
+
+class Comm:
+    """One NCCL rank inside libarv2 (arv2_comm_*).  `Comm.unique_id()` on one rank, the 128 bytes handed to the
+    others by any transport (torch.distributed broadcast, a file, MPI ...), then `Comm(device, rank, n, id)` on each."""
+
+    def __init__(self, device, rank, n_ranks, unique_id: bytes):
+        assert len(unique_id) == COMM_ID_BYTES
+        self._h = _vp()
+        buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
+        _check(lib().arv2_comm_create(int(device), int(rank), int(n_ranks), C.cast(buf, _vp), C.byref(self._h)))
+        self.rank, self.n_ranks = rank, n_ranks
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        _check(lib().arv2_comm_unique_id(C.cast(buf, _vp)))
+        return buf.raw
+
+    def nccl_version(self):
+        v = C.c_int32()
+        _check(lib().arv2_comm_info(self._h, None, None, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.arv2_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
 class AudioRenderer:
     """Mirror of class AudioRenderer (OR/AudioRenderer.h:16-152) over the C ABI."""
 
     def __init__(self, model: Scene, ir_length_in_seconds, sample_rate, materials, rays_per_dimension,
                  receiver: Receiver | None = None, bands=1, device=0, record_rays=False, path_cache=False,
-                 bvh_builder=0):
+                 bvh_builder=0, _borrowed=None):
         """materials: [(name, absorption | [absorption per band], scattering=0)]."""
-        d = RendererDesc()
-        d.ir_length_in_seconds = int(ir_length_in_seconds)
-        d.sample_rate = int(sample_rate)
-        d.rays_x, d.rays_y, d.rays_z = (int(v) for v in rays_per_dimension)
-        d.bands = bands; d.device = device
-        d.record_rays = 1 if record_rays else 0
-        d.path_cache = 1 if path_cache else 0
-        d.bvh_builder = bvh_builder
-        arr = (Material * max(1, len(materials)))()
-        self._keep = []
-        for i, m in enumerate(materials):
-            name, a = m[0], m[1]
-            b = name.encode(); self._keep.append(b)
-            arr[i].name = b
-            vals = list(a) if isinstance(a, (list, tuple, np.ndarray)) else [a] * MAX_BANDS
-            for k in range(MAX_BANDS):
-                arr[i].mat_absorption[k] = float(vals[min(k, len(vals) - 1)])
-            arr[i].scattering = float(m[2]) if len(m) > 2 else 0.0
-        d.materials = arr; d.n_materials = len(materials)
-        self._h = _vp()
         self.bands = bands
-        self.n_rays = d.rays_x * d.rays_y * d.rays_z
+        self.n_rays = int(rays_per_dimension[0]) * int(rays_per_dimension[1]) * int(rays_per_dimension[2])
         self.sample_rate = int(sample_rate)
-        _check(lib().arv2_create(model._h, receiver._h if receiver is not None else None, C.byref(d), C.byref(self._h)))
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self._h = _vp(_borrowed)                  # a context owned by a MultiRenderer
+        else:
+            d, self._keep = _make_desc(ir_length_in_seconds, sample_rate, materials, rays_per_dimension, bands, device,
+                                       record_rays, path_cache, bvh_builder)
+            self._h = _vp()
+            _check(lib().arv2_create(model._h, receiver._h if receiver is not None else None, C.byref(d), C.byref(self._h)))
         n = C.c_int32(); b = C.c_int32()
         _check(lib().arv2_ir_length(self._h, C.byref(n), C.byref(b)))
         self.ir_length = n.value
@@ -368,6 +432,12 @@ class AudioRenderer:
     def finalize(self):
         _check(lib().arv2_finalize(self._h))
 
+    def render_sharded(self, comm: "Comm"):
+        """This rank's slice + NCCL all-reduce of the histogram + finalise, inside the library (collective)."""
+        ms = C.c_double()
+        _check(lib().arv2_render_sharded(self._h, comm._h, C.byref(ms)))
+        return ms.value
+
     def rerender(self):
         ms = C.c_double()
         _check(lib().arv2_rerender(self._h, C.byref(ms)))
@@ -398,6 +468,12 @@ class AudioRenderer:
         s = C.c_int64()
         _check(lib().arv2_last_segments(self._h, C.byref(s)))
         return s.value
+
+    def last_counters(self, n=24):
+        """Launch counters of the last render (arv2_last_counters; traversal tallies need the stats build)."""
+        out = (C.c_uint64 * n)()
+        _check(lib().arv2_last_counters(self._h, out, n))
+        return [int(v) for v in out]
 
     def path_cache_info(self):
         """(cached segments, device bytes) of the receiver-independent path cache."""
@@ -434,7 +510,41 @@ class AudioRenderer:
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:
-            _lib.arv2_destroy(self._h)
+            if self._owned:
+                _lib.arv2_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class MultiRenderer:
+    """One process, several GPUs (arv2_multi_*): one context and one NCCL rank per device, a render runs
+    arv2_render_sharded on one host thread per device.  `self.renderers[i]` is the context of device i
+    (set parameters on all of them with `each`); every device ends up with the full IR."""
+
+    def __init__(self, model: Scene, ir_length_in_seconds, sample_rate, materials, rays_per_dimension, devices,
+                 receiver: Receiver | None = None, bands=1, record_rays=False, bvh_builder=0):
+        d, self._keep = _make_desc(ir_length_in_seconds, sample_rate, materials, rays_per_dimension, bands, 0, record_rays, False, bvh_builder)
+        dev = (C.c_int32 * len(devices))(*[int(x) for x in devices])
+        self._h = _vp()
+        _check(lib().arv2_multi_create(model._h, receiver._h if receiver is not None else None, C.byref(d), dev, len(devices), C.byref(self._h)))
+        self.renderers = [AudioRenderer(model, ir_length_in_seconds, sample_rate, materials, rays_per_dimension, bands=bands,
+                                        _borrowed=lib().arv2_multi_ctx(self._h, i)) for i in range(lib().arv2_multi_size(self._h))]
+
+    def each(self, fn):
+        for r in self.renderers:
+            fn(r)
+
+    def render(self):
+        ms = C.c_double()
+        _check(lib().arv2_multi_render(self._h, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            for r in self.renderers:
+                r._h = None
+            _lib.arv2_multi_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -538,6 +648,12 @@ def live_callback(stream: "ConvStream", samples, ring: Ring):
     """audioHandlerWithMic + convoluteLiveInput for one block of mic samples."""
     x = np.ascontiguousarray(samples, dtype=np.float64)
     _check(lib().arv2_live_callback(stream._h, x.ctypes.data_as(C.POINTER(C.c_double)), x.size, ring._h))
+
+
+def write_convolved_text(left_path, right_path, left, right):
+    """output_convolute_left.txt / output_convolute_right.txt of the reference (OR/AudioRenderer.cpp:720-744)."""
+    l = np.ascontiguousarray(left, dtype=np.float32); r = np.ascontiguousarray(right, dtype=np.float32)
+    _check(lib().arv2_write_convolved_text(os.fsencode(left_path), os.fsencode(right_path), _f(l), _f(r), l.size))
 
 
 def wav_read(path):

@@ -14,6 +14,7 @@
 
 #include "arv2_internal.h"
 #include "bvh_lbvh.cuh"
+#include "comm.cuh"
 #include "conv.cuh"
 #include "trace.cuh"
 
@@ -28,6 +29,8 @@ using namespace arv2;
 
 struct arv2_scene { HostScene s; };
 struct arv2_receiver { HostReceiver r; };
+struct arv2_comm { int device = 0, rank = 0, n_ranks = 1; ncclComm_t comm = nullptr; };
+struct arv2_multi { std::vector<arv2_ctx*> ctx; std::vector<arv2_comm*> comm; };
 
 #define CK(expr)                                                                                       \
     do {                                                                                               \
@@ -76,7 +79,8 @@ struct arv2_ctx {
     int32_t scene_root_code = 1;     // node the scene tree is entered at: 1 (binary) or kWideBit | 0
     float qk[3] = {1.f, 1.f, 1.f}, qinvk[3] = {1.f, 1.f, 1.f}, qc[3] = {0.f, 0.f, 0.f};   // grid of the quantised nodes (any grid serves the float nodes)
     float* d_keep = nullptr; float* d_scatter = nullptr;
-    double* d_hist = nullptr; float* d_ir_l = nullptr; float* d_ir_r = nullptr;
+    double* d_hist = nullptr; float* d_ir_l = nullptr; float* d_ir_r = nullptr;     // d_ir_r = d_ir_l + bands * ir_len (one allocation)
+    float* h_ir = nullptr;                        // pinned staging of both ears for arv2_get_ir
     unsigned long long* d_counters = nullptr;
     int* d_rec_bin = nullptr; int* d_rec_ear = nullptr; int* d_rec_nseg = nullptr; float* d_rec_energy = nullptr;
     long long rec_capacity = 0, last_range_rays = 0;
@@ -757,11 +761,11 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     // IR buffers (OR/AudioRenderer.cpp:81-85) and the fp64 accumulation histogram
     const size_t irn = (size_t)c->bands * c->ir_len;
     CKC(cudaMalloc(&c->d_hist, 2 * irn * sizeof(double)));
-    CKC(cudaMalloc(&c->d_ir_l, irn * sizeof(float)));
-    CKC(cudaMalloc(&c->d_ir_r, irn * sizeof(float)));
+    CKC(cudaMalloc(&c->d_ir_l, 2 * irn * sizeof(float)));
+    c->d_ir_r = c->d_ir_l + irn;
+    CKC(cudaMallocHost(&c->h_ir, 2 * irn * sizeof(float)));
     CKC(cudaMemset(c->d_hist, 0, 2 * irn * sizeof(double)));
-    CKC(cudaMemset(c->d_ir_l, 0, irn * sizeof(float)));
-    CKC(cudaMemset(c->d_ir_r, 0, irn * sizeof(float)));
+    CKC(cudaMemset(c->d_ir_l, 0, 2 * irn * sizeof(float)));
     CKC(cudaMalloc(&c->d_counters, kCounters * sizeof(unsigned long long)));
 #undef CKC
     (void)rc;
@@ -774,7 +778,8 @@ void arv2_destroy(arv2_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaFree(c->d_nodes); cudaFree(c->d_nodes4); cudaFree(c->d_tris); cudaFree(c->d_keep); cudaFree(c->d_scatter);
-    cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_ir_r); cudaFree(c->d_counters);
+    cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_counters);
+    if (c->h_ir) cudaFreeHost(c->h_ir);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
     cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_off); cudaFree(c->d_pc_vert); cudaFree(c->d_pc_bits); cudaFree(c->order[0].d); cudaFree(c->order[1].d); cudaFree(c->d_wave_paths);
     cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
@@ -816,9 +821,9 @@ int arv2_set_seed(arv2_ctx* c, uint64_t s) { REQUIRE(c, "null ctx"); c->seed = s
 int arv2_set_coherent_order(arv2_ctx* c, int32_t on) { REQUIRE(c, "null ctx"); c->coherent_order = on != 0; return ARV2_OK; }
 int arv2_set_stream(arv2_ctx* c, void* s) { REQUIRE(c, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return ARV2_OK; }
 
-int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t zero_first, double* ms)
+// Everything of a trace up to (not including) a host synchronisation: receiver upload, zeroing, the launch.
+static int enqueue_trace(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t zero_first)
 {
-    REQUIRE(c, "null ctx");
     REQUIRE(ray_begin >= 0 && n_rays >= 0 && ray_begin + n_rays <= c->n_rays_total, "ray range outside the seeded set");
     CK(cudaSetDevice(c->device));
     int rc = upload_receiver(c);
@@ -839,7 +844,14 @@ int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t ze
     if (n_rays > 0) CK(launch_trace(p, c->bands, 0, c->sm_count, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
     c->last_range_rays = n_rays;
-    return finish_timed(c, ms);
+    return ARV2_OK;
+}
+
+int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t zero_first, double* ms)
+{
+    REQUIRE(c, "null ctx");
+    const int rc = enqueue_trace(c, ray_begin, n_rays, zero_first);
+    return rc != ARV2_OK ? rc : finish_timed(c, ms);
 }
 
 int arv2_finalize(arv2_ctx* c)
@@ -881,9 +893,11 @@ int arv2_render(arv2_ctx* c, double* ms)
 {
     REQUIRE(c, "null ctx");
     if (!c->desc.path_cache) {
-        int rc = arv2_render_range(c, 0, c->n_rays_total, 1, ms);
+        // trace, finalise, counters: one enqueue, one host synchronisation (OR/AudioRenderer.cpp:489-523)
+        const int rc = enqueue_trace(c, 0, c->n_rays_total, 1);
         if (rc != ARV2_OK) return rc;
-        return arv2_finalize(c);
+        CK(launch_finalize(c->d_hist, c->bands, c->ir_len, c->mono, c->d_ir_l, c->d_ir_r, c->stream));
+        return finish_timed(c, ms);
     }
     // path-cache mode: trace the receiver-independent paths once, then re-deposit from them
     CK(cudaSetDevice(c->device));
@@ -898,6 +912,150 @@ int arv2_render(arv2_ctx* c, double* ms)
     return rc;
 }
 
+/* ------------------------------------------------------ multi-GPU (NCCL) -- */
+#define NCK(expr)                                                                                      \
+    do {                                                                                               \
+        ncclResult_t r_ = (expr);                                                                      \
+        if (r_ != ncclSuccess) { set_error(std::string(#expr) + ": " + api->GetErrorString(r_)); return ARV2_ERR_CUDA; } \
+    } while (0)
+
+int arv2_comm_unique_id(void* id128)
+{
+    REQUIRE(id128, "null argument");
+    static_assert(sizeof(ncclUniqueId) == ARV2_COMM_ID_BYTES, "ncclUniqueId size");
+    std::string err;
+    const NcclApi* api = nccl_api(&err);
+    if (!api) { set_error(err); return ARV2_ERR_STATE; }
+    ncclUniqueId id;
+    NCK(api->GetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof id);
+    return ARV2_OK;
+}
+
+int arv2_comm_create(int32_t device, int32_t rank, int32_t n_ranks, const void* id128, arv2_comm** out)
+{
+    REQUIRE(out && id128 && n_ranks >= 1 && rank >= 0 && rank < n_ranks, "arv2_comm_create: bad argument");
+    std::string err;
+    const NcclApi* api = nccl_api(&err);
+    if (!api) { set_error(err); return ARV2_ERR_STATE; }
+    CK(cudaSetDevice(device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    auto* m = new arv2_comm;
+    m->device = device; m->rank = rank; m->n_ranks = n_ranks;
+    const ncclResult_t r = api->CommInitRank(&m->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) { set_error(std::string("ncclCommInitRank: ") + api->GetErrorString(r)); delete m; return ARV2_ERR_CUDA; }
+    *out = m;
+    return ARV2_OK;
+}
+
+void arv2_comm_destroy(arv2_comm* m)
+{
+    if (!m) return;
+    if (m->comm) { if (const NcclApi* api = nccl_api(nullptr)) { cudaSetDevice(m->device); api->CommDestroy(m->comm); } }
+    delete m;
+}
+
+int arv2_comm_info(const arv2_comm* m, int32_t* rank, int32_t* n_ranks, int32_t* nccl_version)
+{
+    REQUIRE(m, "null comm");
+    if (rank) *rank = m->rank;
+    if (n_ranks) *n_ranks = m->n_ranks;
+    if (nccl_version) { int v = 0; if (const NcclApi* api = nccl_api(nullptr)) api->GetVersion(&v); *nccl_version = v; }
+    return ARV2_OK;
+}
+
+void arv2_shard_range(int64_t n_rays, int32_t rank, int32_t n_ranks, int64_t* begin, int64_t* count)
+{
+    const int64_t base = n_rays / n_ranks, rem = n_rays % n_ranks;
+    if (begin) *begin = rank * base + std::min<int64_t>(rank, rem);
+    if (count) *count = base + (rank < rem ? 1 : 0);
+}
+
+// One rank's part of a render over R GPUs: this rank's contiguous slice of the seeded ray set, the sum of the fp64
+// histograms over NVLink, the fp32 IR -- enqueued back to back on the context's stream, one host synchronisation.
+int arv2_render_sharded(arv2_ctx* c, arv2_comm* m, double* ms)
+{
+    REQUIRE(c && m, "arv2_render_sharded: null argument");
+    REQUIRE(m->device == c->device, "communicator and context live on different devices");
+    REQUIRE(!c->desc.path_cache, "arv2_render_sharded: not with desc.path_cache");
+    const NcclApi* api = nccl_api(nullptr);
+    REQUIRE(api, "NCCL not loaded");
+    int64_t begin = 0, count = 0;
+    arv2_shard_range(c->n_rays_total, m->rank, m->n_ranks, &begin, &count);
+    const int rc = enqueue_trace(c, begin, count, 1);
+    if (rc != ARV2_OK) return rc;
+    const size_t n = 2 * (size_t)c->bands * c->ir_len;
+    if (m->n_ranks > 1) NCK(api->AllReduce(c->d_hist, c->d_hist, n, ncclFloat64, ncclSum, m->comm, c->stream));
+    CK(launch_finalize(c->d_hist, c->bands, c->ir_len, c->mono, c->d_ir_l, c->d_ir_r, c->stream));
+    return finish_timed(c, ms);
+}
+
+// One process, several devices (the reference application is one process, OR/main.cpp:720-777): one context and one
+// communicator rank per device, one host thread per device for a render.
+int arv2_multi_create(const arv2_scene* scene, const arv2_receiver* receiver, const arv2_renderer_desc* desc, const int32_t* devices,
+                      int32_t n_devices, arv2_multi** out)
+{
+    REQUIRE(scene && desc && devices && out && n_devices >= 1, "arv2_multi_create: bad argument");
+    std::string err;
+    const NcclApi* api = nccl_api(&err);
+    if (!api) { set_error(err); return ARV2_ERR_STATE; }
+    auto* mm = new arv2_multi;
+    int rc = ARV2_OK;
+    for (int i = 0; i < n_devices && rc == ARV2_OK; ++i) {
+        arv2_renderer_desc d = *desc;
+        d.device = devices[i];
+        arv2_ctx* c = nullptr;
+        rc = arv2_create(scene, receiver, &d, &c);
+        if (rc == ARV2_OK) mm->ctx.push_back(c);
+    }
+    if (rc == ARV2_OK) {
+        std::vector<ncclComm_t> comms((size_t)n_devices);
+        std::vector<int> devs(devices, devices + n_devices);
+        const ncclResult_t r = api->CommInitAll(comms.data(), n_devices, devs.data());
+        if (r != ncclSuccess) { set_error(std::string("ncclCommInitAll: ") + api->GetErrorString(r)); rc = ARV2_ERR_CUDA; }
+        else for (int i = 0; i < n_devices; ++i) {
+            auto* m = new arv2_comm;
+            m->device = devices[i]; m->rank = i; m->n_ranks = n_devices; m->comm = comms[(size_t)i];
+            mm->comm.push_back(m);
+        }
+    }
+    if (rc != ARV2_OK) { arv2_multi_destroy(mm); return rc; }
+    *out = mm;
+    return ARV2_OK;
+}
+
+int32_t arv2_multi_size(const arv2_multi* mm) { return mm ? (int32_t)mm->ctx.size() : 0; }
+arv2_ctx* arv2_multi_ctx(arv2_multi* mm, int32_t i) { return (mm && i >= 0 && i < (int32_t)mm->ctx.size()) ? mm->ctx[(size_t)i] : nullptr; }
+
+int arv2_multi_render(arv2_multi* mm, double* ms)
+{
+    REQUIRE(mm && !mm->ctx.empty(), "null multi");
+    const size_t n = mm->ctx.size();
+    std::vector<int> rcs(n, ARV2_OK);
+    std::vector<double> t(n, 0.0);
+    std::vector<std::string> errs(n);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < n; ++i)
+        th.emplace_back([&, i] { rcs[i] = arv2_render_sharded(mm->ctx[i], mm->comm[i], &t[i]); if (rcs[i] != ARV2_OK) errs[i] = arv2_last_error(); });
+    for (auto& x : th) x.join();
+    double worst = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        if (rcs[i] != ARV2_OK) { set_error("device " + std::to_string(mm->ctx[i]->device) + ": " + errs[i]); return rcs[i]; }
+        worst = std::max(worst, t[i]);
+    }
+    if (ms) *ms = worst;
+    return ARV2_OK;
+}
+
+void arv2_multi_destroy(arv2_multi* mm)
+{
+    if (!mm) return;
+    for (auto* m : mm->comm) arv2_comm_destroy(m);
+    for (auto* c : mm->ctx) arv2_destroy(c);
+    delete mm;
+}
+
 int arv2_ir_length(const arv2_ctx* c, int32_t* ir_length, int32_t* bands)
 {
     REQUIRE(c, "null ctx");
@@ -910,10 +1068,12 @@ int arv2_get_ir(arv2_ctx* c, float* l, float* r)
 {
     REQUIRE(c, "null ctx");
     CK(cudaSetDevice(c->device));
-    const size_t bytes = (size_t)c->bands * c->ir_len * sizeof(float);
+    // both ears in one stream-ordered copy into pinned memory, one sync (the reference's getIROnHostMem is two blocking copies)
+    const size_t irn = (size_t)c->bands * c->ir_len;
+    CK(cudaMemcpyAsync(c->h_ir, c->d_ir_l, 2 * irn * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (l) CK(cudaMemcpy(l, c->d_ir_l, bytes, cudaMemcpyDeviceToHost));
-    if (r) CK(cudaMemcpy(r, c->d_ir_r, bytes, cudaMemcpyDeviceToHost));
+    if (l) std::memcpy(l, c->h_ir, irn * sizeof(float));
+    if (r) std::memcpy(r, c->h_ir + irn, irn * sizeof(float));
     return ARV2_OK;
 }
 
@@ -961,6 +1121,13 @@ int arv2_path_cache_info(arv2_ctx* c, int64_t* segments, int64_t* bytes)
     return ARV2_OK;
 }
 
+int arv2_last_counters(arv2_ctx* c, uint64_t* out, int32_t n)
+{
+    REQUIRE(c && out && n >= 0, "bad argument");
+    for (int i = 0; i < n; ++i) out[i] = i < kCounters ? (uint64_t)c->h_counters[i] : 0u;
+    return ARV2_OK;
+}
+
 int arv2_last_segments(arv2_ctx* c, int64_t* segs)
 {
     REQUIRE(c && segs, "null argument");
@@ -993,6 +1160,15 @@ int arv2_write_ir_text(arv2_ctx* c, const char* left_path, const char* right_pat
     std::ofstream fl(left_path), fr(right_path);
     if (!fl.is_open() && !fr.is_open()) { set_error("Error opening the file."); return ARV2_ERR_IO; }   // OR/AudioRenderer.cpp:544-547
     for (int i = 0; i < c->ir_len; ++i) { fl << l[i] << std::endl; fr << r[i] << std::endl; }         // :553-557
+    return ARV2_OK;
+}
+
+int arv2_write_convolved_text(const char* left_path, const char* right_path, const float* l, const float* r, size_t n)
+{
+    REQUIRE(left_path && right_path && l && r, "null argument");
+    std::ofstream fl(left_path), fr(right_path);
+    if (!fl.is_open() && !fr.is_open()) { set_error("Error opening the file."); return ARV2_ERR_IO; }   // OR/AudioRenderer.cpp:722-727
+    for (size_t i = 0; i < n; ++i) { fl << l[i] << std::endl; fr << r[i] << std::endl; }               // :733-737
     return ARV2_OK;
 }
 

@@ -172,6 +172,26 @@ constexpr int kNone = INT_MIN + 1;   // "this child is not entered" (never a nod
 struct Traversal {
     int sp, cur;
     Hit h;
+    // -DARV2_TRACE_STATS (libarv2_stats.so, bench.py's traversal figures): per-lane tallies of the walk
+#ifdef ARV2_TRACE_STATS
+    unsigned long long st_inner = 0, st_wsteps = 0, st_leaf = 0, st_tri = 0, st_wleaf = 0;
+    __device__ __forceinline__ void tally_inner() { ++st_inner; const unsigned m = __activemask(); if ((threadIdx.x & 31) == __ffs(m) - 1) ++st_wsteps; }
+    __device__ __forceinline__ void tally_leaf(int cnt) { ++st_leaf; st_tri += cnt; const unsigned m = __activemask(); if ((threadIdx.x & 31) == __ffs(m) - 1) ++st_wleaf; }
+    __device__ __forceinline__ void flush_stats(unsigned long long* counters)
+    {
+        unsigned long long v[5] = {st_inner, st_wsteps, st_leaf, st_tri, st_wleaf};
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+            if ((threadIdx.x & 31) == 0 && v[i]) atomicAdd(counters + kStatInner + i, v[i]);
+        }
+    }
+#else
+    __device__ __forceinline__ void tally_inner() {}
+    __device__ __forceinline__ void tally_leaf(int) {}
+    __device__ __forceinline__ void flush_stats(unsigned long long*) {}
+#endif
 
     __device__ __forceinline__ void reset(float tmax) { h.t = tmax; h.u = 0.f; h.v = 0.f; h.slot = -1; h.id = INT_MAX; cur = kSentinel; sp = 0; }
     __device__ __forceinline__ void enter(int* stack, int root) { stack[0] = kSentinel; sp = 1; cur = root; }
@@ -275,6 +295,7 @@ struct Traversal {
         (void)org;
         const float ix = g.ix, iy = g.iy, iz = g.iz, ox = g.ox, oy = g.oy, oz = g.oz;
 #endif
+        tally_inner();
         const float4* __restrict__ nodes = p.nodes;
         const F8 na = ldg256_node(nodes + cur * 4), nb = ldg256_node(nodes + cur * 4 + 2);
         const float4 n0 = na.lo, n1 = na.hi, n2 = nb.lo, n3 = nb.hi;
@@ -308,6 +329,7 @@ struct Traversal {
         const int code = ~cur;
         const int first = code >> 3;
         const int cnt = (code & 7) + 1;
+        tally_leaf(cnt);
         for (int i = 0; i < cnt; ++i) {
             const int slot = first + i;
             const F8 A = CACHED ? ldg256(tris + slot * 4) : ldg256_tri(tris + slot * 4);
@@ -651,6 +673,7 @@ __global__ void __launch_bounds__(kThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) tr
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
     if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+    tr.flush_stats(p.counters);
 #ifdef ARV2_TAILSTAT
     if (lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(p.counters + 5, t); atomicMin(p.counters + 6, t); }
 #endif
@@ -836,6 +859,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
     if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+    tr.flush_stats(p.counters);
 #ifdef ARV2_TAILSTAT
     if (lane == 0) {      // per warp: exit time; per CTA: how long this SM was busy
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

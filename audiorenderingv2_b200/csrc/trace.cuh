@@ -57,7 +57,8 @@ struct TraceParams {
 };
 
 constexpr int kWaveQueues = 64;               // most per-depth queues of wave_kernel
-constexpr int kCounters = 16;                 // unsigned long long counters per context
+constexpr int kCounters = 24;                 // unsigned long long counters per context
+constexpr int kStatInner = 16;                // -DARV2_TRACE_STATS: [16] node visits, [17] warp-level node steps, [18] leaf visits, [19] triangle tests, [20] warp-level leaf steps
 __host__ __device__ constexpr int cont_f4(int bands) { return bands == 1 ? 3 : 5; }   // float4 per queued path
 
 // 1 when the kernels were compiled with -DARV2_WIDE=1 (4-wide nodes in TraceParams::nodes4), 2 with -DARV2_QNODES=1

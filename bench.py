@@ -141,9 +141,10 @@ def oracle_flat(tv, tm, names, mats, recv):
 
 
 def cpu_port_rate(n_total_rays, budget_s, chunk):
-    """Times the oracle (CPU port of the identical tracer) on all host cores on a bounded
-    sample of the same workload.  Returns (Grays/s, cores, sample description, segments/ray)."""
+    """Times the oracle (CPU port of the identical tracer, built -O3 -march=native on this machine) on all host
+    cores on a bounded sample of the same workload.  Returns (Grays/s, cores, sample description, segments/ray)."""
     import oracle
+    oracle.use_native()                                       # BASELINE.md section 5; bit-identical to the portable build
     tv, tm, names, mats = scene_case()
     flat = oracle_flat(tv, tm, names, mats, load_receiver())
     prep = oracle.PreparedScene(flat, bands=BANDS)            # BVH build untimed (as on the GPU side)
@@ -156,7 +157,10 @@ def cpu_port_rate(n_total_rays, budget_s, chunk):
         s, _ = prep.trace(p, rays, chunk, n_threads=cores)
         t += time.perf_counter() - t0
         segs += s; rays += chunk
-    return segs / t / 1e9, cores, f"first {rays} rays of the same seeded set ({segs} segments, {t:.1f} s)", segs / max(rays, 1)
+    return segs / t / 1e9, cores, f"first {rays} rays of the same seeded set ({segs} segments, {t:.1f} s), g++ -O3 -march=native", segs / max(rays, 1)
+
+
+REFERENCE_CHUNK = 100_000       # rays the reference arm traces per step
 
 
 def run_reference(args):
@@ -166,8 +170,9 @@ def run_reference(args):
     if rank != 0:
         return
     n_total = RAYS[0] * RAYS[1] * RAYS[2] * args.gpus
-    chunk = 100_000
+    chunk = REFERENCE_CHUNK
     import oracle
+    oracle.use_native()
     tv, tm, names, mats = scene_case()
     flat = oracle_flat(tv, tm, names, mats, load_receiver())
     prep = oracle.PreparedScene(flat, bands=BANDS)
@@ -183,13 +188,18 @@ def run_reference(args):
         t += time.perf_counter() - t0
         segs += s
     val = segs / t / 1e9
+    cfg = workload_config(args.gpus)
+    cfg["reference_rays_per_step"] = chunk
+    cfg["reference_sample"] = (f"each step traces {chunk} rays of the {n_total}-ray seeded set (a rate metric: Grays/s does not "
+                               "depend on the sample size); scene, bounces, IR length as in `workload`")
     line = {
         "impl": "reference", "metric": "Grays/s IR trace", "value": val, "unit": "Grays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": val, "unit": "Grays/s", "cores": cores, "kind": "port",
-                         "sample": f"{chunk} rays per step of the same seeded set (OptiX reference not buildable offline)"},
+                         "sample": f"{chunk} rays per step of the same seeded set, oracle built g++ -O3 -march=native on this box "
+                                   "(OptiX reference not buildable offline)"},
         "e2e": {"value": val, "unit": "Grays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -204,8 +214,83 @@ def workload_config(n_gpus):
     return {"workload": desc,
             "rays_per_gpu": RAYS[0] * RAYS[1] * RAYS[2], "total_rays": RAYS[0] * RAYS[1] * RAYS[2] * n_gpus,
             "max_bounces": MAX_BOUNCES, "sample_rate": FS, "ir_seconds": IR_SECONDS, "bands": BANDS,
-            "parallelism": f"ray-range sharding x{n_gpus}, NCCL all-reduce of the fp64 IR histogram",
+            "parallelism": f"ray-range sharding x{n_gpus}, ncclAllReduce of the fp64 IR histogram inside libarv2 (arv2_render_sharded)",
             "l2": "flushed between timed steps (512 MiB write)"}
+
+
+class Job:
+    """One rank of the bench: device, process group, the library's own NCCL communicator."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import audiorenderingv2_b200 as arv
+        self.torch, self.dist, self.arv = torch, dist, arv
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            raise SystemExit(f"--gpus {args.gpus} needs {args.gpus} ranks (launch with torch.distributed.run); WORLD_SIZE={self.world}")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        # libarv2's communicator: rank 0 makes the NCCL id inside the library, torch.distributed only carries the 128 bytes
+        uid = torch.zeros(arv.COMM_ID_BYTES, dtype=torch.uint8, device=self.dev)
+        if self.rank == 0:
+            uid = torch.frombuffer(bytearray(arv.Comm.unique_id()), dtype=torch.uint8).to(self.dev)
+        if self.world > 1:
+            dist.broadcast(uid, 0)
+        self.comm = arv.Comm(self.local, self.rank, self.world, bytes(uid.cpu().numpy().tobytes()))
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.flush = torch.empty(512 << 20, dtype=torch.uint8, device=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce_max_sum(self, per_step_ms, total):
+        """(sum over steps of the max over ranks of the step time, sum over ranks of `total`)"""
+        t = self.torch.tensor(per_step_ms, dtype=self.torch.float64, device=self.dev)
+        s = self.torch.tensor([float(total)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(s)
+        return float(t.sum().item()), float(s.item())
+
+    def renderer(self, scene, receiver, mats, total_rays, **kw):
+        r = self.arv.AudioRenderer(scene, IR_SECONDS, FS, mats, (total_rays, 1, 1), receiver=receiver, device=self.local, bands=BANDS, **kw)
+        r.setBasePower(100.0); r.setThresholds(0.0, MAX_BOUNCES); r.set_hrtf_absorption_rate(0.9)
+        r.setEmitterPosInOptix(EMITTER); r.setSphereCenterInOptix(RECEIVER, YAW); r.set_seed(SEED)
+        r.set_stream(self.stream.cuda_stream)
+        return r
+
+    def timed_renders(self, r, steps, warmup, sample_clocks=False):
+        """`steps` sharded renders (this rank's slice, all-reduce, finalise: arv2_render_sharded), each bracketed by a
+        barrier + synchronize and timed with CUDA events on the launching stream; L2 flushed before each."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):
+                r.render_sharded(self.comm)
+            self.barrier()
+            clocks = ClockSampler(self.local) if sample_clocks else None
+            step_ms, kern_ms, segs = [], [], 0
+            ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+            for _ in range(steps):
+                self.flush.fill_(1)                     # evict the BVH from L2 between timed steps
+                self.barrier()
+                ev0.record(self.stream)
+                kern_ms.append(r.render_sharded(self.comm))
+                ev1.record(self.stream)
+                torch.cuda.synchronize()
+                step_ms.append(ev0.elapsed_time(ev1))
+                segs += r.last_segments()
+            self.barrier()
+            clk = clocks.stop() if clocks else None
+        total_ms, total_segs = self.reduce_max_sum(step_ms, segs)
+        return {"value": total_segs / (total_ms * 1e-3) / 1e9, "total_ms": total_ms, "total_segs": total_segs,
+                "kernel_ms": float(np.mean(kern_ms)), "local_segs_per_step": segs / steps, "clocks": clk}
 
 
 def main():
@@ -215,8 +300,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="arv2", choices=["arv2", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--skip-extras", action="store_true", help="skip the re-render and convolution sub-metrics")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the re-render / convolution / C3 / C4 sub-metrics")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2 = BASELINE configs[1] (default), c4 = configs[3]")
+    ap.add_argument("--stats-pass", action="store_true", help="internal: print the traversal tallies of the stats build and exit")
     args = ap.parse_args()
     select_workload(args.workload)
     if os.environ.get("ARV2_BENCH_RAYS"):           # tuning aid (tail-effect experiments); not a driver-facing line
@@ -229,20 +315,11 @@ def main():
 
     if args.impl == "reference":
         return run_reference(args)
+    if args.stats_pass:
+        return stats_pass()
 
-    import torch
-    import torch.distributed as dist
-    import audiorenderingv2_b200 as arv
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} needs {args.gpus} ranks (launch with torch.distributed.run); WORLD_SIZE={world}")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    job = Job(args)
+    torch, dist, arv, world, rank, local, dev = job.torch, job.dist, job.arv, job.world, job.rank, job.local, job.dev
 
     tv, tm, names, mats = scene_case()
     recv = load_receiver()
@@ -251,87 +328,60 @@ def main():
     scene = arv.Scene.from_triangles(tv, tm, names)
     receiver = arv.Receiver.from_triangles(*recv)
     t_build = time.perf_counter()
-    # the seeded ray set has total_rays rays; this rank traces [rank*per_gpu, (rank+1)*per_gpu)
-    r = arv.AudioRenderer(scene, IR_SECONDS, FS, mats, (total_rays, 1, 1), receiver=receiver, device=local, bands=BANDS)
+    # the seeded ray set has total_rays rays; rank r traces arv2_shard_range(total_rays, r, world) = per_gpu rays
+    r = job.renderer(scene, receiver, mats, total_rays)
     t_build = time.perf_counter() - t_build
-    r.setBasePower(100.0); r.setThresholds(0.0, MAX_BOUNCES); r.set_hrtf_absorption_rate(0.9)
-    r.setEmitterPosInOptix(EMITTER); r.setSphereCenterInOptix(RECEIVER, YAW); r.set_seed(SEED)
-    stream = torch.cuda.Stream(device=dev)
-    r.set_stream(stream.cuda_stream)
 
-    hist_ptr, hist_n = r.hist_device()
+    # first render of a context and of a new seed: direction keys + radix sort of the ray order + the trace (ADVICE:
+    # the steady-state figure below re-uses the order of its seed; the reference draws fresh directions every render)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); r.render_sharded(job.comm); torch.cuda.synchronize(); first_ms = 1e3 * (time.perf_counter() - t0)
+    r.set_seed(SEED + 1)
+    t0 = time.perf_counter(); r.render_sharded(job.comm); torch.cuda.synchronize(); new_seed_ms = 1e3 * (time.perf_counter() - t0)
+    r.set_seed(SEED)
 
-    class _Ext:
-        __cuda_array_interface__ = {"shape": (hist_n,), "typestr": "<f8", "data": (hist_ptr, False), "version": 3}
-    hist = torch.as_tensor(_Ext(), device=dev)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    main_run = job.timed_renders(r, args.steps, args.warmup, sample_clocks=True)
+    value, total_ms, total_segs, clk = main_run["value"], main_run["total_ms"], main_run["total_segs"], main_run["clocks"]
 
-    def step():
-        """one IR render of this rank's shard; returns kernel ms (device events inside the library)"""
-        ms = r.render_range(rank * per_gpu, per_gpu, zero_first=True)
-        if world > 1:
-            dist.all_reduce(hist)
-        r.finalize()
-        return ms
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step()
-        barrier()
-        clocks = ClockSampler(local)
-        step_ms, kern_ms, segs = [], [], 0
-        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-        for _ in range(args.steps):
-            flush.fill_(1)                     # evict the BVH from L2 between timed steps
-            barrier()
-            ev0.record(stream)
-            kern_ms.append(step())
-            ev1.record(stream)
-            torch.cuda.synchronize()
-            step_ms.append(ev0.elapsed_time(ev1))
-            segs += r.last_segments()
-        barrier()
-        clk = clocks.stop()
-
-        # max over ranks per step, summed: the whole job advances at the slowest rank
-        t_steps = torch.tensor(step_ms, dtype=torch.float64, device=dev)
-        seg_t = torch.tensor([float(segs)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_steps, op=dist.ReduceOp.MAX)
-            dist.all_reduce(seg_t)
-        total_ms = float(t_steps.sum().item())
-        total_segs = float(seg_t.item())
-        value = total_segs / (total_ms * 1e-3) / 1e9
-
-        # ---- e2e: the call a user of the reference makes (full_render_cycle minus the
-        # convolution): move the receiver (host -> device upload of its sub-tree), render,
-        # read both IRs back to host memory.
-        ir_bytes = 2 * BANDS * r.ir_length * 4
-        e2e_ms, e2e_segs = [], 0
+    # ---- e2e: the call a user of the reference makes (full_render_cycle minus the convolution): move the receiver
+    # (host -> device upload of its sub-tree), render, read both IRs back to host memory.
+    ir_bytes = 2 * BANDS * r.ir_length * 4
+    e2e_ms, e2e_segs = [], 0
+    with torch.cuda.stream(job.stream):
         for k in range(args.steps):
-            flush.fill_(1)
-            barrier()
+            job.flush.fill_(1)
+            job.barrier()
             t0 = time.perf_counter()
             r.setSphereCenterInOptix((RECEIVER[0] + 0.01 * (k + 1), RECEIVER[1], RECEIVER[2]), YAW)
-            step()
+            r.render_sharded(job.comm)
             r.get_ir()
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
             e2e_segs += r.last_segments()
-        t_e2e = torch.tensor(e2e_ms, dtype=torch.float64, device=dev)
-        seg_e = torch.tensor([float(e2e_segs)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-            dist.all_reduce(seg_e)
-        e2e_value = float(seg_e.item()) / (float(t_e2e.sum().item()) * 1e-3) / 1e9
-        r.setSphereCenterInOptix(RECEIVER, YAW)
+    e2e_total_ms, e2e_total_segs = job.reduce_max_sum(e2e_ms, e2e_segs)
+    e2e_value = e2e_total_segs / (e2e_total_ms * 1e-3) / 1e9
+    upload_bytes = r.last_upload_bytes()
+    r.setSphereCenterInOptix(RECEIVER, YAW)
 
-    kernel_ms = float(np.mean(kern_ms))
-    segs_per_launch = segs / args.steps
+    # ---- the sharded IR is the single-GPU IR (every N the driver runs checks it on hardware)
+    sharded_check = None
+    if world > 1:
+        with torch.cuda.stream(job.stream):
+            r.render_sharded(job.comm)
+            ls, rs = r.get_ir()
+            sharded_segs = job.reduce_max_sum([0.0], r.last_segments())[1]
+            job.barrier()
+            if rank == 0:
+                r.render()                                  # all total_rays rays on this one GPU
+                l1, r1 = r.get_ir()
+                den = np.maximum(np.abs(l1), 1e-30)
+                sharded_check = {"ir_max_rel_diff": float(np.max(np.abs(ls - l1)[l1 != 0] / den[l1 != 0])) if (l1 != 0).any() else 0.0,
+                                 "nonzero_bins_equal": bool(np.array_equal(ls != 0, l1 != 0) and np.array_equal(rs != 0, r1 != 0)),
+                                 "segments_equal": int(sharded_segs) == r.last_segments(), "rays": total_rays}
+                sharded_check["ok"] = bool(sharded_check["ir_max_rel_diff"] <= 1e-6 and sharded_check["nonzero_bins_equal"] and sharded_check["segments_equal"])
+            job.barrier()
+
+    kernel_ms = main_run["kernel_ms"]
+    segs_per_launch = main_run["local_segs_per_step"]
     achieved = segs_per_launch * BYTES_PER_SEGMENT / (kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
 
@@ -341,14 +391,25 @@ def main():
     except (OSError, KeyError, ValueError):
         pass
 
-    extras = {}
+    extras = {"first_render_ms": first_ms, "new_seed_render_ms": new_seed_ms,
+              "render_note": "value / e2e re-use the direction-sorted ray order of their seed (cached per seed and ray range); "
+                             "first_render_ms = first render of a context (sort + queue allocation + trace), new_seed_render_ms = a render "
+                             "right after arv2_set_seed (sort + trace); the scene BVH is built once per context (bvh_build_s), the "
+                             "reference rebuilds its GAS on every move"}
+    r.close()
     if not args.skip_extras and WORKLOAD == "c2":
         extras.update(bench_rerender(arv, torch, dev, local, scene, receiver, mats, args))
         extras.update(bench_conv(arv, torch, dist, dev, local, rank, world, args))
         extras.update(bench_lbvh(arv, scene, receiver, mats, local))
+        extras.update(bench_c3_strong(job, scene, receiver, mats))
+        del scene
+        extras.update(bench_c4(job, args))
+        if rank == 0:
+            extras["traversal"] = traversal_figures(local)
+        job.barrier()
     if not args.skip_extras and WORKLOAD == "c4":
         # configs[3] "interactive receiver moves": 10M rays x 50 segments x (32 B + 8 bands x 4 B) = 32 GB of cached paths
-        del flush
+        job.flush = None
         torch.cuda.empty_cache()
         extras.update(bench_rerender(arv, torch, dev, local, scene, receiver, mats, args))
 
@@ -358,23 +419,127 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "segments_per_step": total_segs / args.steps, "paths_per_s": total_rays * args.steps / (total_ms * 1e-3),
         "bvh_build_s": t_build,
-        "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": r.last_upload_bytes(),
-                "d2h_bytes_per_step": ir_bytes + 16, "ms_per_step": float(t_e2e.sum().item()) / args.steps},
+        "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": upload_bytes,
+                "d2h_bytes_per_step": ir_bytes + 8 * 24, "ms_per_step": e2e_total_ms / args.steps},
         "gpu_launches": 2 * args.steps,
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": f"wave_kernel<{BANDS},0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": segs_per_launch * BYTES_PER_SEGMENT,
-                     "bytes_per_segment": BYTES_PER_SEGMENT, "kernel_ms": kernel_ms},
+                     "bytes_per_segment": BYTES_PER_SEGMENT, "kernel_ms": kernel_ms,
+                     "note": "nominal: the scene is L2-resident and DRAM idles; what binds is in `traversal`"},
     }
+    if sharded_check is not None:
+        line["sharded_equals_single"] = sharded_check
     line.update(extras)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_port_rate(per_gpu, 12.0, 50_000)
         line["cpu_baseline"] = {"value": v, "unit": "Grays/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    job.comm.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_c3_strong(job, scene, receiver, mats):
+    """BASELINE configs[2]: the same room, 100M rays in total, strong-sharded over the N ranks (each traces 100M / N),
+    ncclAllReduce of the histogram inside the library."""
+    n_total = 100_000_000
+    r = job.renderer(scene, receiver, mats, n_total)
+    run = job.timed_renders(r, steps=2, warmup=1)
+    r.close()
+    job.torch.cuda.empty_cache()
+    return {"c3_strong_grays_per_s": run["value"], "c3_strong_ms_per_render": run["total_ms"] / 2, "c3_total_rays": n_total,
+            "c3_rays_per_gpu": n_total // job.world, "c3_segments_per_render": run["total_segs"] / 2}
+
+
+def bench_c4(job, args):
+    """BASELINE configs[3] (the target's scene): synthetic 1M-triangle hall, 8 frequency bands, 10M rays per GPU (weak),
+    plus the interactive receiver move (re-render from the path cache) on this rank's 10M rays."""
+    global RAYS, EMITTER, RECEIVER, SEED, BANDS, BYTES_PER_SEGMENT, WORKLOAD
+    saved = (RAYS, EMITTER, RECEIVER, SEED, BANDS, BYTES_PER_SEGMENT, WORKLOAD)
+    select_workload("c4")
+    try:
+        arv, torch = job.arv, job.torch
+        tv, tm, names, mats = scene_case()
+        scene = arv.Scene.from_triangles(tv, tm, names)
+        receiver = arv.Receiver.from_triangles(*load_receiver())
+        per_gpu = RAYS[0] * RAYS[1] * RAYS[2]
+        r = job.renderer(scene, receiver, mats, per_gpu * job.world)
+        run = job.timed_renders(r, steps=3, warmup=2)
+        r.close()
+        peak = measured_hbm_peak()[0]
+        achieved = run["local_segs_per_step"] * BYTES_PER_SEGMENT / (run["kernel_ms"] * 1e-3) / 1e9
+        out = {"c4_grays_per_s": run["value"], "c4_ms_per_render": run["total_ms"] / 3, "c4_rays_per_gpu": per_gpu,
+               "c4_roofline_frac": achieved / peak, "c4_bytes_per_segment": BYTES_PER_SEGMENT, "c4_kernel_ms": run["kernel_ms"]}
+        job.flush = None
+        torch.cuda.empty_cache()
+        rr = bench_rerender(arv, torch, job.dev, job.local, scene, receiver, mats, args)
+        t = torch.tensor([rr["rerender_ms"]], dtype=torch.float64, device=job.dev)
+        if job.world > 1:
+            job.dist.all_reduce(t, op=job.dist.ReduceOp.MAX)
+        out.update({"c4_rerender_ms": float(t.item()), "c4_rerender_cached_segments": rr["rerender_cached_segments"],
+                    "c4_rerender_roofline_frac": rr["rerender_roofline"]["frac"], "c4_path_cache_build_ms": rr["path_cache_build_ms"]})
+        job.flush = torch.empty(512 << 20, dtype=torch.uint8, device=job.dev)
+        return out
+    finally:
+        RAYS, EMITTER, RECEIVER, SEED, BANDS, BYTES_PER_SEGMENT, WORKLOAD = saved
+
+
+NCU_FIGURES = os.path.join(ROOT, "profiles", "ncu_figures.json")
+
+
+def stats_pass():
+    """Runs in a child process with ARV2_LIB = lib/libarv2_stats.so (trace kernels compiled with -DARV2_TRACE_STATS):
+    one render of the workload, prints the traversal tallies."""
+    import audiorenderingv2_b200 as arv
+    tv, tm, names, mats = scene_case()
+    scene = arv.Scene.from_triangles(tv, tm, names)
+    receiver = arv.Receiver.from_triangles(*load_receiver())
+    n = min(RAYS[0] * RAYS[1] * RAYS[2], 2_000_000)
+    r = arv.AudioRenderer(scene, IR_SECONDS, FS, mats, (n, 1, 1), receiver=receiver, bands=BANDS)
+    r.setBasePower(100.0); r.setThresholds(0.0, MAX_BOUNCES); r.set_hrtf_absorption_rate(0.9)
+    r.setEmitterPosInOptix(EMITTER); r.setSphereCenterInOptix(RECEIVER, YAW); r.set_seed(SEED)
+    r.render()
+    ms = r.render()
+    c = r.last_counters()
+    print(json.dumps({"rays": n, "segments": c[1], "node_visits": c[16], "warp_node_steps": c[17], "leaf_visits": c[18],
+                      "tri_tests": c[19], "warp_leaf_steps": c[20], "kernel_ms_with_tallies": ms}))
+
+
+def traversal_figures(local):
+    """What north_star asks the bench to evidence for the traversal: node visits per segment and the lanes of a warp
+    that are active per traversal step (live, from the stats build of the same kernels), the bytes the traversal asks
+    of L1/L2 per second, and ncu's warp-execution efficiency / L2 throughput of the committed capture (labelled)."""
+    out = {}
+    stats_lib = os.path.join(ROOT, "audiorenderingv2_b200", "lib", "libarv2_stats.so")
+    for wl in ("c2", "c4"):
+        try:
+            env = dict(os.environ, ARV2_LIB=stats_lib, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", ""))
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+                env.pop(k, None)
+            if not env["CUDA_VISIBLE_DEVICES"]:
+                env["CUDA_VISIBLE_DEVICES"] = str(local)
+            else:
+                env["CUDA_VISIBLE_DEVICES"] = env["CUDA_VISIBLE_DEVICES"].split(",")[local]
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--stats-pass", "--workload", wl], env=env,
+                                 capture_output=True, text=True, timeout=300)
+            d = json.loads(res.stdout.strip().splitlines()[-1])
+            segs = max(d["segments"], 1)
+            out[wl] = {"node_visits_per_segment": d["node_visits"] / segs, "leaf_visits_per_segment": d["leaf_visits"] / segs,
+                       "tri_tests_per_segment": d["tri_tests"] / segs,
+                       "lanes_per_node_step": d["node_visits"] / max(d["warp_node_steps"], 1),
+                       "lanes_per_leaf_step": d["leaf_visits"] / max(d["warp_leaf_steps"], 1),
+                       "requested_bytes_per_segment": (64 * d["node_visits"] + 48 * d["tri_tests"]) / segs,
+                       "source": f"live: lib/libarv2_stats.so (-DARV2_TRACE_STATS), {d['rays']} rays of the workload"}
+        except Exception as e:       # noqa: BLE001
+            out[wl] = {"error": repr(e)[:200]}
+    try:
+        out["ncu"] = json.load(open(NCU_FIGURES))
+    except (OSError, ValueError):
+        out["ncu"] = None
+    return out
 
 
 def measured_hbm_peak():

@@ -184,6 +184,36 @@ int arv2_render(arv2_ctx* ctx, double* ms);
 int arv2_render_range(arv2_ctx* ctx, int64_t ray_begin, int64_t n_rays, int32_t zero_first,
                       double* ms);
 int arv2_finalize(arv2_ctx* ctx);
+/* ---- several GPUs: rays shard, histograms are summed with NCCL over NVLink (the reference
+ * hard-wires device 0, OR/AudioRenderer.cpp:252-253).  libarv2 binds libnccl.so.2 at run
+ * time: the copy already loaded in the process (a torch rank), else the system's. ---- */
+#define ARV2_COMM_ID_BYTES 128
+typedef struct arv2_comm arv2_comm;
+/* ncclGetUniqueId: one rank makes the 128-byte id and hands it to the others (any transport). */
+int arv2_comm_unique_id(void* id128);
+/* ncclCommInitRank on `device`; collective over the n_ranks callers (one process or thread per GPU). */
+int arv2_comm_create(int32_t device, int32_t rank, int32_t n_ranks, const void* id128, arv2_comm** out);
+int arv2_comm_info(const arv2_comm* comm, int32_t* rank, int32_t* n_ranks, int32_t* nccl_version);
+void arv2_comm_destroy(arv2_comm* comm);
+/* The contiguous slice [begin, begin+count) of an n_rays set that `rank` of n_ranks traces. */
+void arv2_shard_range(int64_t n_rays, int32_t rank, int32_t n_ranks, int64_t* begin, int64_t* count);
+/* AudioRenderer::render on n_ranks GPUs: trace this rank's slice of the seeded ray set, ncclAllReduce
+ * the fp64 histogram and finalise on the context's stream, one host synchronisation at the end.
+ * Every rank ends up with the full IR; it equals the single-GPU arv2_render to fp32 rounding.
+ * Collective: all ranks call it with contexts created from the same scene, parameters and seed. */
+int arv2_render_sharded(arv2_ctx* ctx, arv2_comm* comm, double* ms);
+/* One process driving several devices (the reference application is one process): one context
+ * and one NCCL rank per device (ncclCommInitAll); arv2_multi_render runs arv2_render_sharded on one
+ * host thread per device.  Set parameters on every context (arv2_multi_ctx(m, i)); read the IR
+ * from any of them. */
+typedef struct arv2_multi arv2_multi;
+int arv2_multi_create(const arv2_scene* scene, const arv2_receiver* receiver, const arv2_renderer_desc* desc,
+                      const int32_t* devices, int32_t n_devices, arv2_multi** out);
+int32_t arv2_multi_size(const arv2_multi* m);
+arv2_ctx* arv2_multi_ctx(arv2_multi* m, int32_t i);
+int arv2_multi_render(arv2_multi* m, double* ms);   /* ms = the slowest device's trace */
+void arv2_multi_destroy(arv2_multi* m);
+
 /* Interactive receiver move: re-deposit from the cached receiver-independent
  * paths (requires desc.path_cache and one arv2_render since the last emitter
  * change).  Bit-identical to arv2_render for the same seed. */
@@ -202,6 +232,12 @@ int arv2_last_upload_bytes(arv2_ctx* ctx, int64_t* bytes);
 /* The receiver-independent path cache arv2_rerender scans (desc.path_cache, after one arv2_render): cached segments
  * of the whole ray set and the device bytes they occupy (32 B record + 4 B x bands energy + 8 B scan vertex each). */
 int arv2_path_cache_info(arv2_ctx* ctx, int64_t* segments, int64_t* bytes);
+/* Launch counters of the last render / re-render (diagnostics; unsigned 64-bit each): [1] segments traced;
+ * in a library built with -DARV2_TRACE_STATS (lib/libarv2_stats.so) also [16] BVH node visits, [17] warp-level
+ * node steps, [18] leaf visits, [19] triangle tests, [20] warp-level leaf steps -- what bench.py's "traversal"
+ * figures are computed from.  Entries beyond what the library keeps read 0. */
+#define ARV2_N_COUNTERS 24
+int arv2_last_counters(arv2_ctx* ctx, uint64_t* out, int32_t n);
 /* Segments (closest-hit queries) traced by the last render on this context. */
 int arv2_last_segments(arv2_ctx* ctx, int64_t* segments);
 /* Per-ray records of the last render (desc.record_rays), indexed by the ray's position in the
@@ -213,6 +249,12 @@ int arv2_get_records(arv2_ctx* ctx, int64_t capacity, int32_t* bin, int32_t* ear
 /* Text dump of AudioRenderer::render's write_ir_to_file branch
  * (OR/AudioRenderer.cpp:525-567): one value per line, ostream default format. */
 int arv2_write_ir_text(arv2_ctx* ctx, const char* left_path, const char* right_path);
+
+/* Text dump of convoluteAudioFile's write_output_to_file branch (OR/AudioRenderer.cpp:720-744;
+ * read by utils/main.py:17-28): n values per file, one per line, ostream default format.  The
+ * reference names the files output_convolute_left.txt / output_convolute_right.txt. */
+int arv2_write_convolved_text(const char* left_path, const char* right_path, const float* left,
+                              const float* right, size_t n);
 
 /* ------------------------------------------------------------ convolution -- */
 typedef enum {

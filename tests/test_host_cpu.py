@@ -278,3 +278,37 @@ def test_ring_is_the_reference_circular_buffer():
     assert list(ring.get_and_reset(8)) == [5, 6, 1, 1, 1, 1, 1, 0]
     with pytest.raises(arv.Arv2Error):
         ring.get_and_reset(9)
+
+
+def test_shard_range_in_the_library_is_the_python_rule():
+    for n in (0, 1, 7, 1_000_000, 100_000_007):
+        for w in (1, 2, 3, 4, 8):
+            for r in range(w):
+                assert arv.shard_range(n, r, w) == sharding.ray_range(r, w, n)
+
+
+def test_convolved_output_text_dump(tmp_path):
+    """output_convolute_left.txt / _right.txt (OR/AudioRenderer.cpp:720-744): one value per line in ostream's default
+    format (6 significant digits), readable the way utils/main.py:17-28 reads them."""
+    rng = np.random.default_rng(2)
+    l = (rng.standard_normal(1000) * 10.0 ** rng.integers(-8, 3, 1000)).astype(np.float32); r = -l[::-1].copy()
+    a, b = tmp_path / "output_convolute_left.txt", tmp_path / "output_convolute_right.txt"
+    arv.write_convolved_text(a, b, l, r)
+    la = open(a).read().split("\n")
+    assert len(la) == 1001 and la[-1] == ""
+    assert la[:5] == ["%g" % v for v in l[:5]]
+    assert np.allclose([float(s) for s in la[:-1]], l, rtol=1e-5, atol=0)
+    assert np.allclose([float(s) for s in open(b)], r, rtol=1e-5, atol=0)
+
+
+def test_nccl_binds_at_run_time_and_needs_a_device():
+    """libarv2 dlopens libnccl.so.2 (no link-time dependency); a communicator needs a CUDA device like everything else."""
+    import subprocess
+    deps = subprocess.run(["ldd", arv.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libnccl" not in deps
+    uid = arv.Comm.unique_id()
+    assert len(uid) == arv.COMM_ID_BYTES and uid != bytes(arv.COMM_ID_BYTES)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(arv.Arv2Error, match=r"error -3"):
+            arv.Comm(0, 0, 1, uid)
