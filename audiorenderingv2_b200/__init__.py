@@ -102,6 +102,7 @@ SYMBOLS = {
     "arv2_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _vp, C.POINTER(_vp)]),
     "arv2_comm_info": (C.c_int, [_vp, _ip, _ip, _ip]),
     "arv2_comm_destroy": (None, [_vp]),
+    "arv2_comm_reduce_f32": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int32, _vp]),
     "arv2_shard_range": (None, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "arv2_render_sharded": (C.c_int, [_vp, _vp, C.POINTER(C.c_double)]),
     "arv2_multi_create": (C.c_int, [_vp, _vp, C.POINTER(RendererDesc), _ip, C.c_int32, C.POINTER(_vp)]),
@@ -128,6 +129,9 @@ SYMBOLS = {
     "arv2_stream_process": (C.c_int, [_vp, _fp, _fp]),
     "arv2_stream_process_device": (C.c_int, [_vp, _vp, _vp, _vp]),
     "arv2_stream_process_device_blocks": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp]),
+    "arv2_stream_process_blocks": (C.c_int, [_vp, _fp, _fp, _fp, C.c_int32]),
+    "arv2_stream_mix_device": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp]),
+    "arv2_stream_set_gains": (C.c_int, [_vp, _fp]),
     "arv2_stream_reset": (C.c_int, [_vp]),
     "arv2_stream_close": (None, [_vp]),
     "arv2_global_angle": (C.c_float, [C.c_float, C.c_float]),
@@ -352,6 +356,10 @@ class Comm:
         buf = C.create_string_buffer(COMM_ID_BYTES)
         _check(lib().arv2_comm_unique_id(C.cast(buf, _vp)))
         return buf.raw
+
+    def reduce_f32(self, d_buf, count, root=0, cuda_stream=None):
+        """ncclReduce(sum) of `count` device floats onto `root`, in place."""
+        _check(lib().arv2_comm_reduce_f32(self._h, d_buf, int(count), int(root), cuda_stream))
 
     def nccl_version(self):
         v = C.c_int32()
@@ -578,6 +586,23 @@ class ConvStream:
     def process_device_blocks(self, d_in, d_out, n_blocks, cuda_stream=None):
         """n_blocks consecutive blocks: d_in [n_blocks][n_sources][block], d_out [n_blocks][n_sources][2][block]."""
         _check(lib().arv2_stream_process_device_blocks(self._h, d_in, d_out, n_blocks, cuda_stream))
+
+    def process_blocks(self, blocks_in, want_out=True, want_mix=False):
+        """Up to 16 blocks, host buffers: blocks_in [n_blocks][n_sources][block] -> (out [n_blocks][n_sources][2][block] | None,
+        mix [n_blocks][2][block] | None)."""
+        x = np.ascontiguousarray(blocks_in, dtype=np.float32).reshape(-1, self.n_sources, self.block)
+        nb = x.shape[0]
+        out = np.empty((nb, self.n_sources, 2, self.block), np.float32) if want_out else None
+        mix = np.empty((nb, 2, self.block), np.float32) if want_mix else None
+        _check(lib().arv2_stream_process_blocks(self._h, _f(x), _f(out) if want_out else None, _f(mix) if want_mix else None, nb))
+        return out, mix
+
+    def mix_device(self, d_out, d_mix, n_blocks, cuda_stream=None):
+        _check(lib().arv2_stream_mix_device(self._h, d_out, d_mix, n_blocks, cuda_stream))
+
+    def set_gains(self, gains):
+        g = None if gains is None else np.ascontiguousarray(gains, dtype=np.float32)
+        _check(lib().arv2_stream_set_gains(self._h, _f(g) if g is not None else None))
 
     def reset(self):
         _check(lib().arv2_stream_reset(self._h))

@@ -112,11 +112,20 @@ struct arv2_stream {
     int device = 0, n_src = 0, block = 0, ir_len = 0, P = 0, slot = 0;
     cudaStream_t stream = nullptr;
     float2* d_tw = nullptr; float2* d_fdl = nullptr; float2* d_H[2] = {nullptr, nullptr};
-    float2** d_Hptr = nullptr; float2** h_Hptr = nullptr;
+    float2** d_Hptr = nullptr; float2** h_Hptr = nullptr;     // h_Hptr: one pinned entry per (source, swap parity)
     std::vector<int> active;
-    float* d_tail = nullptr; float* d_in = nullptr; float* d_out = nullptr; float* d_ir = nullptr;
-    float* h_in = nullptr; float* h_out = nullptr; float* h_ir = nullptr;
+    float* d_tail = nullptr; float* d_ir = nullptr;
+    float* d_in = nullptr; float* d_out = nullptr; float* d_mix = nullptr;     // device side of the host-buffer calls: [kHostBlocks][n_src][block], [..][n_src][2][block], [..][2][block]
+    float* d_gain = nullptr;                       // [n_src] mix gains (null = 1)
+    // host-buffer entry points: pinned, device-mapped staging the kernels read / write directly (no copy engine, no
+    // stream synchronisation per block), and a completion word the host spins on
+    float* h_in = nullptr; float* h_out = nullptr; float* h_mix = nullptr; float* h_ir = nullptr;
+    unsigned* h_flag = nullptr; unsigned flag_seq = 0; unsigned* d_done = nullptr;
+    // ordering between the stream the steps run on (the caller's or our own) and the IR swaps on our own stream
+    cudaEvent_t ev_step = nullptr, ev_swap = nullptr, ev_ir_copied = nullptr;
+    bool step_pending = false, swap_pending = false, ir_copy_pending = false;
 };
+constexpr int kHostBlocks = 16;                    // most blocks one host-buffer call carries (an RtAudio callback: 4096 frames = 8)
 
 namespace {
 
@@ -965,6 +974,17 @@ int arv2_comm_info(const arv2_comm* m, int32_t* rank, int32_t* n_ranks, int32_t*
     return ARV2_OK;
 }
 
+// Sum a device float buffer over the ranks onto `root` (in place there): the stereo mix of the sources each rank convolves.
+int arv2_comm_reduce_f32(arv2_comm* m, float* d_buf, size_t count, int32_t root, void* cuda_stream)
+{
+    REQUIRE(m && d_buf && root >= 0 && root < m->n_ranks, "arv2_comm_reduce_f32: bad argument");
+    const NcclApi* api = nccl_api(nullptr);
+    REQUIRE(api, "NCCL not loaded");
+    CK(cudaSetDevice(m->device));
+    if (m->n_ranks > 1) NCK(api->Reduce(d_buf, d_buf, count, ncclFloat32, ncclSum, root, m->comm, (cudaStream_t)cuda_stream));
+    return ARV2_OK;
+}
+
 void arv2_shard_range(int64_t n_rays, int32_t rank, int32_t n_ranks, int64_t* begin, int64_t* count)
 {
     const int64_t base = n_rays / n_ranks, rem = n_rays % n_ranks;
@@ -1246,8 +1266,12 @@ int arv2_stream_open(int32_t device, int32_t n_sources, int32_t block, int32_t i
     s->device = device; s->n_src = n_sources; s->block = block; s->ir_len = ir_length;
     s->P = (ir_length + block - 1) / block;
     const size_t spec = (size_t)s->P * block;          // float2 per (source) FDL or per ear
+    const size_t nin = (size_t)n_sources * block;
 #define CKS(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); arv2_stream_close(s); return ARV2_ERR_CUDA; } } while (0)
     CKS(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CKS(cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming));
+    CKS(cudaEventCreateWithFlags(&s->ev_swap, cudaEventDisableTiming));
+    CKS(cudaEventCreateWithFlags(&s->ev_ir_copied, cudaEventDisableTiming));
     CKS(cudaMalloc(&s->d_tw, 2 * block * sizeof(float2)));
     CKS(conv_upload_twiddles(s->d_tw, 2 * block, s->stream));
     CKS(cudaMalloc(&s->d_fdl, (size_t)n_sources * spec * sizeof(float2)));
@@ -1256,16 +1280,24 @@ int arv2_stream_open(int32_t device, int32_t n_sources, int32_t block, int32_t i
         CKS(cudaMemsetAsync(s->d_H[b], 0, (size_t)n_sources * 2 * spec * sizeof(float2), s->stream));
     }
     CKS(cudaMalloc(&s->d_Hptr, n_sources * sizeof(float2*)));
-    CKS(cudaMallocHost(&s->h_Hptr, n_sources * sizeof(float2*)));
+    CKS(cudaMallocHost(&s->h_Hptr, 2 * n_sources * sizeof(float2*)));
     s->active.assign(n_sources, 0);
-    for (int i = 0; i < n_sources; ++i) s->h_Hptr[i] = s->d_H[0] + (size_t)i * 2 * spec;
-    CKS(cudaMemcpyAsync(s->d_Hptr, s->h_Hptr, n_sources * sizeof(float2*), cudaMemcpyHostToDevice, s->stream));
-    CKS(cudaMalloc(&s->d_tail, (size_t)n_sources * 2 * block * sizeof(float)));
-    CKS(cudaMalloc(&s->d_in, (size_t)n_sources * block * sizeof(float)));
-    CKS(cudaMalloc(&s->d_out, (size_t)n_sources * 2 * block * sizeof(float)));
+    for (int i = 0; i < n_sources; ++i)
+        for (int b = 0; b < 2; ++b) s->h_Hptr[2 * i + b] = s->d_H[b] + (size_t)i * 2 * spec;
+    for (int i = 0; i < n_sources; ++i)
+        CKS(cudaMemcpyAsync(s->d_Hptr + i, s->h_Hptr + 2 * i, sizeof(float2*), cudaMemcpyHostToDevice, s->stream));
+    CKS(cudaMalloc(&s->d_tail, 2 * nin * sizeof(float)));
+    CKS(cudaMalloc(&s->d_in, (size_t)kHostBlocks * nin * sizeof(float)));
+    CKS(cudaMalloc(&s->d_out, (size_t)kHostBlocks * 2 * nin * sizeof(float)));
+    CKS(cudaMalloc(&s->d_mix, (size_t)kHostBlocks * 2 * block * sizeof(float)));
+    CKS(cudaMalloc(&s->d_done, sizeof(unsigned)));
+    CKS(cudaMemsetAsync(s->d_done, 0, sizeof(unsigned), s->stream));
     CKS(cudaMalloc(&s->d_ir, (size_t)2 * ir_length * sizeof(float)));
-    CKS(cudaMallocHost(&s->h_in, (size_t)n_sources * block * sizeof(float)));
-    CKS(cudaMallocHost(&s->h_out, (size_t)n_sources * 2 * block * sizeof(float)));
+    CKS(cudaHostAlloc(&s->h_in, (size_t)kHostBlocks * nin * sizeof(float), cudaHostAllocMapped));
+    CKS(cudaHostAlloc(&s->h_out, (size_t)kHostBlocks * 2 * nin * sizeof(float), cudaHostAllocMapped));
+    CKS(cudaHostAlloc(&s->h_mix, (size_t)kHostBlocks * 2 * block * sizeof(float), cudaHostAllocMapped));
+    CKS(cudaHostAlloc(&s->h_flag, sizeof(unsigned), cudaHostAllocMapped));
+    *s->h_flag = 0u;
     CKS(cudaMallocHost(&s->h_ir, (size_t)2 * ir_length * sizeof(float)));
 #undef CKS
     *out = s;
@@ -1276,6 +1308,7 @@ int arv2_stream_reset(arv2_stream* s)
 {
     REQUIRE(s, "null stream");
     CK(cudaSetDevice(s->device));
+    if (s->step_pending) { CK(cudaStreamWaitEvent(s->stream, s->ev_step, 0)); s->step_pending = false; }
     CK(cudaMemsetAsync(s->d_fdl, 0, (size_t)s->n_src * s->P * s->block * sizeof(float2), s->stream));
     CK(cudaMemsetAsync(s->d_tail, 0, (size_t)s->n_src * 2 * s->block * sizeof(float), s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -1283,18 +1316,21 @@ int arv2_stream_reset(arv2_stream* s)
     return ARV2_OK;
 }
 
+// New spectra go into the source's inactive buffer and the pointer table flips, all in order on the convolver's own
+// stream; steps may run on another stream (the caller's), so the two are tied with events: the swap waits for the last
+// step enqueued anywhere (a step still in flight may be reading the buffer that was active two swaps ago, or the
+// pointer table), and the next step waits for the swap.  Nothing blocks the host.
 static int stream_swap_ir(arv2_stream* s, int32_t source)
 {
-    // spectra go into the inactive buffer; the pointer table flips in stream order, i.e.
-    // exactly at a block boundary
     const size_t spec = (size_t)s->P * s->block;
     const int nb = 1 - s->active[source];
     float2* H = s->d_H[nb] + (size_t)source * 2 * spec;
+    if (s->step_pending) { CK(cudaStreamWaitEvent(s->stream, s->ev_step, 0)); s->step_pending = false; }
     CK(conv_ir_spectra(s->d_ir, 2, 0, s->ir_len, s->block, s->P, s->d_tw, H, s->stream));
     s->active[source] = nb;
-    s->h_Hptr[source] = H;
-    CK(cudaMemcpyAsync(s->d_Hptr + source, s->h_Hptr + source, sizeof(float2*), cudaMemcpyHostToDevice, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpyAsync(s->d_Hptr + source, s->h_Hptr + 2 * source + nb, sizeof(float2*), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaEventRecord(s->ev_swap, s->stream));
+    s->swap_pending = true;
     return ARV2_OK;
 }
 
@@ -1302,9 +1338,13 @@ int arv2_stream_set_ir(arv2_stream* s, int32_t source, const float* l, const flo
 {
     REQUIRE(s && l && r && source >= 0 && source < s->n_src, "arv2_stream_set_ir: bad argument");
     CK(cudaSetDevice(s->device));
+    if (s->ir_copy_pending) { CK(cudaEventSynchronize(s->ev_ir_copied)); s->ir_copy_pending = false; }     // the staging buffer is free again
     std::memcpy(s->h_ir, l, (size_t)s->ir_len * sizeof(float));
     std::memcpy(s->h_ir + s->ir_len, r, (size_t)s->ir_len * sizeof(float));
+    if (s->step_pending) { CK(cudaStreamWaitEvent(s->stream, s->ev_step, 0)); s->step_pending = false; }
     CK(cudaMemcpyAsync(s->d_ir, s->h_ir, (size_t)2 * s->ir_len * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaEventRecord(s->ev_ir_copied, s->stream));
+    s->ir_copy_pending = true;
     return stream_swap_ir(s, source);
 }
 
@@ -1312,58 +1352,126 @@ int arv2_stream_set_ir_device(arv2_stream* s, int32_t source, const float* dl, c
 {
     REQUIRE(s && dl && dr && source >= 0 && source < s->n_src, "arv2_stream_set_ir_device: bad argument");
     CK(cudaSetDevice(s->device));
+    if (s->step_pending) { CK(cudaStreamWaitEvent(s->stream, s->ev_step, 0)); s->step_pending = false; }
     CK(cudaMemcpyAsync(s->d_ir, dl, (size_t)s->ir_len * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
     CK(cudaMemcpyAsync(s->d_ir + s->ir_len, dr, (size_t)s->ir_len * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
     return stream_swap_ir(s, source);
 }
 
+int arv2_stream_set_gains(arv2_stream* s, const float* gains)
+{
+    REQUIRE(s, "null stream");
+    CK(cudaSetDevice(s->device));
+    if (!gains) { cudaFree(s->d_gain); s->d_gain = nullptr; return ARV2_OK; }
+    if (!s->d_gain) CK(cudaMalloc(&s->d_gain, (size_t)s->n_src * sizeof(float)));
+    CK(cudaMemcpy(s->d_gain, gains, (size_t)s->n_src * sizeof(float), cudaMemcpyHostToDevice));
+    return ARV2_OK;
+}
+
+// n_blocks steps on stream `st` (ours or the caller's), ordered after any pending IR swap; leaves the event the next
+// swap waits on
+static int enqueue_steps(arv2_stream* s, const float* d_in, float* d_out, int32_t n_blocks, cudaStream_t st)
+{
+    CK(cudaSetDevice(s->device));
+    if (s->swap_pending) { if (st != s->stream) CK(cudaStreamWaitEvent(st, s->ev_swap, 0)); s->swap_pending = false; }
+    const size_t nin = (size_t)s->n_src * s->block;
+    for (int32_t b = 0; b < n_blocks; ++b) {
+        s->slot = (s->slot + 1) % s->P;
+        ConvStreamArgs a{};
+        a.in = d_in + (size_t)b * nin; a.out = d_out + (size_t)b * 2 * nin;
+        a.fdl = s->d_fdl; a.H = (const float2* const*)s->d_Hptr; a.tail = s->d_tail; a.tw = s->d_tw;
+        a.n_src = s->n_src; a.block = s->block; a.P = s->P; a.slot = s->slot;
+        CK(conv_stream_step(a, st));
+    }
+    if (st != s->stream && n_blocks > 0) { CK(cudaEventRecord(s->ev_step, st)); s->step_pending = true; }
+    return ARV2_OK;
+}
+
 int arv2_stream_process_device(arv2_stream* s, const float* d_in, float* d_out, void* cuda_stream)
 {
     REQUIRE(s && d_in && d_out, "arv2_stream_process_device: null argument");
-    s->slot = (s->slot + 1) % s->P;
-    ConvStreamArgs a{};
-    a.in = d_in; a.out = d_out; a.fdl = s->d_fdl; a.H = (const float2* const*)s->d_Hptr; a.tail = s->d_tail; a.tw = s->d_tw;
-    a.n_src = s->n_src; a.block = s->block; a.P = s->P; a.slot = s->slot;
-    CK(conv_stream_step(a, cuda_stream ? (cudaStream_t)cuda_stream : s->stream));
-    return ARV2_OK;
+    return enqueue_steps(s, d_in, d_out, 1, cuda_stream ? (cudaStream_t)cuda_stream : s->stream);
 }
 
 int arv2_stream_process_device_blocks(arv2_stream* s, const float* d_in, float* d_out, int32_t n_blocks, void* cuda_stream)
 {
     REQUIRE(s && d_in && d_out && n_blocks >= 0, "arv2_stream_process_device_blocks: bad argument");
+    return enqueue_steps(s, d_in, d_out, n_blocks, cuda_stream ? (cudaStream_t)cuda_stream : s->stream);
+}
+
+int arv2_stream_mix_device(arv2_stream* s, const float* d_out, float* d_mix, int32_t n_blocks, void* cuda_stream)
+{
+    REQUIRE(s && d_out && d_mix && n_blocks >= 0, "arv2_stream_mix_device: bad argument");
+    CK(cudaSetDevice(s->device));
+    CK(conv_mix(d_out, s->n_src, s->block, n_blocks, s->d_gain, d_mix, cuda_stream ? (cudaStream_t)cuda_stream : s->stream));
+    return ARV2_OK;
+}
+
+// Host buffers in, host buffers out, n_blocks <= kHostBlocks: the steps read the input from mapped pinned memory and the
+// result lands in mapped pinned memory; one completion word instead of copies + a stream synchronisation.
+static int process_host(arv2_stream* s, const float* in, float* out, float* mix, int32_t n_blocks)
+{
+    REQUIRE(n_blocks >= 1 && n_blocks <= kHostBlocks, "at most 16 blocks per host-buffer call");
+    CK(cudaSetDevice(s->device));
     const size_t nin = (size_t)s->n_src * s->block;
-    for (int32_t b = 0; b < n_blocks; ++b) {
-        const int rc = arv2_stream_process_device(s, d_in + (size_t)b * nin, d_out + (size_t)b * 2 * nin, cuda_stream);
+    std::memcpy(s->h_in, in, (size_t)n_blocks * nin * sizeof(float));
+    const unsigned seq = ++s->flag_seq;
+    static const bool zero_copy = getenv("ARV2_CONV_ZEROCOPY") != nullptr;      // A/B: the step kernels read / write the mapped buffers themselves (slower, r08)
+    if (zero_copy) {
+        float* step_out = out ? s->h_out : s->d_out;
+        const int rc = enqueue_steps(s, s->h_in, step_out, n_blocks, s->stream);
         if (rc != ARV2_OK) return rc;
+        if (mix) CK(conv_mix(step_out, s->n_src, s->block, n_blocks, s->d_gain, s->h_mix, s->stream));
+        CK(conv_signal(s->h_flag, seq, s->stream));
+    } else {
+        // staging by one-CTA kernels over the mapped buffers: in -> device, steps (+ mix) on device buffers, results + completion word -> host
+        CK(conv_stage(s->h_in, s->d_in, (long long)n_blocks * (long long)nin, nullptr, nullptr, 0, nullptr, 0u, s->d_done, s->stream));
+        const int rc = enqueue_steps(s, s->d_in, s->d_out, n_blocks, s->stream);
+        if (rc != ARV2_OK) return rc;
+        if (mix) CK(conv_mix(s->d_out, s->n_src, s->block, n_blocks, s->d_gain, s->d_mix, s->stream));
+        CK(conv_stage(out ? s->d_out : nullptr, s->h_out, out ? (long long)n_blocks * 2 * (long long)nin : 0,
+                      mix ? s->d_mix : nullptr, s->h_mix, mix ? (long long)n_blocks * 2 * s->block : 0, s->h_flag, seq, s->d_done, s->stream));
     }
+    volatile unsigned* flag = s->h_flag;
+    for (unsigned long long spins = 0; *flag != seq; ++spins) {
+        if ((spins & 0xfffff) == 0xfffff) {                              // every ~1M polls: is the device still alive?
+            const cudaError_t e = cudaStreamQuery(s->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) { set_error(std::string("stream step: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
+        }
+    }
+    if (out) std::memcpy(out, s->h_out, (size_t)n_blocks * 2 * nin * sizeof(float));
+    if (mix) std::memcpy(mix, s->h_mix, (size_t)n_blocks * 2 * s->block * sizeof(float));
     return ARV2_OK;
 }
 
 int arv2_stream_process(arv2_stream* s, const float* in, float* out)
 {
     REQUIRE(s && in && out, "arv2_stream_process: null argument");
-    CK(cudaSetDevice(s->device));
-    const size_t nin = (size_t)s->n_src * s->block, nout = 2 * nin;
-    std::memcpy(s->h_in, in, nin * sizeof(float));
-    CK(cudaMemcpyAsync(s->d_in, s->h_in, nin * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    const int rc = arv2_stream_process_device(s, s->d_in, s->d_out, nullptr);
-    if (rc != ARV2_OK) return rc;
-    CK(cudaMemcpyAsync(s->h_out, s->d_out, nout * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    std::memcpy(out, s->h_out, nout * sizeof(float));
-    return ARV2_OK;
+    return process_host(s, in, out, nullptr, 1);
+}
+
+int arv2_stream_process_blocks(arv2_stream* s, const float* in, float* out, float* mix, int32_t n_blocks)
+{
+    REQUIRE(s && in && (out || mix), "arv2_stream_process_blocks: null argument");
+    return process_host(s, in, out, mix, n_blocks);
 }
 
 void arv2_stream_close(arv2_stream* s)
 {
     if (!s) return;
     cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_tw); cudaFree(s->d_fdl); cudaFree(s->d_H[0]); cudaFree(s->d_H[1]); cudaFree(s->d_Hptr);
-    cudaFree(s->d_tail); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_ir);
+    cudaFree(s->d_tail); cudaFree(s->d_in); cudaFree(s->d_out); cudaFree(s->d_mix); cudaFree(s->d_done); cudaFree(s->d_ir); cudaFree(s->d_gain);
     if (s->h_Hptr) cudaFreeHost(s->h_Hptr);
     if (s->h_in) cudaFreeHost(s->h_in);
     if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->h_mix) cudaFreeHost(s->h_mix);
+    if (s->h_flag) cudaFreeHost(s->h_flag);
     if (s->h_ir) cudaFreeHost(s->h_ir);
+    if (s->ev_step) cudaEventDestroy(s->ev_step);
+    if (s->ev_swap) cudaEventDestroy(s->ev_swap);
+    if (s->ev_ir_copied) cudaEventDestroy(s->ev_ir_copied);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -1374,16 +1482,19 @@ int arv2_live_callback(arv2_stream* s, const double* in, size_t n_in, arv2_ring*
     REQUIRE(s && in && ring, "arv2_live_callback: null argument");
     REQUIRE(s->n_src == 1, "arv2_live_callback needs a 1-source stream");
     REQUIRE(n_in % (size_t)s->block == 0, "n_in must be a multiple of the stream block");
-    std::vector<float> x((size_t)s->block), y((size_t)2 * s->block);
+    const size_t B = (size_t)s->block;
+    std::vector<float> x(std::min<size_t>(n_in, (size_t)kHostBlocks * B)), y(2 * x.size());
     std::vector<double> zipped(2 * n_in);
-    for (size_t b = 0; b < n_in / (size_t)s->block; ++b) {
-        for (int i = 0; i < s->block; ++i) x[i] = (float)in[b * s->block + i];
-        const int rc = arv2_stream_process(s, x.data(), y.data());
+    for (size_t done = 0; done < n_in; done += x.size()) {
+        const size_t nb = std::min<size_t>((n_in - done) / B, (size_t)kHostBlocks);     // one call carries up to 16 blocks
+        for (size_t i = 0; i < nb * B; ++i) x[i] = (float)in[done + i];
+        const int rc = process_host(s, x.data(), y.data(), nullptr, (int32_t)nb);
         if (rc != ARV2_OK) return rc;
-        for (int i = 0; i < s->block; ++i) {                     // gain 1/(ir_len/2) of the reference = 2x, then d_zipArrays
-            zipped[2 * (b * s->block + i)] = 2.0 * (double)y[i];
-            zipped[2 * (b * s->block + i) + 1] = 2.0 * (double)y[s->block + i];
-        }
+        for (size_t b = 0; b < nb; ++b)
+            for (size_t i = 0; i < B; ++i) {                     // gain 1/(ir_len/2) of the reference = 2x, then d_zipArrays
+                zipped[2 * (done + b * B + i)] = 2.0 * (double)y[b * 2 * B + i];
+                zipped[2 * (done + b * B + i) + 1] = 2.0 * (double)y[b * 2 * B + B + i];
+            }
     }
     return arv2_ring_add(ring, zipped.data(), zipped.size());
 }

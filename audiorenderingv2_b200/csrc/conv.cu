@@ -545,7 +545,76 @@ cudaError_t launch_cluster(K kernel, unsigned grid, size_t smem, cudaStream_t st
     return cudaLaunchKernelExC(&cfg, (const void*)kernel, args);
 }
 
+// Stereo mix: the per-source outputs of n_blocks steps summed over the sources in source order (deterministic;
+// an in-kernel RED.ADD from the 16 clusters of a step would make the sum depend on their timing).
+__global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ out, int n_src, int per_block /* 2 * block */, long long n,
+                                                  const float* __restrict__ gain, float* __restrict__ mix)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [n_blocks][2][block]
+    if (i >= n) return;
+    const long long b = i / per_block, t = i % per_block;
+    const float* src = out + (b * n_src) * per_block + t;
+    float acc = 0.f;
+    for (int s = 0; s < n_src; ++s) acc = fmaf(gain ? gain[s] : 1.f, src[(long long)s * per_block], acc);
+    mix[i] = acc;
+}
+
+// Host staging <-> device buffers by the SMs instead of the copy engines (a 32-64 KB cudaMemcpyAsync costs ~6 us of
+// latency each way, a one-CTA kernel over mapped pinned memory ~2 us), with the completion word written by the same
+// kernel once its stores are out.
+__global__ void __launch_bounds__(1024) stage_kernel(const float4* __restrict__ src0, float4* __restrict__ dst0, long long n0,
+                                                     const float4* __restrict__ src1, float4* __restrict__ dst1, long long n1,
+                                                     volatile unsigned* flag, unsigned value, unsigned* done)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i < n0; i += nt) dst0[i] = src0[i];
+    for (long long i = tid; i < n1; i += nt) dst1[i] = src1[i];
+    if (flag) {
+        // the CTA that arrives last publishes the completion word, after every CTA's stores went out at system scope
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned prev = gridDim.x > 1 ? atomicAdd(done, 1u) : 0u;
+            if (prev == gridDim.x - 1) {
+                if (gridDim.x > 1) *done = 0u;
+                __threadfence_system();
+                *flag = value;
+            }
+        }
+    }
+}
+
+// Stream-ordered completion mark in mapped host memory: the host-buffer entry points spin on it instead of paying a
+// cudaStreamSynchronize per 512-sample block.
+__global__ void flag_kernel(volatile unsigned* flag, unsigned value) { __threadfence_system(); *flag = value; }
+
 } // namespace
+
+cudaError_t conv_mix(const float* d_out, int n_src, int block, int n_blocks, const float* d_gain, float* d_mix, cudaStream_t stream)
+{
+    const long long n = (long long)n_blocks * 2 * block;
+    if (n <= 0) return cudaSuccess;
+    mix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_out, n_src, 2 * block, n, d_gain, d_mix);
+    return cudaGetLastError();
+}
+
+cudaError_t conv_stage(const float* src0, float* dst0, long long n0, const float* src1, float* dst1, long long n1,
+                       unsigned* mapped_flag, unsigned value, unsigned* d_done, cudaStream_t stream)
+{
+    // one CTA moves ~14 GB/s over PCIe: 16 KB per CTA, at most 16 CTAs
+    const long long bytes = (n0 + n1) * 4;
+    unsigned grid = (unsigned)((bytes + 16383) / 16384);
+    grid = grid < 1u ? 1u : (grid > 16u ? 16u : grid);
+    if (!d_done) grid = 1u;
+    stage_kernel<<<grid, 1024, 0, stream>>>((const float4*)src0, (float4*)dst0, n0 / 4, (const float4*)src1, (float4*)dst1, n1 / 4, mapped_flag, value, d_done);
+    return cudaGetLastError();
+}
+
+cudaError_t conv_signal(unsigned* mapped_flag, unsigned value, cudaStream_t stream)
+{
+    flag_kernel<<<1, 1, 0, stream>>>(mapped_flag, value);
+    return cudaGetLastError();
+}
 
 cudaError_t conv_upload_twiddles(float2* d_tw, int N, cudaStream_t stream)
 {

@@ -40,6 +40,15 @@ struct ConvStreamArgs {
 // + DSMEM reduction + stereo inverse FFT + overlap-add, in ONE cluster launch.
 cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream);
 
+// mix[b][ear][t] = sum over sources s (in order) of gain[s] * out[b][s][ear][t]; gain may be null (= 1).
+cudaError_t conv_mix(const float* d_out, int n_src, int block, int n_blocks, const float* d_gain, float* d_mix, cudaStream_t stream);
+// Copy (1..16 CTAs) of up to two float arrays (lengths multiples of 4, 16 B aligned; either may be empty) between mapped
+// pinned host memory and device memory, then -- if mapped_flag is given -- the completion word.
+cudaError_t conv_stage(const float* src0, float* dst0, long long n0, const float* src1, float* dst1, long long n1,
+                       unsigned* mapped_flag, unsigned value, unsigned* d_done /* zeroed device word, for > 1 CTA */, cudaStream_t stream);
+// *mapped_flag = value once everything enqueued on `stream` before this has completed (mapped, pinned host memory).
+cudaError_t conv_signal(unsigned* mapped_flag, unsigned value, cudaStream_t stream);
+
 struct ConvFileArgs {
     const float2* X;         // [n_seg*blocks_per_seg][block]
     const float2* H;         // [P][2][block]

@@ -399,7 +399,7 @@ def main():
     r.close()
     if not args.skip_extras and WORKLOAD == "c2":
         extras.update(bench_rerender(arv, torch, dev, local, scene, receiver, mats, args))
-        extras.update(bench_conv(arv, torch, dist, dev, local, rank, world, args))
+        extras.update(bench_conv(arv, torch, dist, dev, local, rank, world, args, comm=job.comm))
         extras.update(bench_lbvh(arv, scene, receiver, mats, local))
         extras.update(bench_c3_strong(job, scene, receiver, mats))
         del scene
@@ -601,9 +601,10 @@ def bench_lbvh(arv, scene, receiver, mats, local):
     return {"lbvh_create_ms": best, "lbvh_trace_grays_per_s": segs / (ms * 1e-3) / 1e9}
 
 
-def bench_conv(arv, torch, dist, dev, local, rank, world, args):
-    """conv us per 512-sample block: 16 sources x 2 s IR @48 kHz (96000 taps -> 188
-    partitions), sources sharded over the GPUs (BASELINE config 5)."""
+def bench_conv(arv, torch, dist, dev, local, rank, world, args, comm=None):
+    """conv us per 512-sample block: 16 sources x 2 s IR @48 kHz (96000 taps -> 188 partitions), sources sharded over
+    the GPUs (BASELINE config 5), each rank's sources mixed to stereo on the device and the per-rank mixes summed onto
+    rank 0 with ncclReduce inside libarv2 -- the one stereo buffer playback consumes."""
     n_src_total, block, ir_len = 16, 512, IR_SECONDS * FS
     n_src = max(1, n_src_total // world)
     st = arv.ConvStream(n_src, block, ir_len, device=local)
@@ -616,32 +617,53 @@ def bench_conv(arv, torch, dist, dev, local, rank, world, args):
     x = (0.1 * torch.randn(n_blocks, n_src, block, device=dev)).contiguous()
     y = torch.empty(n_src, 2, block, device=dev)
     yb = torch.empty(n_blocks, n_src, 2, block, device=dev)
+    mix = torch.empty(n_blocks, 2, block, device=dev)
     s = torch.cuda.Stream(device=dev)
+
+    def run(with_mix):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(s)
+        st.process_device_blocks(x.data_ptr(), yb.data_ptr(), n_blocks, s.cuda_stream)    # one call, steps overlap on the device
+        if with_mix:
+            st.mix_device(yb.data_ptr(), mix.data_ptr(), n_blocks, s.cuda_stream)
+            if comm is not None and world > 1:
+                comm.reduce_f32(mix.data_ptr(), mix.numel(), 0, s.cuda_stream)
+        e1.record(s)
+        torch.cuda.synchronize()
+        return 1e3 * e0.elapsed_time(e1) / n_blocks
+
     with torch.cuda.stream(s):
         for k in range(32):
             st.process_device(x[k].data_ptr(), y.data_ptr(), s.cuda_stream)
         torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(s)
-        st.process_device_blocks(x.data_ptr(), yb.data_ptr(), n_blocks, s.cuda_stream)    # one call, steps overlap on the device
-        e1.record(s)
-        torch.cuda.synchronize()
-        dev_us = 1e3 * e0.elapsed_time(e1) / n_blocks
-    # host-buffer path (H2D + step + D2H + sync per block): the live-callback call
-    xin = (0.1 * rng.standard_normal((n_src, block))).astype(np.float32)
+        run(True)
+        dev_us = run(False)
+        mix_us = run(True)
+    # host-buffer path (mapped pinned staging, completion word): the live-callback call, one block and 8 blocks
+    xin = (0.1 * rng.standard_normal((8, n_src, block))).astype(np.float32)
     for _ in range(8):
-        st.process(xin)
+        st.process(xin[0])
     t0 = time.perf_counter()
     for _ in range(64):
-        st.process(xin)
+        st.process(xin[0])
     host_us = 1e6 * (time.perf_counter() - t0) / 64
-    tt = torch.tensor([dev_us, host_us], dtype=torch.float64, device=dev)
+    t0 = time.perf_counter()
+    for _ in range(32):
+        st.process_blocks(xin, want_out=False, want_mix=True)
+    host8_us = 1e6 * (time.perf_counter() - t0) / (32 * 8)
+    tt = torch.tensor([dev_us, host_us, mix_us, host8_us], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     st.close()
     bytes_per_block_src = 3 * 188 * 512 * 8 + 4096 + 6144
     return {"conv_us_per_block": float(tt[0].item()), "conv_us_per_block_host_buffers": float(tt[1].item()),
+            "conv_us_per_block_with_stereo_mix": float(tt[2].item()),
+            "conv_us_per_block_host_buffers_8_blocks_mix": float(tt[3].item()),
             "conv_sources_per_gpu": n_src, "conv_deadline_us": 1e6 * block / FS,
+            "conv_mix": "per-rank device mix of its sources + ncclReduce(sum) onto rank 0 (arv2_stream_mix_device, arv2_comm_reduce_f32)",
             "conv_achieved_gbs": n_src * bytes_per_block_src / (float(tt[0].item()) * 1e-6) / 1e9}
 
 

@@ -195,6 +195,8 @@ int arv2_comm_unique_id(void* id128);
 int arv2_comm_create(int32_t device, int32_t rank, int32_t n_ranks, const void* id128, arv2_comm** out);
 int arv2_comm_info(const arv2_comm* comm, int32_t* rank, int32_t* n_ranks, int32_t* nccl_version);
 void arv2_comm_destroy(arv2_comm* comm);
+/* ncclReduce(sum, float32) of `count` device floats onto `root`, in place (the stereo mix of sharded sources). */
+int arv2_comm_reduce_f32(arv2_comm* comm, float* d_buf, size_t count, int32_t root, void* cuda_stream);
 /* The contiguous slice [begin, begin+count) of an n_rays set that `rank` of n_ranks traces. */
 void arv2_shard_range(int64_t n_rays, int32_t rank, int32_t n_ranks, int64_t* begin, int64_t* count);
 /* AudioRenderer::render on n_ranks GPUs: trace this rank's slice of the seeded ray set, ncclAllReduce
@@ -279,7 +281,9 @@ typedef struct arv2_stream arv2_stream;
 int arv2_stream_open(int32_t device, int32_t n_sources, int32_t block, int32_t ir_length,
                      arv2_stream** out);
 /* Load / swap the IR of one source (host float[ir_length] per ear).  Takes effect
- * atomically at the next block boundary (double-buffered partition spectra). */
+ * atomically at the next block boundary (double-buffered partition spectra).  Asynchronous: the
+ * spectra are computed and the pointer flips in stream order; steps enqueued before the call (on
+ * any stream) finish with the old IR, steps enqueued after it use the new one. */
 int arv2_stream_set_ir(arv2_stream* s, int32_t source, const float* ir_left, const float* ir_right);
 /* Same, from device pointers (e.g. arv2_ir_device of a renderer on this GPU). */
 int arv2_stream_set_ir_device(arv2_stream* s, int32_t source, const float* d_left, const float* d_right);
@@ -293,6 +297,17 @@ int arv2_stream_process_device(arv2_stream* s, const float* d_in, float* d_out, 
  * device-resident, enqueued on `cuda_stream` without syncing.  The steps are launched back to back and overlap on
  * the device (programmatic dependent launch); the result is the one n_blocks single-block calls give. */
 int arv2_stream_process_device_blocks(arv2_stream* s, const float* d_in, float* d_out, int32_t n_blocks, void* cuda_stream);
+/* Host buffers, up to 16 consecutive blocks per call (one RtAudio callback): in = float[n_blocks][n_sources][block];
+ * out (may be NULL) = float[n_blocks][n_sources][2][block]; mix (may be NULL) = float[n_blocks][2][block], the stereo
+ * sum of the sources.  The kernels read and write pinned, device-mapped staging directly and the call returns on a
+ * completion word: no copy-engine transfers, no stream synchronisation. */
+int arv2_stream_process_blocks(arv2_stream* s, const float* in, float* out, float* mix, int32_t n_blocks);
+/* The stereo buffer playback consumes (OR/main.cpp:69-97): d_mix[b][ear][t] = sum over this stream's sources, in source
+ * order, of gain[s] * d_out[b][s][ear][t] (device buffers; enqueued on `cuda_stream`).  Across GPUs, sum the per-rank
+ * mixes onto one rank with arv2_comm_reduce_f32. */
+int arv2_stream_mix_device(arv2_stream* s, const float* d_out, float* d_mix, int32_t n_blocks, void* cuda_stream);
+/* Per-source gains of the mix (host float[n_sources]; NULL = all 1). */
+int arv2_stream_set_gains(arv2_stream* s, const float* gains);
 int arv2_stream_reset(arv2_stream* s);
 void arv2_stream_close(arv2_stream* s);
 

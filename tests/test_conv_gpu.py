@@ -173,9 +173,10 @@ def test_stream_ir_swap_and_reset():
 
 
 def test_stream_ir_swap_between_overlapped_blocks():
-    """An IR swap enqueued between two runs of overlapped device-resident blocks lands exactly at the block boundary
-    (the spectra kernel and the pointer copy are ordinary stream operations: the step after them waits for them, the
-    steps before them are complete): bit-identical to the serialised host-buffer path."""
+    """An IR swap enqueued -- without any host synchronisation -- between two runs of overlapped device-resident blocks
+    on the CALLER'S stream lands exactly at the block boundary: the swap (spectra kernel + pointer flip on the
+    convolver's own stream) waits on an event for the steps already enqueued, the steps enqueued after it wait on an
+    event for the swap.  Bit-identical to the serialised host-buffer path."""
     import torch
     block, ir_len, n_src, half = 512, 6000, 2, 24
     rng = np.random.default_rng(21)
@@ -194,7 +195,8 @@ def test_stream_ir_swap_between_overlapped_blocks():
             s = torch.cuda.Stream(device=dev)
             torch.cuda.synchronize()
             st.process_device_blocks(dx.data_ptr(), dy.data_ptr(), half, s.cuda_stream)
-            torch.cuda.synchronize()          # set_ir runs on the stream object's own CUDA stream
+            # no synchronisation here: set_ir works on the convolver's own stream and orders itself against the steps
+            # in flight on `s` with events (the swap waits for them, the next steps wait for the swap)
             for i, (a, b) in enumerate(irs_b):
                 st.set_ir(i, a, b)
             st.process_device_blocks(dx[half].data_ptr(), dy[half].data_ptr(), half, s.cuda_stream)
@@ -277,3 +279,75 @@ def test_c5_sixteen_sources_two_second_ir():
             ref = np.concatenate([oracle.direct_conv_window(x[i], irs[i][ear], b, n) for b, n in windows])
             assert rel_l2(got, ref) <= TOL, (i, ear)
     st.close()
+
+
+def test_stream_two_quick_swaps_do_not_race():
+    """Two swaps of the same source back to back while steps are in flight on another stream: the second one rewrites
+    the buffer that was active before the first -- which a running step may still read unless the swap waits for it."""
+    import torch
+    block, ir_len, n_src, nb = 512, 20000, 3, 40
+    rng = np.random.default_rng(31)
+    irs = [[(decaying_ir(ir_len, 400 + 10 * v + i, 0.1, 48000), decaying_ir(ir_len, 450 + 10 * v + i, 0.08, 48000)) for i in range(n_src)] for v in range(3)]
+    x = (0.1 * rng.standard_normal((2 * nb, n_src, block))).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    st = arv.ConvStream(n_src, block, ir_len)
+    for i, (a, b) in enumerate(irs[0]):
+        st.set_ir(i, a, b)
+    dx = torch.from_numpy(x).to(dev); dy = torch.empty(2 * nb, n_src, 2, block, device=dev)
+    s = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    st.process_device_blocks(dx.data_ptr(), dy.data_ptr(), nb, s.cuda_stream)
+    for v in (1, 2):
+        for i, (a, b) in enumerate(irs[v]):
+            st.set_ir(i, a, b)
+    st.process_device_blocks(dx[nb].data_ptr(), dy[nb].data_ptr(), nb, s.cuda_stream)
+    torch.cuda.synchronize()
+    got = dy.cpu().numpy()
+    ref = arv.ConvStream(n_src, block, ir_len)
+    for i, (a, b) in enumerate(irs[0]):
+        ref.set_ir(i, a, b)
+    want = np.empty_like(got)
+    for k in range(2 * nb):
+        if k == nb:
+            for i, (a, b) in enumerate(irs[2]):
+                ref.set_ir(i, a, b)
+        want[k] = ref.process(x[k])
+    assert np.array_equal(got, want)
+    st.close(); ref.close()
+
+
+def test_stream_host_blocks_and_stereo_mix():
+    """arv2_stream_process_blocks: up to 16 blocks per call through mapped pinned buffers = the same blocks one call at
+    a time, bit for bit; the stereo mix (the buffer playback consumes) = the sources summed in order with their gains,
+    and matches the fp64 direct convolutions summed."""
+    n_src, block, ir_len, nb = 5, 512, 9000, 32
+    rng = np.random.default_rng(77)
+    irs = [(decaying_ir(ir_len, 500 + i, 0.1, 48000), decaying_ir(ir_len, 520 + i, 0.07, 48000)) for i in range(n_src)]
+    x = (0.1 * rng.standard_normal((nb, n_src, block))).astype(np.float32)
+    gains = np.array([1.0, 0.5, 2.0, 0.25, 1.5], np.float32)
+    a = arv.ConvStream(n_src, block, ir_len); b = arv.ConvStream(n_src, block, ir_len)
+    for st in (a, b):
+        for i, (l, r) in enumerate(irs):
+            st.set_ir(i, l, r)
+    a.set_gains(gains)
+    one = np.stack([b.process(x[k]) for k in range(nb)])
+    outs, mixes = [], []
+    for k0 in range(0, nb, 16):
+        o, m = a.process_blocks(x[k0:k0 + 16], want_out=True, want_mix=True)
+        outs.append(o); mixes.append(m)
+    out, mix = np.concatenate(outs), np.concatenate(mixes)
+    assert np.array_equal(out, one)
+    acc = np.zeros((nb, 2, block), np.float32)
+    for s_ in range(n_src):
+        acc = (np.float32(gains[s_]) * out[:, s_].astype(np.float64) + acc.astype(np.float64)).astype(np.float32)      # fmaf(g, x, acc)
+    assert np.allclose(mix, acc, rtol=2e-7, atol=1e-12)          # one fused multiply-add per source, in source order
+    xs = x.transpose(1, 0, 2).reshape(n_src, nb * block)
+    for ear in (0, 1):
+        want = sum(float(gains[i]) * oracle.direct_conv(xs[i], irs[i][ear])[: nb * block] for i in range(n_src))
+        got = mix[:, ear, :].reshape(-1)
+        assert rel_l2(got, want) <= TOL
+    _, m2 = a.process_blocks(x[:3], want_out=False, want_mix=True)      # mix only: per-source outputs stay on the device
+    assert m2.shape == (3, 2, block) and np.isfinite(m2).all()
+    with pytest.raises(arv.Arv2Error):
+        a.process_blocks(np.zeros((17, n_src, block), np.float32))
+    a.close(); b.close()
