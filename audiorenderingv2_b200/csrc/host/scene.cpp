@@ -8,8 +8,9 @@
 //                       group / usemtl flushing), :1385-1593 (polygon ear clipping)
 //   placeReceiver       OR/OptixModel.cpp:153-257
 //   getMaterialAbsorption OR/AudioRenderer.cpp:34-56
-// The output is pinned bit-for-bit against the reference's loader by
-// tests/test_scene_frontend.py (golden meshes generated with oracle/_ref/tinyobj_dump).
+// The output is pinned bit-for-bit against the reference's own code compiled where it lies: the loader against
+// tiny_obj_loader.h and loadOBJ (tests/test_host_cpu.py::test_cpp_obj_loader_matches_reference_tinyobj, tests/golden/
+// meshes.json, ref_loadobj.json), the placement against placeReceiver (tests/test_pin_cpu.py, tests/golden/ref_placement.npz).
 #include <cmath>
 #include <cstdlib>
 #include <cstring>

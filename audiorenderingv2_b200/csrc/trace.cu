@@ -7,18 +7,20 @@
 //   __miss__radiance          OR/devicePrograms.cu:186-190  -> "no hit" branch
 //   fillZeros / addIRs        OR/kernels.cu:77-97,519-536   -> cudaMemsetAsync / finalize_kernel
 //
-// Design: persistent CTAs; every warp keeps 32 paths in flight and refills lanes whose
-// path ended from a warp-local chunk of the seeded ray set (ballot + popc compaction),
-// so no ray state ever goes through HBM.  The r02 profile showed the tracer bound by the
-// L1 data pipe at one wavefront per lane and load instruction (the whole BVH is L2/L1
-// resident, DRAM idles), so every 64 B record (binary node with both child boxes, triangle
-// with its precomputed normal) is fetched with two 256-bit loads (arv2_internal.h).
-// Quantised 32 B binary nodes and 4-wide nodes (8- and 16-bit boxes) were built and measured:
-// all slower or equal, the kernel is bound by the latency of the dependent node chain
-// (profiles/r03_trace_layout_experiments.md).
-// Receiver deposits are aggregated across the warp (match.any) and accumulated in an fp64
-// histogram with native RED.F64, which makes the result independent of the deposit order
-// to ~1e-16.
+// Design (details at each kernel):
+//   wave_kernel      the tracer: persistent, one 32-warp CTA per SM, breadth-first.  A task = 32 paths of one depth
+//                    advanced by 8 segments; survivors are re-packed (ballot / popc) into per-SM, per-depth queues
+//                    whose counters live in shared memory; rays are started in the order of their emission direction
+//                    (direction_keys_kernel + radix sort) so a warp is a coherent bundle for the first bounces.
+//                    trace_kernel = depth-first fallback (no queue memory / A-B), trace2_kernel = the decoupled-lane
+//                    experiment of r03.
+//   closest_hit      software BVH: binary 64 B nodes with both child boxes in the parent, every record fetched with
+//                    256-bit loads (a divergent gather costs the L1 data pipe one wavefront per lane and load
+//                    instruction; the whole scene is L2-resident and DRAM idles).  Quantised 32 B nodes and 4-wide
+//                    nodes were built and measured slower (profiles/r03, r07 sections 18 and 22).
+//   deposits         aggregated across the warp (match.any) and accumulated in an fp64 histogram with native RED.F64:
+//                    the result does not depend on the deposit order to ~1e-16.
+//   re-render        rr_mask_kernel + rr_walk_kernel over the packed path cache (pc_* kernels build it).
 #include <climits>
 #include <cstdlib>
 
