@@ -954,6 +954,16 @@ int arv2_comm_create(int32_t device, int32_t rank, int32_t n_ranks, const void* 
     m->device = device; m->rank = rank; m->n_ranks = n_ranks;
     const ncclResult_t r = api->CommInitRank(&m->comm, n_ranks, id, rank);
     if (r != ncclSuccess) { set_error(std::string("ncclCommInitRank: ") + api->GetErrorString(r)); delete m; return ARV2_ERR_CUDA; }
+    // NCCL connects its channels at the first collective (~1 s on 8 GPUs): pay that here, not in the first render
+    if (n_ranks > 1) {
+        double* d = nullptr;
+        if (cudaMalloc(&d, 16 * sizeof(double)) == cudaSuccess) {
+            cudaMemset(d, 0, 16 * sizeof(double));
+            api->AllReduce(d, d, 16, ncclFloat64, ncclSum, m->comm, (cudaStream_t)0);
+            cudaStreamSynchronize((cudaStream_t)0);
+            cudaFree(d);
+        }
+    }
     *out = m;
     return ARV2_OK;
 }

@@ -58,3 +58,57 @@ def test_multi_renderer_equals_single(golden_scenes, golden_receiver):
         assert np.allclose(l, l2, rtol=1e-6, atol=0) and np.allclose(rr, r2, rtol=1e-6, atol=0)
         m.close()
         a.setSphereCenterInOptix(c.center, c.yaw); a.render()
+
+
+def test_sources_sharded_over_two_gpus_mix_to_one_stereo_buffer():
+    """BASELINE configs[4]'s sharding: source s lives on GPU s mod R; every rank convolves its sources, mixes them to
+    stereo on the device and the per-rank mixes are summed onto rank 0 by ncclReduce inside libarv2.  Rank 0's buffer
+    must be the fp64 direct convolution of every source with its IR, summed."""
+    import threading
+    import torch
+    import oracle
+    from audiorenderingv2_b200 import sharding
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n_total, block, ir_len, nb = 2, 6, 512, 12000, 40
+    rng = np.random.default_rng(8)
+    t = np.arange(ir_len) / 48000.0
+    irs = [((rng.standard_normal(ir_len) * np.exp(-6.9 * t / 0.15)).astype(np.float32),
+            (rng.standard_normal(ir_len) * np.exp(-6.9 * t / 0.1)).astype(np.float32)) for _ in range(n_total)]
+    x = (0.1 * rng.standard_normal((n_total, nb * block))).astype(np.float32)
+    uid = arv.Comm.unique_id()
+    result, errors = {}, []
+
+    def rank_main(rank):
+        try:
+            torch.cuda.set_device(rank)
+            dev = torch.device("cuda", rank)
+            mine = sharding.sources_of(rank, world, n_total)
+            comm = arv.Comm(rank, rank, world, uid)
+            st = arv.ConvStream(len(mine), block, ir_len, device=rank)
+            for j, s in enumerate(mine):
+                st.set_ir(j, *irs[s])
+            xb = torch.from_numpy(np.ascontiguousarray(x[mine].reshape(len(mine), nb, block).transpose(1, 0, 2))).to(dev)
+            yb = torch.empty(nb, len(mine), 2, block, device=dev)
+            mix = torch.empty(nb, 2, block, device=dev)
+            s_ = torch.cuda.Stream(device=dev)
+            st.process_device_blocks(xb.data_ptr(), yb.data_ptr(), nb, s_.cuda_stream)
+            st.mix_device(yb.data_ptr(), mix.data_ptr(), nb, s_.cuda_stream)
+            comm.reduce_f32(mix.data_ptr(), mix.numel(), 0, s_.cuda_stream)
+            s_.synchronize()
+            result[rank] = mix.cpu().numpy()
+            st.close(); comm.close()
+        except Exception as e:      # noqa: BLE001
+            errors.append((rank, repr(e)))
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t_ in th:
+        t_.start()
+    for t_ in th:
+        t_.join(timeout=120)
+    assert not errors, errors
+    got = result[0]
+    for ear in (0, 1):
+        want = sum(oracle.direct_conv(x[s], irs[s][ear])[: nb * block] for s in range(n_total))
+        g = got[:, ear, :].reshape(-1)
+        assert np.linalg.norm(g - want) <= 1e-5 * np.linalg.norm(want)
