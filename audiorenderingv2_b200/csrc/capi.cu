@@ -1385,13 +1385,27 @@ static int enqueue_steps(arv2_stream* s, const float* d_in, float* d_out, int32_
     CK(cudaSetDevice(s->device));
     if (s->swap_pending) { if (st != s->stream) CK(cudaStreamWaitEvent(st, s->ev_swap, 0)); s->swap_pending = false; }
     const size_t nin = (size_t)s->n_src * s->block;
-    for (int32_t b = 0; b < n_blocks; ++b) {
-        s->slot = (s->slot + 1) % s->P;
+    // Experiment (ARV2_CONV_PERSISTENT=1, r08): the blocks of one call in ONE cluster launch, every source's cluster looping
+    // over them.  Bit-identical, but slower: 8.6 us per block against 6.5 (2 sources) and 11.0 against 8.1 (16 sources) --
+    // with one launch per block and programmatic dependent launch, step k+1's accumulation runs in a second CTA on the
+    // same SM while step k's rank 0 is in its FFTs; a looping cluster serialises them (profiles/r08_conv.md).
+    const bool persistent = getenv("ARV2_CONV_PERSISTENT") != nullptr;
+    if (n_blocks > 1 && persistent) {
         ConvStreamArgs a{};
-        a.in = d_in + (size_t)b * nin; a.out = d_out + (size_t)b * 2 * nin;
+        a.in = d_in; a.out = d_out;
         a.fdl = s->d_fdl; a.H = (const float2* const*)s->d_Hptr; a.tail = s->d_tail; a.tw = s->d_tw;
-        a.n_src = s->n_src; a.block = s->block; a.P = s->P; a.slot = s->slot;
-        CK(conv_stream_step(a, st));
+        a.n_src = s->n_src; a.block = s->block; a.P = s->P; a.slot = (s->slot + 1) % s->P; a.n_blocks = n_blocks;
+        CK(conv_stream_blocks(a, st));
+        s->slot = (s->slot + n_blocks) % s->P;
+    } else {
+        for (int32_t b = 0; b < n_blocks; ++b) {
+            s->slot = (s->slot + 1) % s->P;
+            ConvStreamArgs a{};
+            a.in = d_in + (size_t)b * nin; a.out = d_out + (size_t)b * 2 * nin;
+            a.fdl = s->d_fdl; a.H = (const float2* const*)s->d_Hptr; a.tail = s->d_tail; a.tw = s->d_tw;
+            a.n_src = s->n_src; a.block = s->block; a.P = s->P; a.slot = s->slot; a.n_blocks = 1;
+            CK(conv_stream_step(a, st));
+        }
     }
     if (st != s->stream && n_blocks > 0) { CK(cudaEventRecord(s->ev_step, st)); s->step_pending = true; }
     return ARV2_OK;

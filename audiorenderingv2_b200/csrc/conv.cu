@@ -474,6 +474,148 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// stream_blocks_kernel (experiment, ARV2_CONV_PERSISTENT=1; measured SLOWER, see below): the n_blocks consecutive steps
+// of one call (arv2_stream_process_device_blocks: an RtAudio callback of the reference carries 4096 frames = 8 blocks)
+// in ONE cluster launch.  stream_step_kernel is launched once per block, and even with programmatic dependent launch two
+// dependent cluster launches are ~2 us apart; here every source's 8-CTA cluster loops over the blocks.  Per block: all
+// ranks accumulate their old partitions through the TMA ring; rank 0 transforms the newest input block, publishes its
+// spectrum in the delay line and multiplies partition 0, rank C-1 takes partition 1 (published one block earlier);
+// cluster-wide DSMEM reduction; rank 0 inverse-transforms and overlap-adds with the tails it keeps in registers.
+// Results are bit-identical to n_blocks launches of stream_step_kernel (same partition split, same summation order).
+// Measured (r08, profiles/r08_conv.md): 8.6 us per block at 1-4 sources, 11.0 at 16, against 6.5 / 8.1 for one launch
+// per block: the period of a looping cluster is rank 0's whole chain (its share of the ring + 5.7 us of input load, two
+// 1024-point FFTs and the reduction), while separate launches keep two steps resident per SM and run step k+1's ring
+// under step k's FFTs.  Kept as the starting point for splitting the two FFTs over two ranks.
+#ifndef ARV2_CONV_PERSIST_FFTCOST
+#define ARV2_CONV_PERSIST_FFTCOST 8     // same split as stream_step_kernel: the accumulation order must not change
+#endif
+template <int BPT>
+__global__ void __launch_bounds__(kConvStepThreads) stream_blocks_kernel(const ConvStreamArgs a)
+{
+    extern __shared__ __align__(128) float2 smem[];
+    __shared__ unsigned long long full[kStages], empty[kStages];
+    const int block = a.block, N = 2 * block;
+    float2* stw = smem; float2* ring = stw + N;
+    float2* bufa = ring; float2* bufb = bufa + N; float2* part = bufb + N;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    constexpr unsigned C = kConvCluster;
+    const int src = blockIdx.x / C;
+    float2* fdl = a.fdl + (size_t)src * a.P * block;
+    const float2* H = a.H[src];
+    const bool consumer = threadIdx.x < kConvThreads;
+    if (consumer)
+        for (int t = threadIdx.x; t < N; t += kConvThreads) stw[t] = a.tw[t];
+
+    // the split of the old partitions over the ranks (as in stream_step_kernel)
+    const int T = max(0, a.P - 2);
+    int n0 = (T - kFftCostInPartitions * ((int)C - 1)) / (int)C;
+    n0 = max(0, min(T, n0));
+    int first, n;
+    if (rank == 0) { first = 2; n = n0; }
+    else {
+        const int rest = T - n0, per = rest / ((int)C - 1), extra = rest % ((int)C - 1), r1 = (int)rank - 1;
+        first = 2 + n0 + r1 * per + min(r1, extra);
+        n = per + (r1 < extra ? 1 : 0);
+    }
+    // static IR rows of the partition this rank multiplies late (rank 0: partition 0, rank C-1: partition 1), and the
+    // overlap-add tails of this thread's output samples (rank 0): registers for the whole call
+    const int pq = rank == 0 ? 0 : 1;
+    const bool late = (rank == 0 || (rank == C - 1 && a.P > 1)) && consumer;
+    float2 hqL[BPT], hqR[BPT];
+    float tl[BPT], tr[BPT];
+    float* tail = a.tail + (size_t)src * 2 * block;
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+        const int k = threadIdx.x * BPT + i;
+        const bool on = late && k < block;
+        hqL[i] = on ? H[(size_t)pq * 2 * block + k] : make_float2(0.f, 0.f);
+        hqR[i] = on ? H[((size_t)pq * 2 + 1) * block + k] : make_float2(0.f, 0.f);
+        const bool ont = rank == 0 && consumer && k < block;
+        tl[i] = ont ? tail[k] : 0.f; tr[i] = ont ? tail[block + k] : 0.f;
+    }
+    const size_t in_step = (size_t)a.n_src * block, out_step = 2 * in_step;
+    const float sc = 1.0f / (float)N;
+
+    for (int b = 0; b < a.n_blocks; ++b) {
+        const int slot = (a.slot + b) % a.P;
+        // the ring's barriers start every block afresh (its memory was the FFT buffers of the previous block)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int st = 0; st < kStages; ++st) {
+                if (b > 0) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[st])) : "memory"); asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&empty[st])) : "memory"); }
+                mbar_init(&full[st], 1); mbar_init(&empty[st], kConvThreads / 32);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        float2 accL[BPT], accR[BPT];
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) { accL[i] = make_float2(0.f, 0.f); accR[i] = make_float2(0.f, 0.f); }
+        {
+            int s0 = slot - first; if (s0 < 0) s0 += a.P;
+            MacRows r;
+            r.x = fdl + (size_t)s0 * block; r.x_step = -(long long)block; r.x_lo = fdl; r.x_wrap = (long long)a.P * block;
+            r.h = H + (size_t)first * 2 * block; r.h_step = 2 * (long long)block;
+            mac_pipeline<BPT>(ring, full, empty, n, block, r, accL, accR);
+        }
+        __syncthreads();                                  // the ring has drained: its memory becomes bufa / bufb / part
+        if (rank == 0) {
+            const float* in = a.in + (size_t)b * in_step + (size_t)src * block;
+            float2* slot_row = fdl + (size_t)slot * block;
+            for (int t = threadIdx.x; t < N; t += blockDim.x) bufa[t] = make_float2(t < block ? in[t] : 0.f, 0.f);
+            __syncthreads();
+            const float2* F = fft_smem(bufa, bufb, N, stw, false);
+            if (consumer) {
+#pragma unroll
+                for (int i = 0; i < BPT; ++i) {
+                    const int k = threadIdx.x * BPT + i;
+                    if (k < block) {
+                        const float2 xv = k == 0 ? make_float2(F[0].x, F[block].x) : F[k];
+                        slot_row[k] = xv;
+                        mac_bin(k, xv, hqL[i], hqR[i], accL[i], accR[i]);
+                    }
+                }
+            }
+            // the spectrum just stored is read by the other CTAs' bulk copies (async proxy) from the next block on
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncthreads();                              // F (bufa or bufb) is read above; part and bufa are written next
+        }
+        if (rank == C - 1 && a.P > 1 && consumer) {
+            // the previous block: published by rank 0 one iteration (or one call) ago, before a cluster barrier
+            const int s1 = slot >= 1 ? slot - 1 : slot - 1 + a.P;
+            const float2* X1 = fdl + (size_t)s1 * block;
+#pragma unroll
+            for (int i = 0; i < BPT; ++i) {
+                const int k = threadIdx.x * BPT + i;
+                if (k < block) mac_bin(k, __ldcg(X1 + k), hqL[i], hqR[i], accL[i], accR[i]);
+            }
+        }
+        float2* y = reduce_and_inverse<BPT>(cluster, part, bufa, bufb, block, stw, accL, accR);
+        if (y && consumer) {
+            float* out = a.out + (size_t)b * out_step + (size_t)src * 2 * block;
+#pragma unroll
+            for (int i = 0; i < BPT; ++i) {
+                const int t = threadIdx.x * BPT + i;
+                if (t < block) {
+                    const float2 lo = y[t], hi = y[block + t];
+                    out[t] = fmaf(lo.x, sc, tl[i]);
+                    out[block + t] = fmaf(lo.y, sc, tr[i]);
+                    tl[i] = hi.x * sc; tr[i] = hi.y * sc;
+                }
+            }
+        }
+    }
+    if (rank == 0 && consumer) {
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const int t = threadIdx.x * BPT + i;
+            if (t < block) { tail[t] = tl[i]; tail[block + t] = tr[i]; }
+        }
+    }
+}
+
 template <int BPT>
 __global__ void __launch_bounds__(kConvStepThreads) file_kernel(const ConvFileArgs a, int out_blocks_per_seg)
 {
@@ -662,6 +804,22 @@ cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream)
     case 1: return launch_cluster(stream_step_kernel<1>, grid, smem, stream, kargs, pdl);
     case 2: return launch_cluster(stream_step_kernel<2>, grid, smem, stream, kargs, pdl);
     case 4: return launch_cluster(stream_step_kernel<4>, grid, smem, stream, kargs, pdl);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t conv_stream_blocks(const ConvStreamArgs& a, cudaStream_t stream)
+{
+    if (a.n_blocks <= 0) return cudaSuccess;
+    ConvStreamArgs args = a;
+    void* kargs[] = {&args};
+    const unsigned grid = (unsigned)(a.n_src * kConvCluster);
+    const size_t smem = step_smem_bytes(a.block);
+    const int bpt = (a.block + kConvThreads - 1) / kConvThreads;
+    switch (bpt) {
+    case 1: return launch_cluster(stream_blocks_kernel<1>, grid, smem, stream, kargs);
+    case 2: return launch_cluster(stream_blocks_kernel<2>, grid, smem, stream, kargs);
+    case 4: return launch_cluster(stream_blocks_kernel<4>, grid, smem, stream, kargs);
     default: return cudaErrorInvalidValue;
     }
 }

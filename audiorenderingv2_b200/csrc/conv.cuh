@@ -34,11 +34,14 @@ struct ConvStreamArgs {
     const float2* const* H;  // [n_src] -> [P][2][block] active IR spectra of each source
     float* tail;             // [n_src][2][block] overlap-add tails
     const float2* tw;
-    int n_src, block, P, slot; // slot = ring position of the newest block
+    int n_src, block, P, slot; // slot = ring position of the newest block (of the first block for conv_stream_blocks)
+    int n_blocks;              // conv_stream_blocks: consecutive blocks; in / out advance by n_src*block / n_src*2*block floats per block
 };
 // One streaming step for all sources: forward FFT + FDL write + partitioned spectral MAC
 // + DSMEM reduction + stereo inverse FFT + overlap-add, in ONE cluster launch.
 cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream);
+// a.n_blocks consecutive steps in ONE cluster launch (every source's cluster loops over the blocks); same results.
+cudaError_t conv_stream_blocks(const ConvStreamArgs& a, cudaStream_t stream);
 
 // mix[b][ear][t] = sum over sources s (in order) of gain[s] * out[b][s][ear][t]; gain may be null (= 1).
 cudaError_t conv_mix(const float* d_out, int n_src, int block, int n_blocks, const float* d_gain, float* d_mix, cudaStream_t stream);

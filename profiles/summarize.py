@@ -16,7 +16,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max"]
 out = [f"# ncu summaries, tag {tag} (profiles/run_ncu.sh; B200, --clock-control none)\n"]
-for name in ("trace", "rerender", "conv"):
+for name in ("trace", "rerender", "rrwalk", "conv"):
     rep = os.path.join(G, f"{name}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -51,17 +51,32 @@ if os.path.exists(lc):
 open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w").write("\n".join(out) + "\n")
 # per-launch DRAM traffic of the captured kernels, read by bench.py for roofline.traffic
 import json, re
-traffic = {}
-for name in ("trace", "rerender", "conv"):
+traffic, figures = {}, {}
+scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
+for name in ("trace", "rerender", "rrwalk", "conv"):
     rep = os.path.join(G, f"{name}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     d = dict(zip(rows[0], rows[2])); u = dict(zip(rows[0], rows[1]))
-    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = sum(float(d[k].replace(",", "")) * scale.get(u[k], 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in d)
+    val = lambda k: float(d[k].replace(",", "")) * scale.get(u[k], 1)
+    tot = sum(val(k) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in d)
     traffic[name] = {"kernel": d.get("Kernel Name"), "dram_bytes_per_launch": tot, "tag": tag}
+    if name == "trace":
+        # the figures north_star asks for: warp-execution efficiency and achieved L2 / HBM GB/s of the traversal
+        t = val("gpu__time_duration.sum")
+        figures["wave_kernel"] = {
+            "source": f"ncu --set full capture {tag} (profiles/{tag}_ncu_summary.md), C2, one launch, cold L2",
+            "warp_exec_efficiency": val("smsp__thread_inst_executed_per_inst_executed.ratio") / 32.0,
+            "lanes_per_instruction": val("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "l2_gbs": val("lts__t_bytes.sum") / t / 1e9 if "lts__t_bytes.sum" in d else None,
+            "hbm_gbs": tot / t / 1e9,
+            "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "l1_hit_pct": val("l1tex__t_sector_hit_rate.pct"),
+            "kernel_ms": t * 1e3}
 if traffic:
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+if figures:
+    json.dump(figures, open(os.path.join(ROOT, "profiles", "ncu_figures.json"), "w"), indent=1)
 print("\n".join(out))

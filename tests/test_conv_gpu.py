@@ -110,11 +110,14 @@ def test_stream_matches_direct(block, n_src, ir_len):
     assert rel_l2(ol, oracle.direct_conv(x[0], irs[0][0])[: nb * block]) <= 1e-4
 
 
-def test_stream_back_to_back_steps_overlap_safely():
+@pytest.mark.parametrize("persistent", [False, True], ids=["launch-per-block", "one-launch-cluster-loop"])
+def test_stream_back_to_back_steps_overlap_safely(persistent, monkeypatch):
     """Device-resident steps launched back to back overlap (programmatic dependent launch: step k+1 accumulates its
     old partitions while step k finishes).  The result must equal, bit for bit, the same steps run one at a time
     through the host-buffer call (a copy between steps serialises them), and match the fp64 direct convolution."""
     import torch
+    if persistent:
+        monkeypatch.setenv("ARV2_CONV_PERSISTENT", "1")      # the "blocks" mode below then runs stream_blocks_kernel
     n_src, block, ir_len, nb = 4, 512, 20000, 120
     rng = np.random.default_rng(5)
     irs = [(decaying_ir(ir_len, 130 + i, 0.2, 48000), decaying_ir(ir_len, 160 + i, 0.15, 48000)) for i in range(n_src)]
