@@ -52,7 +52,7 @@ open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w").write("\n".jo
 # per-launch DRAM traffic of the captured kernels, read by bench.py for roofline.traffic
 import json, re
 traffic, figures = {}, {}
-scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
+scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
 for name in ("trace", "rerender", "rrwalk", "conv"):
     rep = os.path.join(G, f"{name}_{tag}.ncu-rep")
     if not os.path.exists(rep):
@@ -70,7 +70,8 @@ for name in ("trace", "rerender", "rrwalk", "conv"):
             "source": f"ncu --set full capture {tag} (profiles/{tag}_ncu_summary.md), C2, one launch, cold L2",
             "warp_exec_efficiency": val("smsp__thread_inst_executed_per_inst_executed.ratio") / 32.0,
             "lanes_per_instruction": val("smsp__thread_inst_executed_per_inst_executed.ratio"),
-            "l2_gbs": val("lts__t_bytes.sum") / t / 1e9 if "lts__t_bytes.sum" in d else None,
+            "l2_gbs": val("lts__t_sectors.sum") * 32 / t / 1e9 if "lts__t_sectors.sum" in d else None,
+            "l2_hit_pct": val("lts__t_sector_hit_rate.pct"),
             "hbm_gbs": tot / t / 1e9,
             "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "l1_hit_pct": val("l1tex__t_sector_hit_rate.pct"),
