@@ -440,7 +440,7 @@ int finish_timed(arv2_ctx* c, double* ms)
 extern "C" {
 
 const char* arv2_last_error(void) { return g_error.c_str(); }
-const char* arv2_version(void) { return "arv2-b200 0.1 (sm_100a)"; }
+const char* arv2_version(void) { return "arv2-b200 0.2 (sm_100a)"; }
 
 /* ------------------------------------------------------------------ scene -- */
 int arv2_scene_load_obj(const char* path, arv2_scene** out)

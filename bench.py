@@ -289,8 +289,16 @@ class Job:
             self.barrier()
             clk = clocks.stop() if clocks else None
         total_ms, total_segs = self.reduce_max_sum(step_ms, segs)
+        # per rank: mean trace-kernel time and mean step time (what the slowest rank and the exchange cost)
+        mine = torch.tensor([float(np.mean(kern_ms)), float(np.mean(step_ms))], dtype=torch.float64, device=self.dev)
+        allr = [torch.zeros_like(mine) for _ in range(self.world)]
+        if self.world > 1:
+            self.dist.all_gather(allr, mine)
+        else:
+            allr = [mine]
         return {"value": total_segs / (total_ms * 1e-3) / 1e9, "total_ms": total_ms, "total_segs": total_segs,
-                "kernel_ms": float(np.mean(kern_ms)), "local_segs_per_step": segs / steps, "clocks": clk}
+                "kernel_ms": float(np.mean(kern_ms)), "local_segs_per_step": segs / steps, "clocks": clk,
+                "rank_kernel_ms": [round(float(a[0].item()), 4) for a in allr], "rank_step_ms": [round(float(a[1].item()), 4) for a in allr]}
 
 
 def main():
@@ -422,6 +430,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "Grays/s", "h2d_bytes_per_step": upload_bytes,
                 "d2h_bytes_per_step": ir_bytes + 8 * 24, "ms_per_step": e2e_total_ms / args.steps},
         "gpu_launches": 2 * args.steps,
+        "rank_kernel_ms": main_run["rank_kernel_ms"], "rank_step_ms": main_run["rank_step_ms"],
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": f"wave_kernel<{BANDS},0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
