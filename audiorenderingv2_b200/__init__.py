@@ -93,6 +93,7 @@ SYMBOLS = {
     "arv2_set_mono": (C.c_int, [_vp, C.c_int32]),
     "arv2_set_seed": (C.c_int, [_vp, C.c_uint64]),
     "arv2_set_coherent_order": (C.c_int, [_vp, C.c_int32]),
+    "arv2_set_sweep_min_rays": (C.c_int, [_vp, C.c_int64]),
     "arv2_set_stream": (C.c_int, [_vp, _vp]),
     "arv2_render": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "arv2_render_range": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
@@ -421,6 +422,10 @@ class AudioRenderer:
 
     def set_coherent_order(self, on):
         _check(lib().arv2_set_coherent_order(self._h, 1 if on else 0))
+
+    def set_sweep_min_rays(self, n):
+        """Launches of >= n rays use the bounce-synchronous sweep_kernel (0: never); scheduling only."""
+        _check(lib().arv2_set_sweep_min_rays(self._h, int(n)))
 
     def set_stream(self, cuda_stream_ptr):
         _check(lib().arv2_set_stream(self._h, cuda_stream_ptr))

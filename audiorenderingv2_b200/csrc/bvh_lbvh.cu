@@ -152,13 +152,16 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const unsig
 // Stable LSD radix sort of (key, value) pairs on bits [lo_bit, hi_bit) of the keys, kRadixBits
 // per pass, with the count / scan / scatter kernels above.  Returns 0 or 1: which of the two
 // ping-pong buffers holds the result.
-cudaError_t radix_sort_pairs(unsigned* keys[2], int* vals[2], int n, int lo_bit, int hi_bit, int* result, cudaStream_t stream)
+size_t radix_sort_scratch_bytes(int n) { return n <= 0 ? 0 : (size_t)kRadix * (size_t)((n + kSortTile - 1) / kSortTile) * 4; }
+
+cudaError_t radix_sort_pairs(unsigned* keys[2], int* vals[2], int n, int lo_bit, int hi_bit, int* result, cudaStream_t stream, unsigned* scratch)
 {
     *result = 0;
     if (n <= 0) return cudaSuccess;
     const int sort_blocks = (n + kSortTile - 1) / kSortTile;
-    unsigned* counts = nullptr;
-    cudaError_t e = cudaMalloc(&counts, (size_t)kRadix * sort_blocks * 4);
+    unsigned* counts = scratch;
+    cudaError_t e = cudaSuccess;
+    if (!counts) e = cudaMalloc(&counts, (size_t)kRadix * sort_blocks * 4);
     if (e != cudaSuccess) return e;
     int cur = 0;
     for (int shift = lo_bit; shift < hi_bit; shift += kRadixBits) {
@@ -168,9 +171,10 @@ cudaError_t radix_sort_pairs(unsigned* keys[2], int* vals[2], int n, int lo_bit,
         cur ^= 1;
     }
     e = cudaGetLastError();
+    *result = cur;
+    if (scratch) return e;               // the caller's scratch: nothing to free, nothing to wait for
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(counts);
-    *result = cur;
     return e;
 }
 

@@ -15,7 +15,11 @@ cudaError_t build_bvh_lbvh(const float* d_verts, const int* d_mats, int n, int i
                            int* d_order, int node_offset, int slot_offset, LbvhResult* out, cudaStream_t stream);
 
 // Stable radix sort of (key, value) pairs on key bits [lo_bit, hi_bit), 6 bits per pass; keys[0] / vals[0]
-// hold the input, *result says which ping-pong buffer holds the output.  Synchronises the stream.
-cudaError_t radix_sort_pairs(unsigned* keys[2], int* vals[2], int n, int lo_bit, int hi_bit, int* result, cudaStream_t stream);
+// hold the input, *result says which ping-pong buffer holds the output.  With scratch == nullptr the per-tile digit
+// counts are allocated here and the stream is synchronised before they are freed; with the caller's scratch
+// (radix_sort_scratch_bytes(n) bytes) the sort is only enqueued.
+size_t radix_sort_scratch_bytes(int n);
+cudaError_t radix_sort_pairs(unsigned* keys[2], int* vals[2], int n, int lo_bit, int hi_bit, int* result, cudaStream_t stream,
+                             unsigned* scratch = nullptr);
 
 } // namespace arv2

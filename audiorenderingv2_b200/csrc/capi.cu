@@ -93,9 +93,16 @@ struct arv2_ctx {
     // breadth-first tracer: per-depth path queues, grown on demand
     float4* d_wave_paths = nullptr; size_t wave_slots = 0;
     bool wave = true;
+    // bounce-synchronous tracer (sweep_kernel) for large launches: path states handed over through global memory
+    SweepWork sweep{}; long long sweep_rays = 0; int sweep_nbins = 0;
+    long long sweep_min_rays = 3000000;    // launches of at least this many rays use it (<= 0: never); crossover measured at 2 M rays (profiles/r09_trace_sweeps.md)
     // direction-sorted start orders, cached per (seed, ray range); two slots so that alternating ranges do not re-sort
     struct RayOrder { int* d = nullptr; long long begin = -1, n = -1; unsigned long long seed = 0, stamp = 0; } order[2];
     unsigned long long order_clock = 0;
+    // workspace of the sort, kept (with the two order buffers, all of order_cap entries) for launches of up to kOrderKeep
+    // rays: a render with a new seed then costs the key kernel and eight sort kernels, no allocation and no synchronisation
+    unsigned* d_sort_keys[2] = {nullptr, nullptr}; int* d_sort_spare = nullptr; unsigned* d_sort_counts = nullptr;
+    long long order_cap = 0;
     bool coherent_order = true;
     // pinned staging for the receiver sub-tree
     float4* h_stage = nullptr; size_t stage_f4 = 0;
@@ -260,6 +267,15 @@ void fill_params(arv2_ctx* c, TraceParams* p, long long ray_begin, long long n_r
 // (Morton code of the octahedral map, GPU radix sort on its top 24 bits), so the 32 lanes of a
 // warp walk the same part of the scene over the first bounces.  Depends only on (seed, range);
 // the result per ray and the fp64 histogram do not depend on the order.
+constexpr long long kOrderKeep = 32LL << 20;
+
+void free_ray_orders(arv2_ctx* c)
+{
+    for (auto& o : c->order) { cudaFree(o.d); o = arv2_ctx::RayOrder{}; }
+    cudaFree(c->d_sort_keys[0]); cudaFree(c->d_sort_keys[1]); cudaFree(c->d_sort_spare); cudaFree(c->d_sort_counts);
+    c->d_sort_keys[0] = c->d_sort_keys[1] = nullptr; c->d_sort_spare = nullptr; c->d_sort_counts = nullptr; c->order_cap = 0;
+}
+
 int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
 {
     if (!c->coherent_order || n_rays <= 0 || n_rays > 0x7fffffffLL) return ARV2_OK;
@@ -268,6 +284,34 @@ int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
         if (o.d && o.begin == ray_begin && o.n == n_rays && o.seed == c->seed) { o.stamp = ++c->order_clock; return ARV2_OK; }
         if (o.stamp < slot->stamp) slot = &o;                     // least recently used
     }
+    if (n_rays <= kOrderKeep) {
+        // persistent buffers: grown (and both cached orders dropped) when a launch is larger than any before
+        if (n_rays > c->order_cap) {
+            CK(cudaStreamSynchronize(c->stream));
+            free_ray_orders(c);
+            slot = &c->order[0];
+            const size_t bytes = (size_t)n_rays * 4;
+            cudaError_t e = cudaMalloc(&c->d_sort_keys[0], bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&c->d_sort_keys[1], bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&c->d_sort_spare, bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&c->order[0].d, bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&c->order[1].d, bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&c->d_sort_counts, radix_sort_scratch_bytes((int)n_rays));
+            if (e != cudaSuccess) { free_ray_orders(c); cudaGetLastError(); set_error(std::string("ray order: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
+            c->order_cap = n_rays;
+        }
+        slot->n = -1;
+        int* vals[2] = {slot->d, c->d_sort_spare};
+        int res = 0;
+        cudaError_t e = launch_direction_keys(c->seed, ray_begin, n_rays, c->d_sort_keys[0], vals[0], c->stream);
+        if (e == cudaSuccess) e = radix_sort_pairs(c->d_sort_keys, vals, (int)n_rays, 8, 32, &res, c->stream, c->d_sort_counts);
+        if (e != cudaSuccess) { set_error(std::string("ray order: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
+        if (res == 1) std::swap(slot->d, c->d_sort_spare);
+        slot->begin = ray_begin; slot->n = n_rays; slot->seed = c->seed; slot->stamp = ++c->order_clock;
+        return ARV2_OK;
+    }
+    // very large launches: transient workspace (2 x 8 B per ray), only the order itself is kept
+    if (c->order_cap > 0) { CK(cudaStreamSynchronize(c->stream)); free_ray_orders(c); slot = &c->order[0]; }
     cudaFree(slot->d); slot->d = nullptr; slot->n = -1;
     unsigned* keys[2] = {nullptr, nullptr};
     int* vals[2] = {nullptr, nullptr};
@@ -338,6 +382,48 @@ int ensure_wave(arv2_ctx* c, TraceParams* p, long long n_rays)
     return ARV2_OK;
 }
 
+void free_sweep(arv2_ctx* c)
+{
+    cudaFree(c->sweep.state[0]); cudaFree(c->sweep.state[1]); cudaFree(c->sweep.key); cudaFree(c->sweep.rank); cudaFree(c->sweep.perm);
+    cudaFree(c->sweep.bins); cudaFree(c->sweep.tile_sums); cudaFree(c->sweep.count);
+    c->sweep = SweepWork{}; c->sweep_rays = 0; c->sweep_nbins = 0;
+}
+
+// Workspace of the bounce-synchronous tracer for a launch of n_rays rays; returns false (and the launch uses wave_kernel)
+// when the launch is too small for it, the depth is absurd or the memory is not there.
+bool ensure_sweep(arv2_ctx* c, long long n_rays)
+{
+    if (c->sweep_min_rays <= 0 || n_rays < c->sweep_min_rays || n_rays > 0x7fffffffLL || c->n_scene <= 0) return false;
+    SweepWork& w = c->sweep;
+    // 8 segments for the fresh bundles, then 3 per sweep, bins = 8^3 cells x 32^2 direction cells (profiles/r09_trace_sweeps.md)
+    int seg = 3, first = 8, cb = 3, db = 5, dm = 0;
+    if (const char* e = getenv("ARV2_SWEEP_SEGMENTS")) seg = atoi(e) > 0 ? atoi(e) : seg;          // tuning aids
+    if (const char* e = getenv("ARV2_SWEEP_FIRST")) first = atoi(e) > 0 ? atoi(e) : first;
+    if (const char* e = getenv("ARV2_SWEEP_CELL_BITS")) cb = atoi(e) >= 0 ? atoi(e) : cb;
+    if (const char* e = getenv("ARV2_SWEEP_DIR_BITS")) db = atoi(e) >= 0 ? atoi(e) : db;
+    if (const char* e = getenv("ARV2_SWEEP_DIR_MAJOR")) dm = atoi(e) != 0;
+    if (cb > 8 || db > 8 || 3 * cb + 2 * db > 22) { cb = 3; db = 5; }
+    if (((long long)c->max_bounces + seg - 1) / seg > 4096) return false;
+    const int n_bins = sweep_bins(cb, db);
+    if (n_rays > c->sweep_rays || n_bins > c->sweep_nbins) {
+        free_sweep(c);
+        const size_t st = (size_t)n_rays * cont_f4(c->bands) * sizeof(float4);
+        bool ok = cudaMalloc(&w.state[0], st) == cudaSuccess && cudaMalloc(&w.state[1], st) == cudaSuccess &&
+                  cudaMalloc(&w.key, (size_t)n_rays * 4) == cudaSuccess && cudaMalloc(&w.rank, (size_t)n_rays * 4) == cudaSuccess &&
+                  cudaMalloc(&w.perm, (size_t)n_rays * 4) == cudaSuccess && cudaMalloc(&w.bins, (size_t)n_bins * 4) == cudaSuccess && cudaMalloc(&w.tile_sums, (size_t)(n_bins / 4096) * 4) == cudaSuccess &&
+                  cudaMalloc(&w.count, 2 * sizeof(unsigned long long)) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); free_sweep(c); return false; }
+        c->sweep_rays = n_rays; c->sweep_nbins = n_bins;
+    }
+    w.segments = seg; w.first_segments = first; w.cell_bits = cb; w.dir_bits = db; w.dir_major = dm;
+    for (int a = 0; a < 3; ++a) {
+        const float lo = c->scene_bvh.lo[a], hi = c->scene_bvh.hi[a];
+        w.lo[a] = lo;
+        w.scale[a] = (float)(1 << cb) / std::max(hi - lo, 1e-6f);
+    }
+    return true;
+}
+
 void free_cache(arv2_ctx* c)
 {
     cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_off); cudaFree(c->d_pc_vert); cudaFree(c->d_pc_bits);
@@ -376,10 +462,12 @@ int build_cache(arv2_ctx* c, double* ms)
     fill_params(c, &p, 0, n);
     p.rec_bin = nullptr; p.rec_ear = nullptr; p.rec_energy = nullptr; p.rec_nseg = nullptr;
     p.pc_seg = t_seg; p.pc_energy = t_energy; p.pc_nseg = t_nseg; p.pc_stride = (long long)std::max(1u, c->max_bounces);
-    rc = ensure_wave(c, &p, n);
+    const bool sweeps = ensure_sweep(c, n);
+    if (!sweeps) rc = ensure_wave(c, &p, n);
     if (rc != ARV2_OK) { drop(); return rc; }
     CKB(cudaEventRecord(c->ev0, c->stream));
-    CKB(launch_trace(p, c->bands, 1, c->sm_count, c->stream));
+    if (sweeps) CKB(launch_trace_sweeps(p, c->sweep, c->bands, 1, c->stream));
+    else CKB(launch_trace(p, c->bands, 1, c->sm_count, c->stream));
     CKB(launch_cache_offsets(t_nseg, n, c->d_pc_off, scratch, c->stream));
     unsigned long long total = 0;
     CKB(cudaMemcpyAsync(&total, c->d_pc_off + n, sizeof total, cudaMemcpyDeviceToHost, c->stream));
@@ -648,6 +736,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     auto* c = new arv2_ctx;
     if (getenv("ARV2_NO_SORT")) c->coherent_order = false;   // tuning aids (A/B)
     if (getenv("ARV2_NO_WAVE")) c->wave = false;
+    if (const char* e = getenv("ARV2_SWEEP")) c->sweep_min_rays = atoll(e);      // tuning aid: launches of >= this many rays are traced in sweeps (0 = never)
     if (getenv("ARV2_RR_SERIAL")) c->rr_serial = true;
     c->desc = *desc; c->desc.materials = nullptr; c->desc.n_materials = 0;
     c->device = desc->device;
@@ -790,7 +879,7 @@ void arv2_destroy(arv2_ctx* c)
     cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_counters);
     if (c->h_ir) cudaFreeHost(c->h_ir);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
-    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_off); cudaFree(c->d_pc_vert); cudaFree(c->d_pc_bits); cudaFree(c->order[0].d); cudaFree(c->order[1].d); cudaFree(c->d_wave_paths);
+    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_off); cudaFree(c->d_pc_vert); cudaFree(c->d_pc_bits); free_ray_orders(c); cudaFree(c->d_wave_paths); free_sweep(c);
     cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -828,6 +917,7 @@ int arv2_set_hrtf_absorption_rate(arv2_ctx* c, float v) { REQUIRE(c, "null ctx")
 int arv2_set_mono(arv2_ctx* c, int32_t v) { REQUIRE(c, "null ctx"); c->mono = v ? 1 : 0; return ARV2_OK; }
 int arv2_set_seed(arv2_ctx* c, uint64_t s) { REQUIRE(c, "null ctx"); c->seed = s; c->cache_valid = false; return ARV2_OK; }
 int arv2_set_coherent_order(arv2_ctx* c, int32_t on) { REQUIRE(c, "null ctx"); c->coherent_order = on != 0; return ARV2_OK; }
+int arv2_set_sweep_min_rays(arv2_ctx* c, int64_t n) { REQUIRE(c, "null ctx"); c->sweep_min_rays = n; return ARV2_OK; }
 int arv2_set_stream(arv2_ctx* c, void* s) { REQUIRE(c, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return ARV2_OK; }
 
 // Everything of a trace up to (not including) a host synchronisation: receiver upload, zeroing, the launch.
@@ -847,10 +937,12 @@ static int enqueue_trace(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t
     if (rc != ARV2_OK) return rc;
     TraceParams p;
     fill_params(c, &p, ray_begin, n_rays);
-    rc = ensure_wave(c, &p, n_rays);
+    const bool sweeps = ensure_sweep(c, n_rays);
+    if (!sweeps) rc = ensure_wave(c, &p, n_rays);
     if (rc != ARV2_OK) return rc;
     CK(cudaEventRecord(c->ev0, c->stream));
-    if (n_rays > 0) CK(launch_trace(p, c->bands, 0, c->sm_count, c->stream));
+    if (n_rays > 0 && sweeps) CK(launch_trace_sweeps(p, c->sweep, c->bands, 0, c->stream));
+    else if (n_rays > 0) CK(launch_trace(p, c->bands, 0, c->sm_count, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
     c->last_range_rays = n_rays;
     return ARV2_OK;

@@ -878,6 +878,161 @@ __global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams
 }
 
 // ---------------------------------------------------------------------------------------
+// sweep_kernel: bounce-synchronous tracer for launches of many millions of rays.  Every sweep advances ALL paths alive
+// by sweep.segments segments, one lane per path, and hands the survivors over through global memory; between two sweeps
+// the survivors are re-binned by (cell of their new origin, octant-map cell of their new direction): a counting sort whose
+// histogram and per-path rank are taken by the sweep itself (one atomic per survivor), followed by a scan of the bins and
+// a scatter of the read order.  The 32 lanes of a warp then start in the same part of the scene and head the same way at
+// EVERY depth, not only over the first bounces of the direction-sorted start order (wave_kernel keeps a warp together,
+// but a bundle has fanned out after ~5 bounces).  Results are per ray and the histogram is fp64: nothing depends on the order.
+#ifndef ARV2_SWEEP_THREADS
+#define ARV2_SWEEP_THREADS 128
+#endif
+constexpr int kSweepThreads = ARV2_SWEEP_THREADS;
+__device__ __forceinline__ unsigned spread16(unsigned v);
+
+__device__ __forceinline__ unsigned spread3_10(unsigned v)
+{
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__device__ __forceinline__ unsigned sweep_bin(const SweepParams& w, F3 org, F3 d)
+{
+    const float cmax = (float)((1 << w.cell_bits) - 1);
+    const unsigned cx = (unsigned)fminf(fmaxf((org.x - w.lo[0]) * w.scale[0], 0.f), cmax);
+    const unsigned cy = (unsigned)fminf(fmaxf((org.y - w.lo[1]) * w.scale[1], 0.f), cmax);
+    const unsigned cz = (unsigned)fminf(fmaxf((org.z - w.lo[2]) * w.scale[2], 0.f), cmax);
+    const unsigned mc = spread3_10(cx) | (spread3_10(cy) << 1) | (spread3_10(cz) << 2);
+    const float inv = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z) + 1e-30f);
+    float u = d.x * inv, v = d.y * inv;
+    if (d.z < 0.f) { const float uu = (1.f - fabsf(v)) * copysignf(1.f, u), vv = (1.f - fabsf(u)) * copysignf(1.f, v); u = uu; v = vv; }
+    const float dmax = (float)((1 << w.dir_bits) - 1), ds = (float)(1 << w.dir_bits);
+    const unsigned iu = (unsigned)fminf(fmaxf((u * 0.5f + 0.5f) * ds, 0.f), dmax);
+    const unsigned iv = (unsigned)fminf(fmaxf((v * 0.5f + 0.5f) * ds, 0.f), dmax);
+    const unsigned md = spread16(iu) | (spread16(iv) << 1);
+    return w.dir_major ? ((md << (3 * w.cell_bits)) | mc) : ((mc << (2 * w.dir_bits)) | md);
+}
+
+template <int NB, int MODE>
+__global__ void __launch_bounds__(kSweepThreads, NB == 1 ? ARV2_MINB : ARV2_MINB8) sweep_kernel(const TraceParams p, const SweepParams w)
+{
+    __shared__ unsigned sh_cnt[kSweepThreads / 32];
+    __shared__ unsigned long long sh_base;
+    const long long n_in = w.in ? (long long)*w.n_in : p.n_rays;
+    const long long i = (long long)blockIdx.x * kSweepThreads + threadIdx.x;
+    if (i == 0) atomicAdd(p.counters + 2, 1ull);             // sweeps of this launch (arv2_last_counters)
+    if (i - threadIdx.x >= n_in) return;                     // CTA-uniform
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long segs = 0;
+    Path<NB> s;
+    s.ray = 0; s.org = f3(0, 0, 0); s.dir = f3(0, 0, 0); s.dist = 0.f; s.depth = 0; s.nseg = 0;
+    Traversal tr;
+    int stack[kStack];
+    bool have = i < n_in;
+    if (have) {
+        if (!w.in) new_path<NB>(p, s, i);
+        else load_path<NB>(w.in + (size_t)(w.perm ? __ldg(w.perm + i) : (int)i) * cont_f4(NB), s);
+    }
+    for (int k = 0; k < w.segments; ++k) {
+        if (!__any_sync(FULL, have)) break;
+        bool ended = false;
+        Deposit d; d.dep = false; d.bin = -1; d.ear = 0; d.primary = 0;
+        if (have) ended = advance_segment<NB, MODE>(p, s, stack, tr, d);
+        if (MODE == 0) deposit_warp<NB>(p, d.dep, d.bin, d.primary, s.energy);
+        if (ended) { end_path<NB, MODE>(p, s, d, segs); have = false; }
+    }
+    if (have && !path_goes_on<NB>(p, s)) {                   // would end at its next loop guard
+        Deposit none; none.dep = false; none.bin = -1; none.ear = 0; none.primary = 0;
+        end_path<NB, MODE>(p, s, none, segs); have = false;
+    }
+    // ---- survivors: compacted per CTA (one global atomic), binned for the next sweep
+    const unsigned m = __ballot_sync(FULL, have);
+    if (lane == 0) sh_cnt[warp] = (unsigned)__popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned total = 0;
+#pragma unroll
+        for (int q = 0; q < kSweepThreads / 32; ++q) total += sh_cnt[q];
+        sh_base = total ? atomicAdd(w.n_out, (unsigned long long)total) : 0ull;
+    }
+    __syncthreads();
+    if (have) {
+        unsigned long long pos = sh_base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+        for (int q = 0; q < warp; ++q) pos += sh_cnt[q];
+        store_path<NB>(w.out + (size_t)pos * cont_f4(NB), s);
+        const unsigned bin = sweep_bin(w, s.org, s.dir);
+        w.key[pos] = bin;
+        w.rank[pos] = atomicAdd(w.bins + bin, 1u);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
+    if (lane == 0 && segs) atomicAdd(p.counters + 1, segs);
+    tr.flush_stats(p.counters);
+}
+
+// exclusive scan of the bin counts in place, tiles of 4096 bins (n_bins a multiple of 4096): sweep_tile_sums_kernel
+// writes one total per tile, sweep_scan_kernel re-reads its tile, adds up the totals of the tiles before it (at most
+// 1024 of them: one pass of the CTA) and writes the exclusive prefix
+__device__ __forceinline__ unsigned block_exclusive_1024(unsigned v, unsigned* sh, unsigned* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned t = sh[lane];
+        unsigned ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, ti, o); if (lane >= o) ti += u; }
+        sh[lane] = ti - t;
+        if (lane == 31) sh[32] = ti;
+    }
+    __syncthreads();
+    if (total) *total = sh[32];
+    return sh[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(1024) sweep_tile_sums_kernel(const unsigned* __restrict__ bins, unsigned* __restrict__ tile_sums)
+{
+    __shared__ unsigned sh[33];
+    const uint4 v = reinterpret_cast<const uint4*>(bins)[(size_t)blockIdx.x * 1024 + threadIdx.x];
+    unsigned total;
+    block_exclusive_1024(v.x + v.y + v.z + v.w, sh, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) sweep_scan_kernel(unsigned* __restrict__ bins, const unsigned* __restrict__ tile_sums)
+{
+    __shared__ unsigned sh[33];
+    __shared__ unsigned sh_before;
+    unsigned before = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += 1024) before += tile_sums[t];
+    unsigned tot;
+    block_exclusive_1024(before, sh, &tot);
+    if (threadIdx.x == 0) sh_before = tot;
+    __syncthreads();
+    uint4* const b = reinterpret_cast<uint4*>(bins) + (size_t)blockIdx.x * 1024 + threadIdx.x;
+    const uint4 v = *b;
+    unsigned run = sh_before + block_exclusive_1024(v.x + v.y + v.z + v.w, sh, nullptr);
+    uint4 o;
+    o.x = run; run += v.x; o.y = run; run += v.y; o.z = run; run += v.z; o.w = run;
+    *b = o;
+}
+
+__global__ void __launch_bounds__(256) sweep_scatter_kernel(const unsigned* __restrict__ key, const unsigned* __restrict__ rank,
+                                                            const unsigned* __restrict__ bins, const unsigned long long* __restrict__ n, int* __restrict__ perm)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)*n) return;
+    perm[__ldg(bins + key[i]) + rank[i]] = (int)i;
+}
+
+// ---------------------------------------------------------------------------------------
 // trace2_kernel: the same path tracer with the lanes of a warp decoupled.  Per-segment
 // node-visit counts vary so much inside a warp (sum / (32 x max) = 49 % on the conference
 // scene) that lanes of trace_kernel idle most of the time (9.5 of 32 lanes per instruction,
@@ -1603,6 +1758,50 @@ cudaError_t launch_trace(const TraceParams& p, int bands, int mode, int sm_count
 {
     if (bands == 1) return mode == 0 ? launch_trace_t<1, 0>(p, sm_count, stream) : launch_trace_t<1, 1>(p, sm_count, stream);
     if (bands == 8) return mode == 0 ? launch_trace_t<8, 0>(p, sm_count, stream) : launch_trace_t<8, 1>(p, sm_count, stream);
+    return cudaErrorInvalidValue;
+}
+
+template <int NB, int MODE>
+cudaError_t launch_sweeps_t(const TraceParams& p, const SweepWork& work, cudaStream_t stream)
+{
+    const int n_bins = sweep_bins(work.cell_bits, work.dir_bits);
+    // the first sweep keeps the direction-sorted bundles of fresh rays together for first_segments segments (a bundle
+    // of neighbours is far more coherent than any bin), the others advance by `segments`
+    const long long first = work.first_segments < 1 ? 1 : work.first_segments;
+    const long long rest = (long long)p.max_bounces - first;
+    const long long n_sweeps = 1 + (rest > 0 ? (rest + work.segments - 1) / work.segments : 0);
+    const unsigned grid = (unsigned)((p.n_rays + kSweepThreads - 1) / kSweepThreads), grid_sc = (unsigned)((p.n_rays + 255) / 256);
+    SweepParams w{};
+    w.key = work.key; w.rank = work.rank; w.bins = work.bins;
+    w.cell_bits = work.cell_bits; w.dir_bits = work.dir_bits; w.dir_major = work.dir_major;
+    for (int a = 0; a < 3; ++a) { w.lo[a] = work.lo[a]; w.scale[a] = work.scale[a]; }
+    cudaError_t e = cudaSuccess;
+    for (long long k = 0; k < n_sweeps && e == cudaSuccess; ++k) {
+        const int cur = (int)(k & 1), nxt = cur ^ 1;
+        w.segments = k == 0 ? (int)first : work.segments;
+        w.in = k == 0 ? nullptr : work.state[cur];
+        w.perm = k == 0 ? nullptr : work.perm;
+        w.n_in = work.count + cur;
+        w.out = work.state[nxt];
+        w.n_out = work.count + nxt;
+        if ((e = cudaMemsetAsync(work.bins, 0, (size_t)n_bins * sizeof(unsigned), stream)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(work.count + nxt, 0, sizeof(unsigned long long), stream)) != cudaSuccess) break;
+        sweep_kernel<NB, MODE><<<grid, kSweepThreads, 0, stream>>>(p, w);
+        if (k + 1 < n_sweeps) {
+            sweep_tile_sums_kernel<<<n_bins / 4096, 1024, 0, stream>>>(work.bins, work.tile_sums);
+            sweep_scan_kernel<<<n_bins / 4096, 1024, 0, stream>>>(work.bins, work.tile_sums);
+            sweep_scatter_kernel<<<grid_sc, 256, 0, stream>>>(work.key, work.rank, work.bins, work.count + nxt, work.perm);
+        }
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+cudaError_t launch_trace_sweeps(const TraceParams& p, const SweepWork& work, int bands, int mode, cudaStream_t stream)
+{
+    if (p.n_rays <= 0) return cudaSuccess;
+    if (bands == 1) return mode == 0 ? launch_sweeps_t<1, 0>(p, work, stream) : launch_sweeps_t<1, 1>(p, work, stream);
+    if (bands == 8) return mode == 0 ? launch_sweeps_t<8, 0>(p, work, stream) : launch_sweeps_t<8, 1>(p, work, stream);
     return cudaErrorInvalidValue;
 }
 

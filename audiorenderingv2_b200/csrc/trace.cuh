@@ -17,7 +17,7 @@ struct TraceParams {
     const float* keep;          // [n_mats][bands]  1 - mat_absorption
     const float* scattering;    // [n_mats]
     double* hist;               // [2][bands][ir_len] fp64 accumulation
-    unsigned long long* counters; // [0] next ray chunk, [1] segments traced, [7] watchdog
+    unsigned long long* counters; // [0] next ray chunk, [1] segments traced, [2] sweeps (sweep_kernel launches), [7] watchdog
     int* rec_bin; int* rec_ear; float* rec_energy; int* rec_nseg;   // optional per-ray records
     // receiver-independent path cache (optional).  While it is being filled (launch_trace mode 1) it is ray-major with
     // a fixed stride: segment k of ray r at [r*pc_stride + k].  launch_cache_compact then packs it (CSR): the segments
@@ -55,6 +55,28 @@ struct TraceParams {
     int chunk;                  // rays a warp claims per global atomic
     int refill_below;           // lanes of a warp are refilled only while fewer than this many hold a path (32 = always)
 };
+
+// Bounce-synchronous tracer (sweep_kernel): the survivors of a sweep are handed over through global memory and re-binned
+// by (origin cell, direction cell) for the next one.
+struct SweepParams {
+    const float4* in;                 // path states the sweep reads (null: the launch's fresh rays, in p.ray_order)
+    const int* perm;                  // read order of `in`
+    const unsigned long long* n_in;   // paths in `in`
+    float4* out;                      // survivors, compacted
+    unsigned long long* n_out;        // zeroed: survivors
+    unsigned* key; unsigned* rank;    // per survivor: its bin and its arrival rank in the bin
+    unsigned* bins;                   // zeroed: survivors per bin
+    int segments;                     // segments per sweep
+    int cell_bits, dir_bits, dir_major;
+    float lo[3], scale[3];            // cell = (origin - lo) * scale per axis
+};
+struct SweepWork {                    // device workspace of one launch (owned by the context)
+    float4* state[2]; unsigned* key; unsigned* rank; int* perm; unsigned* bins; unsigned* tile_sums; unsigned long long* count;
+    int first_segments, segments, cell_bits, dir_bits, dir_major;
+    float lo[3], scale[3];
+};
+constexpr int sweep_bins(int cell_bits, int dir_bits) { return (1 << (3 * cell_bits + 2 * dir_bits)) < 4096 ? 4096 : (1 << (3 * cell_bits + 2 * dir_bits)); }
+cudaError_t launch_trace_sweeps(const TraceParams& p, const SweepWork& work, int bands, int mode, cudaStream_t stream);
 
 constexpr int kWaveQueues = 64;               // most per-depth queues of wave_kernel
 constexpr int kCounters = 24;                 // unsigned long long counters per context

@@ -298,7 +298,15 @@ class Job:
             allr = [mine]
         return {"value": total_segs / (total_ms * 1e-3) / 1e9, "total_ms": total_ms, "total_segs": total_segs,
                 "kernel_ms": float(np.mean(kern_ms)), "local_segs_per_step": segs / steps, "clocks": clk,
-                "rank_kernel_ms": [round(float(a[0].item()), 4) for a in allr], "rank_step_ms": [round(float(a[1].item()), 4) for a in allr]}
+                "rank_kernel_ms": [round(float(a[0].item()), 4) for a in allr], "rank_step_ms": [round(float(a[1].item()), 4) for a in allr],
+                "tracer": tracer_label(r)}
+
+
+def tracer_label(r):
+    """Which kernel traced the last launch: launches of >= 3M rays go through the bounce-synchronous sweep_kernel
+    (arv2_set_sweep_min_rays), smaller ones through the per-SM queues of wave_kernel."""
+    n = int(r.last_counters()[2])
+    return f"sweep_kernel ({n} sweeps, survivors re-binned by origin cell x direction between sweeps)" if n else "wave_kernel"
 
 
 def main():
@@ -460,7 +468,7 @@ def bench_c3_strong(job, scene, receiver, mats):
     r.close()
     job.torch.cuda.empty_cache()
     return {"c3_strong_grays_per_s": run["value"], "c3_strong_ms_per_render": run["total_ms"] / 2, "c3_total_rays": n_total,
-            "c3_rays_per_gpu": n_total // job.world, "c3_segments_per_render": run["total_segs"] / 2}
+            "c3_rays_per_gpu": n_total // job.world, "c3_segments_per_render": run["total_segs"] / 2, "c3_tracer": run["tracer"]}
 
 
 def bench_c4(job, args):
@@ -481,7 +489,8 @@ def bench_c4(job, args):
         peak = measured_hbm_peak()[0]
         achieved = run["local_segs_per_step"] * BYTES_PER_SEGMENT / (run["kernel_ms"] * 1e-3) / 1e9
         out = {"c4_grays_per_s": run["value"], "c4_ms_per_render": run["total_ms"] / 3, "c4_rays_per_gpu": per_gpu,
-               "c4_roofline_frac": achieved / peak, "c4_bytes_per_segment": BYTES_PER_SEGMENT, "c4_kernel_ms": run["kernel_ms"]}
+               "c4_roofline_frac": achieved / peak, "c4_bytes_per_segment": BYTES_PER_SEGMENT, "c4_kernel_ms": run["kernel_ms"],
+               "c4_tracer": run["tracer"]}
         job.flush = None
         torch.cuda.empty_cache()
         rr = bench_rerender(arv, torch, job.dev, job.local, scene, receiver, mats, args)
@@ -506,7 +515,7 @@ def stats_pass():
     tv, tm, names, mats = scene_case()
     scene = arv.Scene.from_triangles(tv, tm, names)
     receiver = arv.Receiver.from_triangles(*load_receiver())
-    n = min(RAYS[0] * RAYS[1] * RAYS[2], 2_000_000)
+    n = min(RAYS[0] * RAYS[1] * RAYS[2], int(os.environ.get("ARV2_STATS_RAYS", 10_000_000)))      # the launch size the bench times: the tracer depends on it
     r = arv.AudioRenderer(scene, IR_SECONDS, FS, mats, (n, 1, 1), receiver=receiver, bands=BANDS)
     r.setBasePower(100.0); r.setThresholds(0.0, MAX_BOUNCES); r.set_hrtf_absorption_rate(0.9)
     r.setEmitterPosInOptix(EMITTER); r.setSphereCenterInOptix(RECEIVER, YAW); r.set_seed(SEED)
@@ -514,7 +523,7 @@ def stats_pass():
     ms = r.render()
     c = r.last_counters()
     print(json.dumps({"rays": n, "segments": c[1], "node_visits": c[16], "warp_node_steps": c[17], "leaf_visits": c[18],
-                      "tri_tests": c[19], "warp_leaf_steps": c[20], "kernel_ms_with_tallies": ms}))
+                      "tri_tests": c[19], "warp_leaf_steps": c[20], "kernel_ms_with_tallies": ms, "tracer": tracer_label(r)}))
 
 
 def traversal_figures(local):
@@ -541,6 +550,7 @@ def traversal_figures(local):
                        "lanes_per_node_step": d["node_visits"] / max(d["warp_node_steps"], 1),
                        "lanes_per_leaf_step": d["leaf_visits"] / max(d["warp_leaf_steps"], 1),
                        "requested_bytes_per_segment": (64 * d["node_visits"] + 48 * d["tri_tests"]) / segs,
+                       "tracer": d.get("tracer"),
                        "source": f"live: lib/libarv2_stats.so (-DARV2_TRACE_STATS), {d['rays']} rays of the workload"}
         except Exception as e:       # noqa: BLE001
             out[wl] = {"error": repr(e)[:200]}

@@ -171,6 +171,11 @@ int arv2_set_seed(arv2_ctx* ctx, uint64_t seed);
  * ray set, every per-ray result and the IR are unchanged; only the lanes of a warp become
  * neighbours in direction.  The order is computed on the GPU once per (seed, ray range). */
 int arv2_set_coherent_order(arv2_ctx* ctx, int32_t on);
+/* Launches of at least min_rays rays are traced bounce-synchronously (sweep_kernel: all paths alive advance together, the
+ * survivors are re-binned by origin cell and direction between two sweeps); smaller launches run in the per-SM queues of
+ * wave_kernel.  Default 3 000 000 (measured crossover on B200: 2 M rays); min_rays <= 0 turns the sweeps off.  Scheduling
+ * only: the ray set, every per-ray result and the IR are unchanged. */
+int arv2_set_sweep_min_rays(arv2_ctx* ctx, int64_t min_rays);
 /* Run everything on this CUDA stream (cudaStream_t as void*; NULL = own stream). */
 int arv2_set_stream(arv2_ctx* ctx, void* cuda_stream);
 
