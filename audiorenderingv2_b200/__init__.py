@@ -341,12 +341,32 @@ def shard_range(n_rays, rank, n_ranks):
     return b.value, c.value
 
 
+def _prefer_bundled_nccl():
+    """libarv2 binds NCCL with dlopen: ARV2_NCCL_LIB, else a libnccl.so.2 already in the process, else the system's.  In a
+    Python process that imports torch LATER, the system's (older) library would then stand in for the one torch's
+    libtorch_cuda.so was linked against (same soname) and break `import torch`; so when the pip-installed NCCL that torch
+    ships with is present and nothing was chosen, it is named explicitly.  A C++ host (arv2_cli) is not affected."""
+    if os.environ.get("ARV2_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            p = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                os.environ["ARV2_NCCL_LIB"] = p
+                return
+    except (ImportError, ValueError, AttributeError):
+        pass
+
+
 class Comm:
     """One NCCL rank inside libarv2 (arv2_comm_*).  `Comm.unique_id()` on one rank, the 128 bytes handed to the
     others by any transport (torch.distributed broadcast, a file, MPI ...), then `Comm(device, rank, n, id)` on each."""
 
     def __init__(self, device, rank, n_ranks, unique_id: bytes):
         assert len(unique_id) == COMM_ID_BYTES
+        _prefer_bundled_nccl()
         self._h = _vp()
         buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
         _check(lib().arv2_comm_create(int(device), int(rank), int(n_ranks), C.cast(buf, _vp), C.byref(self._h)))
@@ -354,6 +374,7 @@ class Comm:
 
     @staticmethod
     def unique_id() -> bytes:
+        _prefer_bundled_nccl()
         buf = C.create_string_buffer(COMM_ID_BYTES)
         _check(lib().arv2_comm_unique_id(C.cast(buf, _vp)))
         return buf.raw
@@ -539,6 +560,7 @@ class MultiRenderer:
                  receiver: Receiver | None = None, bands=1, record_rays=False, bvh_builder=0):
         d, self._keep = _make_desc(ir_length_in_seconds, sample_rate, materials, rays_per_dimension, bands, 0, record_rays, False, bvh_builder)
         dev = (C.c_int32 * len(devices))(*[int(x) for x in devices])
+        _prefer_bundled_nccl()
         self._h = _vp()
         _check(lib().arv2_multi_create(model._h, receiver._h if receiver is not None else None, C.byref(d), dev, len(devices), C.byref(self._h)))
         self.renderers = [AudioRenderer(model, ir_length_in_seconds, sample_rate, materials, rays_per_dimension, bands=bands,

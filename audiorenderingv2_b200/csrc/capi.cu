@@ -117,6 +117,7 @@ struct arv2_ctx {
 
 struct arv2_stream {
     int device = 0, n_src = 0, block = 0, ir_len = 0, P = 0, slot = 0;
+    int stages = 0;                                // ring depth of the step kernel (deep when a step and its successor find SMs of their own)
     cudaStream_t stream = nullptr;
     float2* d_tw = nullptr; float2* d_fdl = nullptr; float2* d_H[2] = {nullptr, nullptr};
     float2** d_Hptr = nullptr; float2** h_Hptr = nullptr;     // h_Hptr: one pinned entry per (source, swap parity)
@@ -1367,6 +1368,15 @@ int arv2_stream_open(int32_t device, int32_t n_sources, int32_t block, int32_t i
     auto* s = new arv2_stream;
     s->device = device; s->n_src = n_sources; s->block = block; s->ir_len = ir_length;
     s->P = (ir_length + block - 1) / block;
+    {
+        cudaDeviceProp prop;
+        const int sms = cudaGetDeviceProperties(&prop, device) == cudaSuccess ? prop.multiProcessorCount : 0;
+        // experiment (r09, profiles/r09_conv.md): a 16-stage ring when a step and its successor find SMs of their own
+        // (2 x sources x 8 CTAs <= SMs).  Measured: 6.42 against 6.53 us per block -- the ring depth is not what bounds a step.
+        bool deep = false;
+        if (const char* e = getenv("ARV2_CONV_DEEP_RING")) deep = atoi(e) != 0 && (atoi(e) > 1 || 2 * n_sources * 8 <= sms);
+        s->stages = conv_ring_stages(block, deep);
+    }
     const size_t spec = (size_t)s->P * block;          // float2 per (source) FDL or per ear
     const size_t nin = (size_t)n_sources * block;
 #define CKS(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); arv2_stream_close(s); return ARV2_ERR_CUDA; } } while (0)
@@ -1482,6 +1492,9 @@ static int enqueue_steps(arv2_stream* s, const float* d_in, float* d_out, int32_
     // with one launch per block and programmatic dependent launch, step k+1's accumulation runs in a second CTA on the
     // same SM while step k's rank 0 is in its FFTs; a looping cluster serialises them (profiles/r08_conv.md).
     const bool persistent = getenv("ARV2_CONV_PERSISTENT") != nullptr;
+    // experiment (r09): blocks 1.. of a call run their forward FFT before waiting for their predecessor (their input was
+    // complete before block 0 passed its wait).  Bit-identical, 6.44 against 6.56 us per block: kept as an opt-in.
+    const bool late_fft = getenv("ARV2_CONV_EARLY_FFT") == nullptr;
     if (n_blocks > 1 && persistent) {
         ConvStreamArgs a{};
         a.in = d_in; a.out = d_out;
@@ -1495,7 +1508,9 @@ static int enqueue_steps(arv2_stream* s, const float* d_in, float* d_out, int32_
             ConvStreamArgs a{};
             a.in = d_in + (size_t)b * nin; a.out = d_out + (size_t)b * 2 * nin;
             a.fdl = s->d_fdl; a.H = (const float2* const*)s->d_Hptr; a.tail = s->d_tail; a.tw = s->d_tw;
-            a.n_src = s->n_src; a.block = s->block; a.P = s->P; a.slot = s->slot; a.n_blocks = 1;
+            a.n_src = s->n_src; a.block = s->block; a.P = s->P; a.slot = s->slot; a.n_blocks = 1; a.stages = s->stages;
+            // the input of blocks 1.. of a call was complete before block 0 passed its wait: their forward FFT may run early
+            a.early_input = (b > 0 && !late_fft) ? 1 : 0;
             CK(conv_stream_step(a, st));
         }
     }

@@ -139,12 +139,22 @@ __global__ void __launch_bounds__(kConvThreads) block_spectra_kernel(const float
 #ifndef ARV2_CONV_FFTCOST
 #define ARV2_CONV_FFTCOST 8
 #endif
-constexpr int kStages = ARV2_CONV_STAGES;                  // most stages (mbarrier pairs) of the ring
+constexpr int kStages = ARV2_CONV_STAGES;                  // stages (mbarrier pairs) of the ring when two CTAs share an SM
+constexpr int kMaxStages = 2 * kStages;                    // ... of the deep ring (one CTA per SM)
 __host__ __device__ constexpr int ring_stages(int block)
 {
     const int budget = 104 * 1024 - 2 * block * (int)sizeof(float2);       // minus the twiddle table
     const int fit = budget / (3 * block * (int)sizeof(float2));
     return fit < 2 ? 2 : (fit > kStages ? kStages : fit);
+}
+// The deep ring of a stream with few sources (2 x sources x 8 CTAs <= SMs: a step and its successor find SMs of their
+// own, nothing has to share one): twice the bytes in flight per CTA.  A bulk copy from L2 takes ~1.2 us under load, so
+// 8 stages of 12 KB stream at 12 KB / 156 ns per CTA whatever the machine could deliver (r09 stamps); 16 stages double it.
+__host__ __device__ constexpr int ring_stages_deep(int block)
+{
+    const int budget = 208 * 1024 - 2 * block * (int)sizeof(float2);
+    const int fit = budget / (3 * block * (int)sizeof(float2));
+    return fit < 2 ? 2 : (fit > kMaxStages ? kMaxStages : fit);
 }
 constexpr int kConvStepThreads = kConvThreads + 32;     // stream / file kernels: kConvThreads consumers + one producer warp
 constexpr int kFftCostInPartitions = ARV2_CONV_FFTCOST;   // rank 0 also runs the forward FFT and takes this many partitions less per peer (8, 16, 24: same step time, r07)
@@ -225,10 +235,10 @@ struct MacRows {
 // per partition: 85 instructions, 280 ns), hence the stepped pointers and the interleaved IR rows.
 template <int BPT>
 __device__ __forceinline__ void mac_pipeline(float2* ring, unsigned long long* full, unsigned long long* empty, int n, int block,
-                                             MacRows r, float2 accL[BPT], float2 accR[BPT])
+                                             MacRows r, float2 accL[BPT], float2 accR[BPT], int stages = 0)
 {
     const unsigned row_bytes = (unsigned)block * sizeof(float2);
-    const int S = ring_stages(block);
+    const int S = stages > 0 ? stages : ring_stages(block);
     if (threadIdx.x >= kConvThreads) {
         if (threadIdx.x == kConvThreads) {
             int s = 0;
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
     CT_DECL
     CT_STAMP();
     extern __shared__ __align__(128) float2 smem[];
-    __shared__ unsigned long long full[kStages], empty[kStages];
+    __shared__ unsigned long long full[kMaxStages], empty[kMaxStages];
     const int block = a.block, N = 2 * block;
     // twiddles, then the TMA ring; the FFT buffers and the partial sums are only needed once the ring has drained
     // and live on top of it (a deeper ring instead of 24 KB of idle buffers)
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
     float2* fdl = a.fdl + (size_t)src * a.P * block;
     const float2* H = a.H[src];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConvThreads / 32); }
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConvThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -350,6 +360,15 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
     if (threadIdx.x < kConvThreads)
         for (int t = threadIdx.x; t < N; t += kConvThreads) stw[t] = a.tw[t];
 
+#ifdef ARV2_CONV_EMPTY_STEP
+    // TIMING EXPERIMENT ONLY: the launch mechanism alone (8-CTA clusters, programmatic dependent launch, same shared memory)
+    { pdl_wait(); pdl_launch_dependents(); return; }
+#endif
+#ifdef ARV2_CONV_EARLY_TRIGGER
+    // TIMING EXPERIMENT ONLY (results are wrong: step k+1 may read partition 2 before step k-1 published it): lets the
+    // successor in at once, to see how much of the 6.4 us period is launch latency + pre-wait work (r09)
+    pdl_launch_dependents();
+#endif
     float2 accL[BPT], accR[BPT];
 #pragma unroll
     for (int i = 0; i < BPT; ++i) { accL[i] = make_float2(0.f, 0.f); accR[i] = make_float2(0.f, 0.f); }
@@ -397,11 +416,32 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
         MacRows r;
         r.x = fdl + (size_t)s0 * block; r.x_step = -(long long)block; r.x_lo = fdl; r.x_wrap = (long long)a.P * block;
         r.h = H + (size_t)first * 2 * block; r.h_step = 2 * (long long)block;
-        mac_pipeline<BPT>(ring, full, empty, n, block, r, accL, accR);
+        mac_pipeline<BPT>(ring, full, empty, n, block, r, accL, accR, a.stages);
+    }
+    // newest block: forward FFT (rank 0; every thread of the CTA).  When the caller guarantees that `in` was complete
+    // before the PREVIOUS step passed its wait (blocks 1.. of one call: the whole call's input was there before block 0),
+    // it runs before this step's wait -- the transform needs nothing from step k, only its result may not be published
+    // into the delay line yet (the slot is the one step k reads as its oldest partition) -- which takes the input's
+    // round trip and the FFT (2.2 of 5.7 us) off the chain that serialises consecutive steps.
+    const float2* F = nullptr;
+    auto forward_fft = [&]() {
+        const float* in = a.in + (size_t)src * block;
+        CT_MARK(0);
+        for (int t = threadIdx.x; t < N; t += blockDim.x) bufa[t] = make_float2(t < block ? in[t] : 0.f, 0.f);
+        __syncthreads();
+        CT_MARK(1);
+        F = fft_smem(bufa, bufb, N, stw, false);
+        CT_MARK(2);
+    };
+    if (a.early_input && rank == 0) {
+        __syncthreads();                                  // the ring has drained: its memory becomes bufa / bufb / part
+        forward_fft();
     }
     CT_STAMP();
     pdl_wait();
+#ifndef ARV2_CONV_EARLY_TRIGGER
     pdl_launch_dependents();
+#endif
     CT_STAMP();
     __syncthreads();                                      // the ring has drained: its memory becomes bufa / bufb / part
     float tl[BPT], tr[BPT];                               // overlap-add tails of this thread's output samples (rank 0)
@@ -413,15 +453,9 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
             const bool on = threadIdx.x < kConvThreads && t < block;
             tl[i] = on ? tail[t] : 0.f; tr[i] = on ? tail[block + t] : 0.f;
         }
-        // newest block: forward FFT, publish into the frequency-domain delay line, multiply by partition 0
-        const float* in = a.in + (size_t)src * block;
+        // publish the newest block's spectrum into the frequency-domain delay line, multiply by partition 0
         float2* slot = fdl + (size_t)a.slot * block;
-        CT_MARK(0);
-        for (int t = threadIdx.x; t < N; t += blockDim.x) bufa[t] = make_float2(t < block ? in[t] : 0.f, 0.f);
-        __syncthreads();
-        CT_MARK(1);
-        const float2* F = fft_smem(bufa, bufb, N, stw, false);
-        CT_MARK(2);
+        if (!F) forward_fft();
         if (threadIdx.x < kConvThreads) {
 #pragma unroll
             for (int i = 0; i < BPT; ++i) {
@@ -454,6 +488,9 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
         printf("rank 0 cycles: in-load %lld fwd-fft %lld publish+p0 %lld | part-store %lld sync1 %lld dsmem-reduce %lld sync2 %lld inv-fft %lld\n",
                g_ct_marks[1] - g_ct_marks[0], g_ct_marks[2] - g_ct_marks[1], g_ct_marks[3] - g_ct_marks[2], g_ct_marks[4] - g_ct_marks[3],
                g_ct_marks[5] - g_ct_marks[4], g_ct_marks[6] - g_ct_marks[5], g_ct_marks[7] - g_ct_marks[6], g_ct_marks[8] - g_ct_marks[7]);
+    if ((blockIdx.x == 0 || blockIdx.x == 7) && threadIdx.x == 0 && a.slot >= 101 && a.slot <= 104)       // the timeline of consecutive steps
+        printf("T slot %d cta %d: start %llu mac-done %llu wait-done %llu fft+p01-done %llu end %llu (ns mod 1e6)\n", a.slot, blockIdx.x,
+               ct_[0] % 1000000ull, ct_[1] % 1000000ull, ct_[2] % 1000000ull, ct_[3] % 1000000ull, ct_[4] % 1000000ull);
     if ((blockIdx.x == 0 || blockIdx.x == 7) && threadIdx.x == 0 && a.slot == 100)
         printf("cta %d: mac %llu wait %llu fft+p01 %llu reduce+ifft %llu ns (start %llu); mac %lld cycles, whole %lld cycles / %llu ns\n", blockIdx.x,
                ct_[1] - ct_[0], ct_[2] - ct_[1], ct_[3] - ct_[2], ct_[4] - ct_[3], ct_[0] % 1000000ull, cc_[1] - cc_[0], cc_[4] - cc_[0], ct_[4] - ct_[0]);
@@ -669,13 +706,20 @@ __global__ void __launch_bounds__(kConvStepThreads) file_kernel(const ConvFileAr
 }
 
 size_t fft_smem_bytes(int block) { return (size_t)4 * block * sizeof(float2); }
-size_t step_smem_bytes(int block) { return (size_t)(2 + 3 * ring_stages(block)) * block * sizeof(float2); }
+size_t step_smem_bytes(int block, int stages) { return (size_t)(2 + 3 * (stages > 0 ? stages : ring_stages(block))) * block * sizeof(float2); }
 
 template <class K>
 cudaError_t launch_cluster(K kernel, unsigned grid, size_t smem, cudaStream_t stream, void** args, bool pdl = false)
 {
-    cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    // (one attribute call per kernel, device and size class instead of one per launch: a step is launched every few us)
+    static thread_local const void* set_for = nullptr; static thread_local size_t set_smem = 0; static thread_local int set_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (set_for != (const void*)kernel || set_smem < smem || set_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        set_for = (const void*)kernel; set_smem = smem; set_dev = dev;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvStepThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -792,12 +836,14 @@ cudaError_t conv_block_spectra(const float* d_x, long long n, long long seg_len,
     return cudaGetLastError();
 }
 
+int conv_ring_stages(int block, bool deep) { return deep ? ring_stages_deep(block) : ring_stages(block); }
+
 cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream)
 {
     ConvStreamArgs args = a;
     void* kargs[] = {&args};
     const unsigned grid = (unsigned)(a.n_src * kConvCluster);
-    const size_t smem = step_smem_bytes(a.block);
+    const size_t smem = step_smem_bytes(a.block, a.stages);
     const int bpt = (a.block + kConvThreads - 1) / kConvThreads;
     static const bool pdl = getenv("ARV2_CONV_NO_PDL") == nullptr;     // A/B switch
     switch (bpt) {
@@ -814,7 +860,7 @@ cudaError_t conv_stream_blocks(const ConvStreamArgs& a, cudaStream_t stream)
     ConvStreamArgs args = a;
     void* kargs[] = {&args};
     const unsigned grid = (unsigned)(a.n_src * kConvCluster);
-    const size_t smem = step_smem_bytes(a.block);
+    const size_t smem = step_smem_bytes(a.block, 0);
     const int bpt = (a.block + kConvThreads - 1) / kConvThreads;
     switch (bpt) {
     case 1: return launch_cluster(stream_blocks_kernel<1>, grid, smem, stream, kargs);
@@ -832,7 +878,7 @@ cudaError_t conv_file(const ConvFileArgs& a, cudaStream_t stream)
     const long long clusters = (long long)a.n_seg * out_blocks;
     if (clusters == 0) return cudaSuccess;
     const unsigned grid = (unsigned)(clusters * kConvCluster);
-    const size_t smem = step_smem_bytes(a.block);
+    const size_t smem = step_smem_bytes(a.block, 0);
     const int bpt = (a.block + kConvThreads - 1) / kConvThreads;
     switch (bpt) {
     case 1: return launch_cluster(file_kernel<1>, grid, smem, stream, kargs);

@@ -36,10 +36,16 @@ struct ConvStreamArgs {
     const float2* tw;
     int n_src, block, P, slot; // slot = ring position of the newest block (of the first block for conv_stream_blocks)
     int n_blocks;              // conv_stream_blocks: consecutive blocks; in / out advance by n_src*block / n_src*2*block floats per block
+    int stages;                // conv_stream_step: stages of the shared-memory ring (0 = conv_ring_stages(block, false))
+    int early_input;           // conv_stream_step: `in` was complete before the previous step passed its wait (blocks 1.. of one
+                               // call): the forward FFT of the newest block runs before this step waits for its predecessor
 };
 // One streaming step for all sources: forward FFT + FDL write + partitioned spectral MAC
 // + DSMEM reduction + stereo inverse FFT + overlap-add, in ONE cluster launch.
 cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream);
+// ring depth of a step: the default leaves room for two CTAs per SM (a step and its successor share the SMs when a step
+// fills the machine), the deep one takes a whole SM (twice the bytes in flight: streams with few sources)
+int conv_ring_stages(int block, bool deep);
 // a.n_blocks consecutive steps in ONE cluster launch (every source's cluster loops over the blocks); same results.
 cudaError_t conv_stream_blocks(const ConvStreamArgs& a, cudaStream_t stream);
 
