@@ -1651,4 +1651,7 @@ int arv2_wav_write_stereo_normalized(const char* path, const float* l, const flo
 
 void arv2_free(void* p) { std::free(p); }
 
+/* not in include/arv2.h: tuning builds only (-DARV2_CONV_TIMING -DARV2_CONV_TRACE) */
+extern "C" int arv2_debug_conv_trace(void* out, size_t bytes) { return arv2::conv_debug_trace(out, bytes) == cudaSuccess ? 0 : -1; }
+
 } // extern "C"

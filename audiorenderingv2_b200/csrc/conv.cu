@@ -33,8 +33,21 @@ namespace {
 #ifdef ARV2_CONV_TIMING
 __device__ long long g_ct_marks[16];                 // clock64 marks of cluster 0, rank 0, thread 0 (debug build only)
 #define CT_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_ct_marks[i] = clock64(); } while (0)
+// -DARV2_CONV_TRACE (with ARV2_CONV_TIMING): globaltimer stamps of every step without printf: g_ct_trace[slot % 256][cta % 16][64],
+// consumer thread 0 in [0, 40) (0 start, 1 ring ready, 2 + i after partition i, 36 mac done, 37 wait done, 38 end), producer
+// lane in [40, 64) (40 + i when the copies of partition i are issued); read back with arv2_debug_conv_trace
+__device__ unsigned long long g_ct_trace[256][16][96];
+#ifdef ARV2_CONV_TRACE
+// (stamps go to shared memory and are dumped when the step ends: no global store before the wait)
+__shared__ unsigned long long sh_ct_trace[96];
+#define CT_TRACE(slot, idx) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); sh_ct_trace[idx] = t_; } while (0)
+#define CT_TRACE_DUMP(slot) do { __syncthreads(); if (threadIdx.x < 96) g_ct_trace[(slot) & 255][blockIdx.x & 15][threadIdx.x] = sh_ct_trace[threadIdx.x]; } while (0)
+#else
+#define CT_TRACE(slot, idx) do {} while (0)
+#endif
 #else
 #define CT_MARK(i) do {} while (0)
+#define CT_TRACE(slot, idx) do {} while (0)
 #endif
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -235,8 +248,9 @@ struct MacRows {
 // per partition: 85 instructions, 280 ns), hence the stepped pointers and the interleaved IR rows.
 template <int BPT>
 __device__ __forceinline__ void mac_pipeline(float2* ring, unsigned long long* full, unsigned long long* empty, int n, int block,
-                                             MacRows r, float2 accL[BPT], float2 accR[BPT], int stages = 0)
+                                             MacRows r, float2 accL[BPT], float2 accR[BPT], int stages = 0, int trace_slot = -1)
 {
+    (void)trace_slot;
     const unsigned row_bytes = (unsigned)block * sizeof(float2);
     const int S = stages > 0 ? stages : ring_stages(block);
     if (threadIdx.x >= kConvThreads) {
@@ -246,9 +260,11 @@ __device__ __forceinline__ void mac_pipeline(float2* ring, unsigned long long* f
             float2* dst = ring;
             for (int i = 0; i < n; ++i) {
                 if (i >= S) mbar_wait(&empty[s], parity);
+                if (trace_slot >= 0 && i < 24) CT_TRACE(trace_slot, 64 + i);
                 mbar_expect_tx(&full[s], 3 * row_bytes);
                 bulk_g2s(dst, r.x, row_bytes, &full[s]);
                 bulk_g2s(dst + block, r.h, 2 * row_bytes, &full[s]);
+                if (trace_slot >= 0 && i < 24) CT_TRACE(trace_slot, 40 + i);
                 r.x += r.x_step; if (r.x < r.x_lo) r.x += r.x_wrap;
                 r.h += r.h_step;
                 dst += 3 * block;
@@ -265,6 +281,7 @@ __device__ __forceinline__ void mac_pipeline(float2* ring, unsigned long long* f
         mac_rows<BPT>(src, src + block, src + 2 * block, block, accL, accR);
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
+        if (trace_slot >= 0 && threadIdx.x == 0 && i < 34) CT_TRACE(trace_slot, 2 + i);
         src += 3 * block;
         if (++s == S) { s = 0; src = ring; parity ^= 1u; }
     }
@@ -337,6 +354,11 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
 {
     CT_DECL
     CT_STAMP();
+#ifdef ARV2_CONV_TRACE
+    if (threadIdx.x < 96) sh_ct_trace[threadIdx.x] = 0ull;
+    __syncthreads();
+#endif
+    if (threadIdx.x == 0) CT_TRACE(a.slot, 0);
     extern __shared__ __align__(128) float2 smem[];
     __shared__ unsigned long long full[kMaxStages], empty[kMaxStages];
     const int block = a.block, N = 2 * block;
@@ -416,7 +438,9 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
         MacRows r;
         r.x = fdl + (size_t)s0 * block; r.x_step = -(long long)block; r.x_lo = fdl; r.x_wrap = (long long)a.P * block;
         r.h = H + (size_t)first * 2 * block; r.h_step = 2 * (long long)block;
-        mac_pipeline<BPT>(ring, full, empty, n, block, r, accL, accR, a.stages);
+        if (threadIdx.x == 0) CT_TRACE(a.slot, 1);
+        mac_pipeline<BPT>(ring, full, empty, n, block, r, accL, accR, a.stages, a.slot);
+        if (threadIdx.x == 0) CT_TRACE(a.slot, 36);
     }
     // newest block: forward FFT (rank 0; every thread of the CTA).  When the caller guarantees that `in` was complete
     // before the PREVIOUS step passed its wait (blocks 1.. of one call: the whole call's input was there before block 0),
@@ -442,6 +466,7 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
 #ifndef ARV2_CONV_EARLY_TRIGGER
     pdl_launch_dependents();
 #endif
+    if (threadIdx.x == 0) CT_TRACE(a.slot, 37);
     CT_STAMP();
     __syncthreads();                                      // the ring has drained: its memory becomes bufa / bufb / part
     float tl[BPT], tr[BPT];                               // overlap-add tails of this thread's output samples (rank 0)
@@ -483,7 +508,11 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
     CT_STAMP();
     float2* y = reduce_and_inverse<BPT>(cluster, part, bufa, bufb, block, stw, accL, accR);
     CT_STAMP();
-#ifdef ARV2_CONV_TIMING
+    if (threadIdx.x == 0) CT_TRACE(a.slot, 38);
+#ifdef ARV2_CONV_TRACE
+    CT_TRACE_DUMP(a.slot);
+#endif
+#if defined(ARV2_CONV_TIMING) && !defined(ARV2_CONV_TRACE)
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.slot == 100)
         printf("rank 0 cycles: in-load %lld fwd-fft %lld publish+p0 %lld | part-store %lld sync1 %lld dsmem-reduce %lld sync2 %lld inv-fft %lld\n",
                g_ct_marks[1] - g_ct_marks[0], g_ct_marks[2] - g_ct_marks[1], g_ct_marks[3] - g_ct_marks[2], g_ct_marks[4] - g_ct_marks[3],
@@ -834,6 +863,16 @@ cudaError_t conv_block_spectra(const float* d_x, long long n, long long seg_len,
     if (grid == 0) return cudaSuccess;
     block_spectra_kernel<<<grid, kConvThreads, smem, stream>>>(d_x, n, seg_len, blocks_per_seg, block, d_tw, d_X);
     return cudaGetLastError();
+}
+
+cudaError_t conv_debug_trace(void* out, size_t bytes)
+{
+#ifdef ARV2_CONV_TRACE
+    return cudaMemcpyFromSymbol(out, g_ct_trace, bytes < sizeof(g_ct_trace) ? bytes : sizeof(g_ct_trace));
+#else
+    (void)out; (void)bytes;
+    return cudaErrorNotSupported;
+#endif
 }
 
 int conv_ring_stages(int block, bool deep) { return deep ? ring_stages_deep(block) : ring_stages(block); }

@@ -46,6 +46,8 @@ cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream);
 // ring depth of a step: the default leaves room for two CTAs per SM (a step and its successor share the SMs when a step
 // fills the machine), the deep one takes a whole SM (twice the bytes in flight: streams with few sources)
 int conv_ring_stages(int block, bool deep);
+// builds with -DARV2_CONV_TIMING -DARV2_CONV_TRACE: the stamps of the last steps (conv.cu: g_ct_trace)
+cudaError_t conv_debug_trace(void* out, size_t bytes);
 // a.n_blocks consecutive steps in ONE cluster launch (every source's cluster loops over the blocks); same results.
 cudaError_t conv_stream_blocks(const ConvStreamArgs& a, cudaStream_t stream);
 
