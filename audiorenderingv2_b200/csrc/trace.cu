@@ -14,6 +14,11 @@
 //                    (direction_keys_kernel + radix sort) so a warp is a coherent bundle for the first bounces.
 //                    trace_kernel = depth-first fallback (no queue memory / A-B), trace2_kernel = the decoupled-lane
 //                    experiment of r03.
+//   sweep_kernel     the tracer of launches of >= 3 M rays: bounce-synchronous, one launch per sweep over ALL paths alive
+//                    (8 segments for the fresh bundles, then 3 per sweep); the survivors are compacted into a second state
+//                    buffer and re-binned by (cell of the new origin, octahedral cell of the new direction) with a counting
+//                    sort whose histogram the sweep takes itself, so a warp is a bundle at EVERY depth (18.0 instead of
+//                    15.4 lanes per node step and +12 % on the 1M-triangle scene, +19 % at 100 M rays; profiles/r09).
 //   closest_hit      software BVH: binary 64 B nodes with both child boxes in the parent, every record fetched with
 //                    256-bit loads (a divergent gather costs the L1 data pipe one wavefront per lane and load
 //                    instruction; the whole scene is L2-resident and DRAM idles).  Quantised 32 B nodes and 4-wide
