@@ -199,8 +199,13 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
 {
+#ifdef ARV2_CONV_BULK_CTA
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+#endif
 }
 
 // Programmatic dependent launch (sm_90+): step k+1 may become resident while step k is still running; everything
@@ -261,10 +266,21 @@ __device__ __forceinline__ void mac_pipeline(float2* ring, unsigned long long* f
             for (int i = 0; i < n; ++i) {
                 if (i >= S) mbar_wait(&empty[s], parity);
                 if (trace_slot >= 0 && i < 24) CT_TRACE(trace_slot, 64 + i);
+#if defined(ARV2_CONV_TRACE) && defined(ARV2_CONV_TRACE_FINE)
+                // where inside the issue of partition i the producer spends its time: [40 + 3j] after expect_tx, + 1 after the
+                // copy of the input spectrum, + 2 after the copy of the IR spectra, for i = 10 + j, j < 8
+                mbar_expect_tx(&full[s], 3 * row_bytes);
+                if (trace_slot >= 0 && i >= 10 && i < 18) CT_TRACE(trace_slot, 40 + 3 * (i - 10));
+                bulk_g2s(dst, r.x, row_bytes, &full[s]);
+                if (trace_slot >= 0 && i >= 10 && i < 18) CT_TRACE(trace_slot, 41 + 3 * (i - 10));
+                bulk_g2s(dst + block, r.h, 2 * row_bytes, &full[s]);
+                if (trace_slot >= 0 && i >= 10 && i < 18) CT_TRACE(trace_slot, 42 + 3 * (i - 10));
+#else
                 mbar_expect_tx(&full[s], 3 * row_bytes);
                 bulk_g2s(dst, r.x, row_bytes, &full[s]);
                 bulk_g2s(dst + block, r.h, 2 * row_bytes, &full[s]);
                 if (trace_slot >= 0 && i < 24) CT_TRACE(trace_slot, 40 + i);
+#endif
                 r.x += r.x_step; if (r.x < r.x_lo) r.x += r.x_wrap;
                 r.h += r.h_step;
                 dst += 3 * block;
