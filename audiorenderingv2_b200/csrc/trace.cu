@@ -15,7 +15,7 @@
 //                    trace_kernel = depth-first fallback (no queue memory / A-B), trace2_kernel = the decoupled-lane
 //                    experiment of r03.
 //   sweep_kernel     the tracer of launches of >= 3 M rays: bounce-synchronous, one launch per sweep over ALL paths alive
-//                    (8 segments for the fresh bundles, then 3 per sweep); the survivors are compacted into a second state
+//                    (8 segments for the fresh bundles, then 2 per sweep); the survivors are compacted into a second state
 //                    buffer and re-binned by (cell of the new origin, octahedral cell of the new direction) with a counting
 //                    sort whose histogram the sweep takes itself, so a warp is a bundle at EVERY depth (18.0 instead of
 //                    15.4 lanes per node step and +12 % on the 1M-triangle scene, +19 % at 100 M rays; profiles/r09).

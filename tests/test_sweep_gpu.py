@@ -44,7 +44,7 @@ def test_sweeps_equal_oracle_and_wave_c1(golden_scenes, golden_receiver, monkeyp
         monkeypatch.setenv(k, v)
     case = c1(golden_scenes, golden_receiver, hrtf=0.9)
     a = run(case, True)
-    first = int(env.get("ARV2_SWEEP_FIRST", 8)); per = int(env.get("ARV2_SWEEP_SEGMENTS", 3))
+    first = int(env.get("ARV2_SWEEP_FIRST", 8)); per = int(env.get("ARV2_SWEEP_SEGMENTS", 2))
     assert n_sweeps(a[0]) == 1 + max(0, -(-(case.max_bounces - first) // per))
     b = run(case, False)
     assert n_sweeps(b[0]) == 0
@@ -57,7 +57,7 @@ def test_sweeps_closed_box_300_bounces(golden_scenes, golden_receiver):
                 rays=(32, 16, 8), emitter=(3, 1, -2), center=(-8, 4, 6), yaw=20.0, max_bounces=300, ir_seconds=60,
                 sample_rate=8000, materials=[("Material.001", 0.01)])
     a = run(case, True)
-    assert n_sweeps(a[0]) == 1 + -(-(300 - 8) // 3)
+    assert n_sweeps(a[0]) == 1 + -(-(300 - 8) // 2)
     assert check_parity(a[1], a[2], a[3], a[4], case.oracle_run()) == 1.0
     assert a[1]["nseg"].max() > 150
 
