@@ -1494,9 +1494,9 @@ static int enqueue_steps(arv2_stream* s, const float* d_in, float* d_out, int32_
     // with one launch per block and programmatic dependent launch, step k+1's accumulation runs in a second CTA on the
     // same SM while step k's rank 0 is in its FFTs; a looping cluster serialises them (profiles/r08_conv.md).
     const bool persistent = getenv("ARV2_CONV_PERSISTENT") != nullptr;
-    // experiment (r09): blocks 1.. of a call run their forward FFT before waiting for their predecessor (their input was
-    // complete before block 0 passed its wait).  Bit-identical, 6.44 against 6.56 us per block: kept as an opt-in.
-    const bool late_fft = getenv("ARV2_CONV_EARLY_FFT") == nullptr;
+    // blocks 1.. of a call run their forward FFT before waiting for their predecessor (their input was complete before
+    // block 0 passed its wait).  Bit-identical; 6.00 against 6.28 us per block with 2 sources (r09; ARV2_CONV_LATE_FFT=1: A/B)
+    const bool late_fft = getenv("ARV2_CONV_LATE_FFT") != nullptr;
     if (n_blocks > 1 && persistent) {
         ConvStreamArgs a{};
         a.in = d_in; a.out = d_out;

@@ -303,6 +303,65 @@ __device__ __forceinline__ void mac_pipeline(float2* ring, unsigned long long* f
     }
 }
 
+// The same pipeline with TWO partitions per stage, for callers whose partitions are consecutive rows (x_step = -block,
+// h_step = 2*block: stream_step_kernel): the IR rows of partitions i, i+1 are one 4-row copy, the two input spectra one
+// 2-row copy unless the delay line wraps between them -- half as many bulk copies per partition.  A step launched as a
+// programmatic dependent stops issuing after its 24th bulk copy until its predecessor has completed (r09 traces), and the
+// producer lane's issue rate (~65 ns per copy) bounds the phase besides.  Stage layout (rows of `block` float2):
+// [X_{i+1}, X_i, HL_i, HR_i, HL_{i+1}, HR_{i+1}]; the accumulation order (i, then i+1) is that of mac_pipeline, so the
+// results are bit-identical.  ring: float2[stages / 2][6][block].
+template <int BPT>
+__device__ __forceinline__ void mac_pipeline_pairs(float2* ring, unsigned long long* full, unsigned long long* empty, int n, int block,
+                                                   MacRows r, float2 accL[BPT], float2 accR[BPT], int stages = 0, int trace_slot = -1)
+{
+    (void)trace_slot;
+    const unsigned row_bytes = (unsigned)block * sizeof(float2);
+    const int S1 = stages > 0 ? stages : ring_stages(block);
+    const int S = S1 / 2 > 0 ? S1 / 2 : 1;                 // pair stages
+    const int pairs = (n + 1) / 2;
+    if (threadIdx.x >= kConvThreads) {
+        if (threadIdx.x == kConvThreads) {
+            int s = 0;
+            unsigned parity = 1;
+            float2* dst = ring;
+            for (int j = 0; j < pairs; ++j) {
+                const bool two = 2 * j + 1 < n;
+                if (j >= S) mbar_wait(&empty[s], parity);
+                const float2* xa = r.x;
+                const float2* xb = xa + r.x_step; if (xb < r.x_lo) xb += r.x_wrap;
+                mbar_expect_tx(&full[s], (two ? 6u : 3u) * row_bytes);
+                if (two) {
+                    if (xb + block == xa) bulk_g2s(dst, xb, 2 * row_bytes, &full[s]);
+                    else { bulk_g2s(dst, xb, row_bytes, &full[s]); bulk_g2s(dst + block, xa, row_bytes, &full[s]); }
+                    bulk_g2s(dst + 2 * block, r.h, 4 * row_bytes, &full[s]);
+                    r.x = xb + r.x_step; if (r.x < r.x_lo) r.x += r.x_wrap;
+                    r.h += 2 * r.h_step;
+                } else {
+                    bulk_g2s(dst + block, xa, row_bytes, &full[s]);
+                    bulk_g2s(dst + 2 * block, r.h, 2 * row_bytes, &full[s]);
+                }
+                if (trace_slot >= 0 && j < 24) CT_TRACE(trace_slot, 40 + j);
+                dst += 6 * block;
+                if (++s == S) { s = 0; dst = ring; parity ^= 1u; }
+            }
+        }
+        return;
+    }
+    int s = 0;
+    unsigned parity = 0;
+    const float2* src = ring;
+    for (int j = 0; j < pairs; ++j) {
+        mbar_wait(&full[s], parity);
+        mac_rows<BPT>(src + block, src + 2 * block, src + 3 * block, block, accL, accR);
+        if (2 * j + 1 < n) mac_rows<BPT>(src, src + 4 * block, src + 5 * block, block, accL, accR);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
+        if (trace_slot >= 0 && threadIdx.x == 0 && j < 34) CT_TRACE(trace_slot, 2 + j);
+        src += 6 * block;
+        if (++s == S) { s = 0; src = ring; parity ^= 1u; }
+    }
+}
+
 // Cluster-wide reduction of the per-CTA partial sums, then the inverse transform on rank 0.  Rank r owns the bins
 // [r*block/C, (r+1)*block/C) of both ears: it sums the C partial sums through distributed shared memory (all C
 // remote loads in flight at once) and writes Z = YL + i*YR, already unpacked to the full Hermitian layout, straight
@@ -455,7 +514,11 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
         r.x = fdl + (size_t)s0 * block; r.x_step = -(long long)block; r.x_lo = fdl; r.x_wrap = (long long)a.P * block;
         r.h = H + (size_t)first * 2 * block; r.h_step = 2 * (long long)block;
         if (threadIdx.x == 0) CT_TRACE(a.slot, 1);
+#ifdef ARV2_CONV_SINGLE_COPIES
         mac_pipeline<BPT>(ring, full, empty, n, block, r, accL, accR, a.stages, a.slot);
+#else
+        mac_pipeline_pairs<BPT>(ring, full, empty, n, block, r, accL, accR, a.stages, a.slot);
+#endif
         if (threadIdx.x == 0) CT_TRACE(a.slot, 36);
     }
     // newest block: forward FFT (rank 0; every thread of the CTA).  When the caller guarantees that `in` was complete
