@@ -117,6 +117,7 @@ struct arv2_ctx {
 
 struct arv2_stream {
     int device = 0, n_src = 0, block = 0, ir_len = 0, P = 0, slot = 0;
+    int cluster = 8;                               // CTAs per source of the step kernel: 16 for streams of <= 4 sources (r09)
     int stages = 0;                                // ring depth of the step kernel (deep when a step and its successor find SMs of their own)
     cudaStream_t stream = nullptr;
     float2* d_tw = nullptr; float2* d_fdl = nullptr; float2* d_H[2] = {nullptr, nullptr};
@@ -1378,6 +1379,13 @@ int arv2_stream_open(int32_t device, int32_t n_sources, int32_t block, int32_t i
         bool deep = false;
         if (const char* e = getenv("ARV2_CONV_DEEP_RING")) deep = atoi(e) != 0 && (atoi(e) > 1 || 2 * n_sources * 8 <= sms);
         s->stages = conv_ring_stages(block, deep);
+        // 16 CTAs per source when there are few sources: every rank then streams at most 12 old partitions before the wait,
+        // which is what a programmatic dependent gets through before its predecessor has completed (profiles/r09_conv.md).
+        // The summation order over partitions depends on the cluster size, so it is fixed per stream.
+        int wide_max = 4;
+        if (const char* e = getenv("ARV2_CONV_CLUSTER16")) wide_max = atoi(e);        // A/B: most sources of a stream that runs 16-CTA clusters (0 = never)
+        const bool wide = n_sources <= wide_max && !getenv("ARV2_CONV_PERSISTENT");
+        s->cluster = (wide && conv_cluster16_ok(n_sources, block)) ? 16 : 8;
     }
     const size_t spec = (size_t)s->P * block;          // float2 per (source) FDL or per ear
     const size_t nin = (size_t)n_sources * block;
@@ -1510,7 +1518,7 @@ static int enqueue_steps(arv2_stream* s, const float* d_in, float* d_out, int32_
             ConvStreamArgs a{};
             a.in = d_in + (size_t)b * nin; a.out = d_out + (size_t)b * 2 * nin;
             a.fdl = s->d_fdl; a.H = (const float2* const*)s->d_Hptr; a.tail = s->d_tail; a.tw = s->d_tw;
-            a.n_src = s->n_src; a.block = s->block; a.P = s->P; a.slot = s->slot; a.n_blocks = 1; a.stages = s->stages;
+            a.n_src = s->n_src; a.block = s->block; a.P = s->P; a.slot = s->slot; a.n_blocks = 1; a.stages = s->stages; a.cluster = s->cluster;
             // the input of blocks 1.. of a call was complete before block 0 passed its wait: their forward FFT may run early
             a.early_input = (b > 0 && !late_fft) ? 1 : 0;
             CK(conv_stream_step(a, st));

@@ -367,12 +367,11 @@ __device__ __forceinline__ void mac_pipeline_pairs(float2* ring, unsigned long l
 // remote loads in flight at once) and writes Z = YL + i*YR, already unpacked to the full Hermitian layout, straight
 // into rank 0's FFT buffer.  Rank 0 returns the time-domain buffer (re = left, im = right, unnormalised); other
 // ranks return nullptr.
-template <int BPT>
+template <int BPT, int C = kConvCluster>
 __device__ float2* reduce_and_inverse(cg::cluster_group& cluster, float2* part, float2* bufa, float2* bufb,
                                       int block, const float2* tw, const float2 accL[BPT], const float2 accR[BPT])
 {
     const unsigned rank = cluster.block_rank();
-    constexpr int C = kConvCluster;
     if (threadIdx.x < kConvThreads) {
 #pragma unroll
         for (int i = 0; i < BPT; ++i) {
@@ -392,12 +391,17 @@ __device__ float2* reduce_and_inverse(cg::cluster_group& cluster, float2* part, 
         float2* z = cluster.map_shared_rank(bufa, 0);
         for (int e = threadIdx.x; e < per; e += blockDim.x) {
             const int k = (int)rank * per + e;
-            float2 vl[C], vr[C];
+            // (eight remote loads of each ear in flight at a time; the ranks are summed in rank order)
+            float2 l = make_float2(0.f, 0.f), rr = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int r = 0; r < C; ++r) { vl[r] = remote[r][k]; vr[r] = remote[r][block + k]; }
-            float2 l = vl[0], rr = vr[0];
+            for (int r0 = 0; r0 < C; r0 += 8) {
+                float2 vl[8], vr[8];
 #pragma unroll
-            for (int r = 1; r < C; ++r) { l.x += vl[r].x; l.y += vl[r].y; rr.x += vr[r].x; rr.y += vr[r].y; }
+                for (int r = 0; r < 8; ++r) { vl[r] = remote[r0 + r][k]; vr[r] = remote[r0 + r][block + k]; }
+                if (r0 == 0) { l = vl[0]; rr = vr[0]; }
+#pragma unroll
+                for (int r = (r0 == 0 ? 1 : 0); r < 8; ++r) { l.x += vl[r].x; l.y += vl[r].y; rr.x += vr[r].x; rr.y += vr[r].y; }
+            }
             if (k == 0) {
                 z[0] = make_float2(l.x, rr.x);
                 z[block] = make_float2(l.y, rr.y);
@@ -424,7 +428,7 @@ __device__ float2* reduce_and_inverse(cg::cluster_group& cluster, float2* part, 
 #define CT_STAMP() do {} while (0)
 #endif
 
-template <int BPT>
+template <int BPT, int CL = kConvCluster>
 __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const ConvStreamArgs a)
 {
     CT_DECL
@@ -443,7 +447,10 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
     float2* bufa = ring; float2* bufb = bufa + N; float2* part = bufb + N;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
-    constexpr unsigned C = kConvCluster;
+    constexpr unsigned C = CL;
+    // a 16-CTA cluster per source (streams of few sources): every rank but 0 streams 12 old partitions = 144 KB, what a
+    // programmatic dependent gets through before its predecessor has completed (r09 traces); rank 0 takes 6
+    constexpr int kFftCost = CL == 16 ? 6 : kFftCostInPartitions;
     const int src = blockIdx.x / C;
     float2* fdl = a.fdl + (size_t)src * a.P * block;
     const float2* H = a.H[src];
@@ -477,7 +484,7 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
     // Rank 0 runs the forward FFT (~8 partitions' worth of time, measured with clock64) and therefore takes a
     // shorter contiguous range of the old partitions; the rest is split evenly over ranks 1..C-1.
     const int T = max(0, a.P - 2);
-    int n0 = (T - kFftCostInPartitions * ((int)C - 1)) / (int)C;
+    int n0 = (T - kFftCost * ((int)C - 1)) / (int)C;
     n0 = max(0, min(T, n0));
     int first, n;
     if (rank == 0) { first = 2; n = n0; }
@@ -542,7 +549,7 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
     }
     CT_STAMP();
     pdl_wait();
-#ifndef ARV2_CONV_EARLY_TRIGGER
+#if !defined(ARV2_CONV_EARLY_TRIGGER) && !defined(ARV2_CONV_LATE_TRIGGER)
     pdl_launch_dependents();
 #endif
     if (threadIdx.x == 0) CT_TRACE(a.slot, 37);
@@ -585,7 +592,10 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
         }
     }
     CT_STAMP();
-    float2* y = reduce_and_inverse<BPT>(cluster, part, bufa, bufb, block, stw, accL, accR);
+#ifdef ARV2_CONV_LATE_TRIGGER
+    pdl_launch_dependents();        // timing experiment (r09): the successor is let in only when this step is in its reduction
+#endif
+    float2* y = reduce_and_inverse<BPT, CL>(cluster, part, bufa, bufb, block, stw, accL, accR);
     CT_STAMP();
     if (threadIdx.x == 0) CT_TRACE(a.slot, 38);
 #ifdef ARV2_CONV_TRACE
@@ -817,7 +827,7 @@ size_t fft_smem_bytes(int block) { return (size_t)4 * block * sizeof(float2); }
 size_t step_smem_bytes(int block, int stages) { return (size_t)(2 + 3 * (stages > 0 ? stages : ring_stages(block))) * block * sizeof(float2); }
 
 template <class K>
-cudaError_t launch_cluster(K kernel, unsigned grid, size_t smem, cudaStream_t stream, void** args, bool pdl = false)
+cudaError_t launch_cluster(K kernel, unsigned grid, size_t smem, cudaStream_t stream, void** args, bool pdl = false, int cluster = kConvCluster)
 {
     // (one attribute call per kernel, device and size class instead of one per launch: a step is launched every few us)
     static thread_local const void* set_for = nullptr; static thread_local size_t set_smem = 0; static thread_local int set_dev = -1;
@@ -832,7 +842,7 @@ cudaError_t launch_cluster(K kernel, unsigned grid, size_t smem, cudaStream_t st
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvStepThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kConvCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
@@ -956,14 +966,56 @@ cudaError_t conv_debug_trace(void* out, size_t bytes)
 
 int conv_ring_stages(int block, bool deep) { return deep ? ring_stages_deep(block) : ring_stages(block); }
 
+template <int BPT>
+cudaError_t step16_prepare()
+{
+    static thread_local int done_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done_dev == dev) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute((const void*)stream_step_kernel<BPT, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) done_dev = dev;
+    return e;
+}
+
+// Can clusters of 16 CTAs of the step kernel be launched here, n_src of them at a time (twice that with a successor in)?
+bool conv_cluster16_ok(int n_src, int block)
+{
+    const int bpt = (block + kConvThreads - 1) / kConvThreads;
+    const void* k = bpt == 1 ? (const void*)stream_step_kernel<1, 16> : bpt == 2 ? (const void*)stream_step_kernel<2, 16> : (const void*)stream_step_kernel<4, 16>;
+    const size_t smem = step_smem_bytes(block, 0);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)n_src * 16); cfg.blockDim = dim3(kConvStepThreads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+    return n >= 2 * n_src;
+}
+
 cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream)
 {
     ConvStreamArgs args = a;
     void* kargs[] = {&args};
-    const unsigned grid = (unsigned)(a.n_src * kConvCluster);
     const size_t smem = step_smem_bytes(a.block, a.stages);
     const int bpt = (a.block + kConvThreads - 1) / kConvThreads;
     static const bool pdl = getenv("ARV2_CONV_NO_PDL") == nullptr;     // A/B switch
+    if (a.cluster == 16) {
+        const unsigned grid16 = (unsigned)(a.n_src * 16);
+        cudaError_t e = bpt == 1 ? step16_prepare<1>() : bpt == 2 ? step16_prepare<2>() : step16_prepare<4>();
+        if (e != cudaSuccess) return e;
+        switch (bpt) {
+        case 1: return launch_cluster(stream_step_kernel<1, 16>, grid16, smem, stream, kargs, pdl, 16);
+        case 2: return launch_cluster(stream_step_kernel<2, 16>, grid16, smem, stream, kargs, pdl, 16);
+        case 4: return launch_cluster(stream_step_kernel<4, 16>, grid16, smem, stream, kargs, pdl, 16);
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    const unsigned grid = (unsigned)(a.n_src * kConvCluster);
     switch (bpt) {
     case 1: return launch_cluster(stream_step_kernel<1>, grid, smem, stream, kargs, pdl);
     case 2: return launch_cluster(stream_step_kernel<2>, grid, smem, stream, kargs, pdl);

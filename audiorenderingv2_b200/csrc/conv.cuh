@@ -37,6 +37,7 @@ struct ConvStreamArgs {
     int n_src, block, P, slot; // slot = ring position of the newest block (of the first block for conv_stream_blocks)
     int n_blocks;              // conv_stream_blocks: consecutive blocks; in / out advance by n_src*block / n_src*2*block floats per block
     int stages;                // conv_stream_step: stages of the shared-memory ring (0 = conv_ring_stages(block, false))
+    int cluster;               // conv_stream_step: CTAs per source, 8 (0 = 8) or 16 (conv_cluster16_ok)
     int early_input;           // conv_stream_step: `in` was complete before the previous step passed its wait (blocks 1.. of one
                                // call): the forward FFT of the newest block runs before this step waits for its predecessor
 };
@@ -46,6 +47,8 @@ cudaError_t conv_stream_step(const ConvStreamArgs& a, cudaStream_t stream);
 // ring depth of a step: the default leaves room for two CTAs per SM (a step and its successor share the SMs when a step
 // fills the machine), the deep one takes a whole SM (twice the bytes in flight: streams with few sources)
 int conv_ring_stages(int block, bool deep);
+// clusters of 16 CTAs per source for streams of few sources: launchable here, 2 * n_src of them at a time?
+bool conv_cluster16_ok(int n_src, int block);
 // builds with -DARV2_CONV_TIMING -DARV2_CONV_TRACE: the stamps of the last steps (conv.cu: g_ct_trace)
 cudaError_t conv_debug_trace(void* out, size_t bytes);
 // a.n_blocks consecutive steps in ONE cluster launch (every source's cluster loops over the blocks); same results.

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 import audiorenderingv2_b200 as arv
 dev = torch.device("cuda", 0)
-for n_src in (1, 2, 4, 16):
+for n_src in [int(v) for v in os.environ.get("NSRC_LIST", "1,2,4,16").split(",")]:
     st = arv.ConvStream(n_src, 512, 96000)
     rng = np.random.default_rng(1)
     for s in range(n_src):
