@@ -44,6 +44,16 @@ def test_c2_fullsize_parity_with_oracle(c2):
     assert np.mean(rec["nseg"][same] == o["nseg"][same]) >= 0.9999
     assert abs(segs - o["segments"]) <= 1e-4 * o["segments"]
     assert (rec["ear"] > 0).mean() > 0.2                  # a fifth of the rays reach the receiver in this room
+    # the same 1M rays through the bounce-synchronous tracer of large launches (sweep_kernel: every survivor re-binned
+    # by origin cell x direction between sweeps): per-ray records EQUAL to the per-SM-queue tracer's
+    rs = c2.renderer(record_rays=True)
+    rs.set_sweep_min_rays(1)
+    ls, rrs, segs_s, recs = _render(rs)
+    assert rs.last_counters()[2] == 1 + (50 - 8) // 2 and r.last_counters()[2] == 0
+    assert segs_s == segs
+    for key in ("bin", "ear", "nseg", "energy"):
+        assert np.array_equal(recs[key], rec[key]), key
+    assert np.allclose(ls, l, rtol=1e-6, atol=0) and np.allclose(rrs, rr, rtol=1e-6, atol=0)
 
 
 def test_c3_shard_deep_in_the_100m_ray_set(c2):
@@ -89,6 +99,15 @@ def test_c4_million_triangle_hall_parity_and_receiver_moves(c4):
     f.render()
     lf, rf = f.get_ir()
     assert check_parity(f.records(), lf, rf, f.last_segments(), o, case=c4) >= 0.9999
+    # ... and so does the tracer bench.py's C4 leg runs at 10M rays (sweep_kernel, 8 bands: 80 B path states)
+    fs = c4.renderer(record_rays=True)
+    fs.set_sweep_min_rays(1)
+    fs.render()
+    assert fs.last_counters()[2] > 1
+    lfs, rfs = fs.get_ir()
+    for key in ("bin", "ear", "nseg", "energy"):
+        assert np.array_equal(fs.records()[key], f.records()[key]), key
+    assert np.allclose(lfs, lf, rtol=1e-6, atol=0) and np.allclose(rfs, rf, rtol=1e-6, atol=0)
     # interactive receiver moves: re-deposit from the cached paths, against the oracle at the new position
     for k in (1, 2):
         pos, yaw = (30.0 - 1.5 * k, 1.6 + 0.2 * k, 15.0 + 2.0 * k), 30.0 + 40.0 * k
