@@ -106,6 +106,8 @@ SYMBOLS = {
     "arv2_comm_reduce_f32": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int32, _vp]),
     "arv2_shard_range": (None, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "arv2_render_sharded": (C.c_int, [_vp, _vp, C.POINTER(C.c_double)]),
+    "arv2_render_tiles": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
+    "arv2_set_shard_mode": (C.c_int, [_vp, C.c_int32]),
     "arv2_multi_create": (C.c_int, [_vp, _vp, C.POINTER(RendererDesc), _ip, C.c_int32, C.POINTER(_vp)]),
     "arv2_multi_size": (C.c_int32, [_vp]),
     "arv2_multi_ctx": (_vp, [_vp, C.c_int32]),
@@ -462,6 +464,16 @@ class AudioRenderer:
         ms = C.c_double()
         _check(lib().arv2_render_range(self._h, int(ray_begin), int(n_rays), 1 if zero_first else 0, C.byref(ms)))
         return ms.value
+
+    def render_tiles(self, rank, n_ranks, zero_first=True):
+        """One rank's direction tiles of the seeded set into the histogram (no exchange, no finalise)."""
+        ms = C.c_double()
+        _check(lib().arv2_render_tiles(self._h, int(rank), int(n_ranks), 1 if zero_first else 0, C.byref(ms)))
+        return ms.value
+
+    def set_shard_mode(self, mode):
+        """arv2_render_sharded: 1 = direction tiles (default), 0 = contiguous slices of ray ids."""
+        _check(lib().arv2_set_shard_mode(self._h, int(mode)))
 
     def finalize(self):
         _check(lib().arv2_finalize(self._h))

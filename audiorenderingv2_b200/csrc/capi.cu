@@ -103,6 +103,10 @@ struct arv2_ctx {
     // rays: a render with a new seed then costs the key kernel and eight sort kernels, no allocation and no synchronisation
     unsigned* d_sort_keys[2] = {nullptr, nullptr}; int* d_sort_spare = nullptr; unsigned* d_sort_counts = nullptr;
     long long order_cap = 0;
+    // direction-tiled shard of the seeded set (arv2_render_tiles / arv2_render_sharded): the global ids of this rank's rays
+    // in direction order, cached per (seed, ray count, rank, ranks)
+    struct TileShard { int* d_ids = nullptr; long long n = -1, n_total = -1; unsigned long long seed = 0; int rank = -1, n_ranks = -1; } tiles;
+    int shard_mode = 1;               // arv2_render_sharded: 1 = direction tiles (default), 0 = contiguous slices of ray ids
     bool coherent_order = true;
     // pinned staging for the receiver sub-tree
     float4* h_stage = nullptr; size_t stage_f4 = 0;
@@ -330,6 +334,50 @@ int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
     slot->d = vals[res]; vals[res] = nullptr;
     cleanup();
     slot->begin = ray_begin; slot->n = n_rays; slot->seed = c->seed; slot->stamp = ++c->order_clock;
+    return ARV2_OK;
+}
+
+// Direction-tiled shard (trace.cu: direction_select_kernel): this rank's rays of the whole seeded set, sorted by direction
+// key.  One pass over all n_total ray ids (Philox + the emission direction: ~0.2 ms per 10 M rays) and a sort of this rank's
+// share; cached per (seed, n_total, rank, n_ranks).  Synchronises the stream (the count is read back).
+// 2^14 tiles for sets of >= 4 M rays (256+ rays per tile; measured on the 8 shards of 8 M rays in the C2 room: slowest / mean
+// shard time 1.052 / 1.024 / 1.026 / 1.007 / 1.011 with 2^8 / 2^10 / 2^12 / 2^14 / 2^16 tiles), fewer for small sets
+constexpr int kTileBits = 14;
+
+int ensure_tiles(arv2_ctx* c, int rank, int n_ranks)
+{
+    arv2_ctx::TileShard& t = c->tiles;
+    const long long n_total = c->n_rays_total;
+    if (t.d_ids && t.seed == c->seed && t.n_total == n_total && t.rank == rank && t.n_ranks == n_ranks) return ARV2_OK;
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(t.d_ids); t = arv2_ctx::TileShard{};
+    if (n_total <= 0) { t.n = 0; t.n_total = n_total; t.seed = c->seed; t.rank = rank; t.n_ranks = n_ranks; return ARV2_OK; }
+    // the octahedral map is not equal-area: a rank's share of 4096 interleaved tiles stays within a few per cent of 1 / R
+    const long long cap = n_total / n_ranks + n_total / (4 * n_ranks) + 65536;
+    unsigned* keys[2] = {nullptr, nullptr};
+    int* vals[2] = {nullptr, nullptr};
+    unsigned long long* d_count = nullptr;
+    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(d_count); };
+    cudaError_t e = cudaMalloc(&d_count, sizeof(unsigned long long));
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaMalloc(&keys[k], (size_t)cap * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMalloc(&vals[k], (size_t)cap * sizeof(int));
+    }
+    unsigned long long count = 0;
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), c->stream);
+    int tile_bits = kTileBits;
+    while (tile_bits > 6 && (n_total >> tile_bits) < 256) --tile_bits;
+    if (const char* env = getenv("ARV2_TILE_BITS")) tile_bits = std::min(20, std::max(4, atoi(env)));      // tuning aid
+    if (e == cudaSuccess) e = launch_direction_select(c->seed, n_total, rank, n_ranks, tile_bits, keys[0], vals[0], d_count, cap, c->sm_count, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&count, d_count, sizeof count, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess && (long long)count > cap) { cleanup(); set_error("direction tiles: a rank's share exceeds its reservation"); return ARV2_ERR_STATE; }
+    int res = 0;
+    if (e == cudaSuccess) e = radix_sort_pairs(keys, vals, (int)count, 8, 32, &res, c->stream);
+    if (e != cudaSuccess) { cleanup(); set_error(std::string("direction tiles: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
+    t.d_ids = vals[res]; vals[res] = nullptr;
+    cleanup();
+    t.n = (long long)count; t.n_total = n_total; t.seed = c->seed; t.rank = rank; t.n_ranks = n_ranks;
     return ARV2_OK;
 }
 
@@ -740,6 +788,7 @@ int arv2_create(const arv2_scene* scene, const arv2_receiver* receiver, const ar
     auto* c = new arv2_ctx;
     if (getenv("ARV2_NO_SORT")) c->coherent_order = false;   // tuning aids (A/B)
     if (getenv("ARV2_NO_WAVE")) c->wave = false;
+    if (getenv("ARV2_SHARD_CONTIGUOUS")) c->shard_mode = 0;      // A/B: multi-GPU shards are contiguous slices of ray ids
     if (const char* e = getenv("ARV2_SWEEP")) c->sweep_min_rays = atoll(e);      // tuning aid: launches of >= this many rays are traced in sweeps (0 = never)
     if (getenv("ARV2_RR_SERIAL")) c->rr_serial = true;
     c->desc = *desc; c->desc.materials = nullptr; c->desc.n_materials = 0;
@@ -883,7 +932,7 @@ void arv2_destroy(arv2_ctx* c)
     cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_counters);
     if (c->h_ir) cudaFreeHost(c->h_ir);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
-    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_off); cudaFree(c->d_pc_vert); cudaFree(c->d_pc_bits); free_ray_orders(c); cudaFree(c->d_wave_paths); free_sweep(c);
+    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_off); cudaFree(c->d_pc_vert); cudaFree(c->d_pc_bits); free_ray_orders(c); cudaFree(c->tiles.d_ids); cudaFree(c->d_wave_paths); free_sweep(c);
     cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -925,7 +974,9 @@ int arv2_set_sweep_min_rays(arv2_ctx* c, int64_t n) { REQUIRE(c, "null ctx"); c-
 int arv2_set_stream(arv2_ctx* c, void* s) { REQUIRE(c, "null ctx"); c->stream = s ? (cudaStream_t)s : c->own_stream; return ARV2_OK; }
 
 // Everything of a trace up to (not including) a host synchronisation: receiver upload, zeroing, the launch.
-static int enqueue_trace(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t zero_first)
+// `ids` (optional): the launch traces the n_rays rays ids[0 .. n_rays) of the seeded set (global ray ids, the order they
+// are started in) instead of the contiguous range; per-ray records are then indexed by the global id.
+static int enqueue_trace(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t zero_first, const int* ids = nullptr)
 {
     REQUIRE(ray_begin >= 0 && n_rays >= 0 && ray_begin + n_rays <= c->n_rays_total, "ray range outside the seeded set");
     CK(cudaSetDevice(c->device));
@@ -935,12 +986,13 @@ static int enqueue_trace(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t
     if (zero_first) CK(cudaMemsetAsync(c->d_hist, 0, 2 * irn * sizeof(double), c->stream));   // fillZeros, OR/AudioRenderer.cpp:491-492
     CK(cudaMemsetAsync(c->d_counters, 0, kCounters * sizeof(unsigned long long), c->stream));
     if (getenv("ARV2_TAILSTAT")) { CK(cudaMemsetAsync(c->d_counters + 4, 0xFF, 8, c->stream)); CK(cudaMemsetAsync(c->d_counters + 6, 0xFF, 8, c->stream)); CK(cudaMemsetAsync(c->d_counters + 14, 0xFF, 8, c->stream)); }
-    rc = ensure_ray_order(c, ray_begin, n_rays);
+    if (!ids) rc = ensure_ray_order(c, ray_begin, n_rays);
     if (rc != ARV2_OK) return rc;
-    rc = ensure_records(c, n_rays);
+    rc = ensure_records(c, ids ? c->n_rays_total : n_rays);
     if (rc != ARV2_OK) return rc;
     TraceParams p;
     fill_params(c, &p, ray_begin, n_rays);
+    if (ids) p.ray_order = ids;
     const bool sweeps = ensure_sweep(c, n_rays);
     if (!sweeps) rc = ensure_wave(c, &p, n_rays);
     if (rc != ARV2_OK) return rc;
@@ -948,9 +1000,29 @@ static int enqueue_trace(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t
     if (n_rays > 0 && sweeps) CK(launch_trace_sweeps(p, c->sweep, c->bands, 0, c->stream));
     else if (n_rays > 0) CK(launch_trace(p, c->bands, 0, c->sm_count, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
-    c->last_range_rays = n_rays;
+    c->last_range_rays = ids ? c->n_rays_total : n_rays;
     return ARV2_OK;
 }
+
+// One rank's direction tiles of the seeded set, traced into the histogram (no exchange, no finalise).
+static int enqueue_tiles(arv2_ctx* c, int32_t rank, int32_t n_ranks, int32_t zero_first)
+{
+    REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "bad rank");
+    REQUIRE(c->n_rays_total <= 0x7fffffffLL, "direction tiles: at most 2^31 - 1 rays");
+    CK(cudaSetDevice(c->device));
+    const int rc = ensure_tiles(c, rank, n_ranks);
+    if (rc != ARV2_OK) return rc;
+    return enqueue_trace(c, 0, c->tiles.n, zero_first, c->tiles.d_ids);
+}
+
+int arv2_render_tiles(arv2_ctx* c, int32_t rank, int32_t n_ranks, int32_t zero_first, double* ms)
+{
+    REQUIRE(c, "null ctx");
+    const int rc = enqueue_tiles(c, rank, n_ranks, zero_first);
+    return rc != ARV2_OK ? rc : finish_timed(c, ms);
+}
+
+int arv2_set_shard_mode(arv2_ctx* c, int32_t mode) { REQUIRE(c && (mode == 0 || mode == 1), "shard mode is 0 (contiguous) or 1 (direction tiles)"); c->shard_mode = mode; return ARV2_OK; }
 
 int arv2_render_range(arv2_ctx* c, int64_t ray_begin, int64_t n_rays, int32_t zero_first, double* ms)
 {
@@ -1098,7 +1170,8 @@ void arv2_shard_range(int64_t n_rays, int32_t rank, int32_t n_ranks, int64_t* be
     if (count) *count = base + (rank < rem ? 1 : 0);
 }
 
-// One rank's part of a render over R GPUs: this rank's contiguous slice of the seeded ray set, the sum of the fp64
+// One rank's part of a render over R GPUs: this rank's share of the seeded ray set (its direction tiles, or with
+// arv2_set_shard_mode(ctx, 0) its contiguous slice of ray ids), the sum of the fp64
 // histograms over NVLink, the fp32 IR -- enqueued back to back on the context's stream, one host synchronisation.
 int arv2_render_sharded(arv2_ctx* c, arv2_comm* m, double* ms)
 {
@@ -1107,9 +1180,14 @@ int arv2_render_sharded(arv2_ctx* c, arv2_comm* m, double* ms)
     REQUIRE(!c->desc.path_cache, "arv2_render_sharded: not with desc.path_cache");
     const NcclApi* api = nccl_api(nullptr);
     REQUIRE(api, "NCCL not loaded");
-    int64_t begin = 0, count = 0;
-    arv2_shard_range(c->n_rays_total, m->rank, m->n_ranks, &begin, &count);
-    const int rc = enqueue_trace(c, begin, count, 1);
+    int rc;
+    if (c->shard_mode == 1 && m->n_ranks > 1 && c->n_rays_total <= 0x7fffffffLL) {
+        rc = enqueue_tiles(c, m->rank, m->n_ranks, 1);
+    } else {
+        int64_t begin = 0, count = 0;
+        arv2_shard_range(c->n_rays_total, m->rank, m->n_ranks, &begin, &count);
+        rc = enqueue_trace(c, begin, count, 1);
+    }
     if (rc != ARV2_OK) return rc;
     const size_t n = 2 * (size_t)c->bands * c->ir_len;
     if (m->n_ranks > 1) NCK(api->AllReduce(c->d_hist, c->d_hist, n, ncclFloat64, ncclSum, m->comm, c->stream));

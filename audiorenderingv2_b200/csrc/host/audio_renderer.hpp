@@ -143,6 +143,7 @@ public:
     void setMonoOutput(bool v) { check(arv2_set_mono(ctx_, v ? 1 : 0), "setMonoOutput"); }
     void set_seed(unsigned long long s) { check(arv2_set_seed(ctx_, s), "set_seed"); }
     void set_coherent_order(bool on) { check(arv2_set_coherent_order(ctx_, on ? 1 : 0), "set_coherent_order"); }
+    void set_shard_mode(int mode) { check(arv2_set_shard_mode(ctx_, mode), "set_shard_mode"); }
     void set_sweep_min_rays(int64_t n) { check(arv2_set_sweep_min_rays(ctx_, n), "set_sweep_min_rays"); }
     void set_write_ir_to_file_flag(bool v) { write_ir_ = v; }
     void set_write_output_to_file_flag(bool v) { write_output_ = v; }

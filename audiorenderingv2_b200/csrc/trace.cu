@@ -1722,6 +1722,40 @@ __global__ void direction_keys_kernel(unsigned long long seed, long long ray_beg
     vals[i] = (int)i;
 }
 
+// Direction tiles of the seeded ray set (multi-GPU sharding): the top tile_bits bits of a ray's direction key name one
+// of 2^tile_bits cells of the octahedral map; rank r of R traces the rays of the tiles t = r (mod R), so every rank holds
+// rays as dense in direction as the whole set (a contiguous slice of ids is 1/R as dense everywhere).  Grid-stride over
+// the whole set: keys and ids of this rank's rays are appended (warp-aggregated) for the sort that follows.
+__global__ void __launch_bounds__(256) direction_select_kernel(unsigned long long seed, long long n_total, int rank, int n_ranks, int tile_bits,
+                                                               unsigned* __restrict__ keys, int* __restrict__ ids, unsigned long long* __restrict__ counter,
+                                                               long long capacity)
+{
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_round = (n_total + 31) / 32 * 32;          // whole warps take part in every ballot
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool mine = false;
+        unsigned key = 0;
+        if (i < n_total) {
+            const F3 d = emit_direction(seed, (uint64_t)i);
+            const float inv = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z) + 1e-30f);
+            float u = d.x * inv, v = d.y * inv;
+            if (d.z < 0.f) { const float uu = (1.f - fabsf(v)) * copysignf(1.f, u), vv = (1.f - fabsf(u)) * copysignf(1.f, v); u = uu; v = vv; }
+            const unsigned iu = (unsigned)fminf(fmaxf((u * 0.5f + 0.5f) * 65536.f, 0.f), 65535.f);
+            const unsigned iv = (unsigned)fminf(fmaxf((v * 0.5f + 0.5f) * 65536.f, 0.f), 65535.f);
+            key = spread16(iu) | (spread16(iv) << 1);
+            mine = (int)((key >> (32 - tile_bits)) % (unsigned)n_ranks) == rank;
+        }
+        const unsigned m = __ballot_sync(FULL, mine);
+        if (m == 0) continue;
+        unsigned long long base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(counter, (unsigned long long)__popc(m));
+        base = __shfl_sync(FULL, base, __ffs(m) - 1);
+        const long long pos = (long long)base + __popc(m & ((1u << lane) - 1u));
+        if (mine && pos < capacity) { keys[pos] = key; ids[pos] = (int)i; }
+    }
+}
+
 __global__ void finalize_kernel(const double* __restrict__ hist, int n, int mono, float* __restrict__ l, float* __restrict__ r)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1871,6 +1905,16 @@ cudaError_t launch_direction_keys(unsigned long long seed, long long ray_begin, 
 {
     if (n <= 0) return cudaSuccess;
     direction_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(seed, ray_begin, n, keys, vals);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_direction_select(unsigned long long seed, long long n_total, int rank, int n_ranks, int tile_bits, unsigned* keys, int* ids,
+                                    unsigned long long* counter, long long capacity, int sm_count, cudaStream_t stream)
+{
+    if (n_total <= 0) return cudaSuccess;
+    long long grid = (n_total + 255) / 256;
+    if (grid > (long long)sm_count * 16) grid = (long long)sm_count * 16;
+    direction_select_kernel<<<(unsigned)grid, 256, 0, stream>>>(seed, n_total, rank, n_ranks, tile_bits, keys, ids, counter, capacity);
     return cudaGetLastError();
 }
 

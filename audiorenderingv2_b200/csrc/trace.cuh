@@ -109,4 +109,9 @@ cudaError_t launch_finalize(const double* hist, int bands, int ir_len, int mono,
 cudaError_t launch_direction_keys(unsigned long long seed, long long ray_begin, long long n, unsigned* keys, int* vals,
                                   cudaStream_t stream);
 
+// The rays of the seeded set [0, n_total) whose direction tile (top tile_bits bits of the direction key) is = rank (mod
+// n_ranks): their keys and global ids appended to keys / ids (at most `capacity`), *counter (zeroed) = how many there are.
+cudaError_t launch_direction_select(unsigned long long seed, long long n_total, int rank, int n_ranks, int tile_bits, unsigned* keys, int* ids,
+                                    unsigned long long* counter, long long capacity, int sm_count, cudaStream_t stream);
+
 } // namespace arv2

@@ -214,7 +214,10 @@ def workload_config(n_gpus):
     return {"workload": desc,
             "rays_per_gpu": RAYS[0] * RAYS[1] * RAYS[2], "total_rays": RAYS[0] * RAYS[1] * RAYS[2] * n_gpus,
             "max_bounces": MAX_BOUNCES, "sample_rate": FS, "ir_seconds": IR_SECONDS, "bands": BANDS,
-            "parallelism": f"ray-range sharding x{n_gpus}, ncclAllReduce of the fp64 IR histogram inside libarv2 (arv2_render_sharded)",
+            "parallelism": (f"ray sharding x{n_gpus}: rank r traces the direction tiles t = r (mod {n_gpus}) of the one seeded ray set "
+                            "(arv2_set_shard_mode(0) / ARV2_SHARD_CONTIGUOUS=1: contiguous slices of ray ids), ncclAllReduce of the fp64 IR "
+                            "histogram inside libarv2 (arv2_render_sharded)") if n_gpus > 1 else
+                           "1 GPU (arv2_render_sharded with a 1-rank communicator: no exchange)",
             "l2": "flushed between timed steps (512 MiB write)"}
 
 
@@ -344,7 +347,7 @@ def main():
     scene = arv.Scene.from_triangles(tv, tm, names)
     receiver = arv.Receiver.from_triangles(*recv)
     t_build = time.perf_counter()
-    # the seeded ray set has total_rays rays; rank r traces arv2_shard_range(total_rays, r, world) = per_gpu rays
+    # the seeded ray set has total_rays rays; rank r traces its share of them (its direction tiles: ~per_gpu rays)
     r = job.renderer(scene, receiver, mats, total_rays)
     t_build = time.perf_counter() - t_build
 

@@ -204,7 +204,16 @@ void arv2_comm_destroy(arv2_comm* comm);
 int arv2_comm_reduce_f32(arv2_comm* comm, float* d_buf, size_t count, int32_t root, void* cuda_stream);
 /* The contiguous slice [begin, begin+count) of an n_rays set that `rank` of n_ranks traces. */
 void arv2_shard_range(int64_t n_rays, int32_t rank, int32_t n_ranks, int64_t* begin, int64_t* count);
-/* AudioRenderer::render on n_ranks GPUs: trace this rank's slice of the seeded ray set, ncclAllReduce
+/* Direction tiles, the default shards of arv2_render_sharded: the octahedral map of the emission directions is cut into
+ * up to 16384 tiles and rank r takes the rays of the tiles t = r (mod n_ranks) -- every rank then holds rays as dense in direction
+ * as the whole set, which keeps the warps' bundles as coherent as on one GPU (a contiguous slice of ray ids is 1/n_ranks as
+ * dense everywhere).  Same seeded set, same per-ray results; the union over the ranks is the whole set.
+ * arv2_render_tiles traces one rank's tiles into the fp64 histogram without exchange or finalise (like arv2_render_range;
+ * per-ray records are indexed by the global ray id).  arv2_set_shard_mode: 1 = direction tiles (default), 0 = contiguous
+ * slices (arv2_shard_range). */
+int arv2_render_tiles(arv2_ctx* ctx, int32_t rank, int32_t n_ranks, int32_t zero_first, double* ms);
+int arv2_set_shard_mode(arv2_ctx* ctx, int32_t mode);
+/* AudioRenderer::render on n_ranks GPUs: trace this rank's share of the seeded ray set, ncclAllReduce
  * the fp64 histogram and finalise on the context's stream, one host synchronisation at the end.
  * Every rank ends up with the full IR; it equals the single-GPU arv2_render to fp32 rounding.
  * Collective: all ranks call it with contexts created from the same scene, parameters and seed. */

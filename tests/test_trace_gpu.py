@@ -120,6 +120,32 @@ def test_sharded_ranges_equal_full(golden_scenes, golden_receiver):
     assert np.allclose(l2, l, rtol=1e-6, atol=0) and np.allclose(rr2, rr, rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("n_ranks", [2, 3, 8])
+def test_direction_tile_shards_cover_the_set_once(golden_scenes, golden_receiver, n_ranks):
+    """The default shards of arv2_render_sharded: rank r traces the rays whose emission direction falls into the tiles
+    t = r (mod R) of the octahedral map.  All R shards, rendered here one after the other into one histogram, must be
+    the seeded set exactly once: per-ray records (indexed by global ray id), segment total and IR equal the full render,
+    which equals the oracle.  Also through sweep_kernel."""
+    case = c1(golden_scenes, golden_receiver, rays=(100, 100, 2), hrtf=0.9)
+    r, rec, l, rr, segs, _ = run(case)
+    assert check_parity(rec, l, rr, segs, case.oracle_run()) == 1.0
+    for sweeps in (False, True):
+        r2 = case.renderer(record_rays=True)
+        r2.set_sweep_min_rays(1 if sweeps else 0)
+        tot, sizes = 0, []
+        for k in range(n_ranks):
+            r2.render_tiles(k, n_ranks, zero_first=(k == 0))
+            tot += r2.last_segments()
+            sizes.append(r2.last_segments())
+        r2.finalize()
+        l2, rr2 = r2.get_ir()
+        rec2 = r2.records()
+        assert tot == segs and min(sizes) > 0.5 * segs / n_ranks and max(sizes) < 1.5 * segs / n_ranks
+        for k in ("bin", "ear", "nseg", "energy"):
+            assert np.array_equal(rec2[k], rec[k]), k
+        assert np.allclose(l2, l, rtol=1e-6, atol=0) and np.allclose(rr2, rr, rtol=1e-6, atol=0)
+
+
 @pytest.mark.parametrize("env", [{}, {"ARV2_RR_SERIAL": "1"}], ids=["mask+walk", "serial-scan"])
 def test_path_cache_rerender_equals_render(golden_scenes, golden_receiver, monkeypatch, env):
     """Receiver moves re-deposit from cached receiver-independent paths; the result must equal a fresh full trace ray
