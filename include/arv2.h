@@ -309,7 +309,10 @@ int arv2_stream_process_device(arv2_stream* s, const float* d_in, float* d_out, 
 /* n_blocks consecutive blocks in one call (an RtAudio callback of the reference carries 4096 frames = 8 blocks of
  * 512, OR/main.cpp:99-135): d_in = float[n_blocks][n_sources][block], d_out = float[n_blocks][n_sources][2][block],
  * device-resident, enqueued on `cuda_stream` without syncing.  The steps are launched back to back and overlap on
- * the device (programmatic dependent launch); the result is the one n_blocks single-block calls give. */
+ * the device (programmatic dependent launch; blocks 1.. start their forward FFT before block 0 has finished, so all of
+ * d_in must have been produced by work enqueued on `cuda_stream` BEFORE this call, which stream order gives for free);
+ * the result is the one n_blocks single-block calls give.  Streams of <= 4 sources run 16 CTAs per source, larger ones 8
+ * (the summation order over the IR partitions, hence the last bits of the output, depends on it; fixed per stream). */
 int arv2_stream_process_device_blocks(arv2_stream* s, const float* d_in, float* d_out, int32_t n_blocks, void* cuda_stream);
 /* Host buffers, up to 16 consecutive blocks per call (one RtAudio callback): in = float[n_blocks][n_sources][block];
  * out (may be NULL) = float[n_blocks][n_sources][2][block]; mix (may be NULL) = float[n_blocks][2][block], the stereo
