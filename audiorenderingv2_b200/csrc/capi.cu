@@ -106,6 +106,9 @@ struct arv2_ctx {
     // direction-tiled shard of the seeded set (arv2_render_tiles / arv2_render_sharded): the global ids of this rank's rays
     // in direction order, cached per (seed, ray count, rank, ranks)
     struct TileShard { int* d_ids = nullptr; long long n = -1, n_total = -1; unsigned long long seed = 0; int rank = -1, n_ranks = -1; } tiles;
+    // workspace of the selection + sort (three id buffers rotate with tiles.d_ids), kept for shards of up to kOrderKeep rays
+    struct TileWork { unsigned* keys[2] = {nullptr, nullptr}; int* vals[2] = {nullptr, nullptr}; unsigned* counts = nullptr;
+                      unsigned long long* d_count = nullptr; long long cap = 0, ids_cap = 0; } tile_ws;
     int shard_mode = 1;               // arv2_render_sharded: 1 = direction tiles (default), 0 = contiguous slices of ray ids
     bool coherent_order = true;
     // pinned staging for the receiver sub-tree
@@ -344,40 +347,59 @@ int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
 // shard time 1.052 / 1.024 / 1.026 / 1.007 / 1.011 with 2^8 / 2^10 / 2^12 / 2^14 / 2^16 tiles), fewer for small sets
 constexpr int kTileBits = 14;
 
+void free_tiles(arv2_ctx* c)
+{
+    arv2_ctx::TileWork& w = c->tile_ws;
+    cudaFree(w.keys[0]); cudaFree(w.keys[1]); cudaFree(w.vals[0]); cudaFree(w.vals[1]); cudaFree(w.counts); cudaFree(w.d_count);
+    w = arv2_ctx::TileWork{};
+    cudaFree(c->tiles.d_ids);
+    c->tiles = arv2_ctx::TileShard{};
+}
+
 int ensure_tiles(arv2_ctx* c, int rank, int n_ranks)
 {
     arv2_ctx::TileShard& t = c->tiles;
+    arv2_ctx::TileWork& w = c->tile_ws;
     const long long n_total = c->n_rays_total;
     if (t.d_ids && t.seed == c->seed && t.n_total == n_total && t.rank == rank && t.n_ranks == n_ranks) return ARV2_OK;
-    CK(cudaStreamSynchronize(c->stream));
-    cudaFree(t.d_ids); t = arv2_ctx::TileShard{};
-    if (n_total <= 0) { t.n = 0; t.n_total = n_total; t.seed = c->seed; t.rank = rank; t.n_ranks = n_ranks; return ARV2_OK; }
-    // the octahedral map is not equal-area: a rank's share of 4096 interleaved tiles stays within a few per cent of 1 / R
+    CK(cudaStreamSynchronize(c->stream));                   // (the previous shard's ids may still be read by a launch in flight)
+    t.n = -1;
+    // the octahedral map is not equal-area: a rank's share of the interleaved tiles stays within a few per cent of 1 / R
     const long long cap = n_total / n_ranks + n_total / (4 * n_ranks) + 65536;
-    unsigned* keys[2] = {nullptr, nullptr};
-    int* vals[2] = {nullptr, nullptr};
-    unsigned long long* d_count = nullptr;
-    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(d_count); };
-    cudaError_t e = cudaMalloc(&d_count, sizeof(unsigned long long));
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-        e = cudaMalloc(&keys[k], (size_t)cap * sizeof(unsigned));
-        if (e == cudaSuccess) e = cudaMalloc(&vals[k], (size_t)cap * sizeof(int));
+    if (cap > w.cap || w.ids_cap < cap) {
+        free_tiles(c);
+        const size_t bytes = (size_t)cap * 4;
+        cudaError_t e = cudaMalloc(&w.d_count, sizeof(unsigned long long));
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+            e = cudaMalloc(&w.keys[k], bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&w.vals[k], bytes);
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&t.d_ids, bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&w.counts, radix_sort_scratch_bytes((int)cap));
+        if (e != cudaSuccess) { free_tiles(c); cudaGetLastError(); set_error(std::string("direction tiles: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
+        w.cap = cap; w.ids_cap = cap;
     }
     unsigned long long count = 0;
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), c->stream);
     int tile_bits = kTileBits;
     while (tile_bits > 6 && (n_total >> tile_bits) < 256) --tile_bits;
     if (const char* env = getenv("ARV2_TILE_BITS")) tile_bits = std::min(20, std::max(4, atoi(env)));      // tuning aid
-    if (e == cudaSuccess) e = launch_direction_select(c->seed, n_total, rank, n_ranks, tile_bits, keys[0], vals[0], d_count, cap, c->sm_count, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&count, d_count, sizeof count, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaMemsetAsync(w.d_count, 0, sizeof(unsigned long long), c->stream);
+    if (e == cudaSuccess) e = launch_direction_select(c->seed, n_total, rank, n_ranks, tile_bits, w.keys[0], w.vals[0], w.d_count, w.cap, c->sm_count, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&count, w.d_count, sizeof count, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e == cudaSuccess && (long long)count > cap) { cleanup(); set_error("direction tiles: a rank's share exceeds its reservation"); return ARV2_ERR_STATE; }
+    if (e == cudaSuccess && (long long)count > w.cap) { set_error("direction tiles: a rank's share exceeds its reservation"); return ARV2_ERR_STATE; }
     int res = 0;
-    if (e == cudaSuccess) e = radix_sort_pairs(keys, vals, (int)count, 8, 32, &res, c->stream);
-    if (e != cudaSuccess) { cleanup(); set_error(std::string("direction tiles: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
-    t.d_ids = vals[res]; vals[res] = nullptr;
-    cleanup();
+    if (e == cudaSuccess) e = radix_sort_pairs(w.keys, w.vals, (int)count, 8, 32, &res, c->stream, w.counts);
+    if (e != cudaSuccess) { set_error(std::string("direction tiles: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
+    std::swap(t.d_ids, w.vals[res]);                         // the sorted ids become the shard, its old buffer joins the workspace
     t.n = (long long)count; t.n_total = n_total; t.seed = c->seed; t.rank = rank; t.n_ranks = n_ranks;
+    if (w.cap > kOrderKeep) {                                // very large shards: only the ids are kept
+        int* keep = t.d_ids; t.d_ids = nullptr;
+        const arv2_ctx::TileShard meta = t;
+        CK(cudaStreamSynchronize(c->stream));
+        free_tiles(c);
+        c->tiles = meta; c->tiles.d_ids = keep;
+    }
     return ARV2_OK;
 }
 
@@ -932,7 +954,7 @@ void arv2_destroy(arv2_ctx* c)
     cudaFree(c->d_hist); cudaFree(c->d_ir_l); cudaFree(c->d_counters);
     if (c->h_ir) cudaFreeHost(c->h_ir);
     cudaFree(c->d_rec_bin); cudaFree(c->d_rec_ear); cudaFree(c->d_rec_nseg); cudaFree(c->d_rec_energy);
-    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_off); cudaFree(c->d_pc_vert); cudaFree(c->d_pc_bits); free_ray_orders(c); cudaFree(c->tiles.d_ids); cudaFree(c->d_wave_paths); free_sweep(c);
+    cudaFree(c->d_pc_seg); cudaFree(c->d_pc_energy); cudaFree(c->d_pc_off); cudaFree(c->d_pc_vert); cudaFree(c->d_pc_bits); free_ray_orders(c); free_tiles(c); cudaFree(c->d_wave_paths); free_sweep(c);
     cudaFree(c->conv.d_tw); cudaFree(c->conv.d_x); cudaFree(c->conv.d_out); cudaFree(c->conv.d_X); cudaFree(c->conv.d_H);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_counters) cudaFreeHost(c->h_counters);
