@@ -101,7 +101,7 @@ struct arv2_ctx {
     unsigned long long order_clock = 0;
     // workspace of the sort, kept (with the two order buffers, all of order_cap entries) for launches of up to kOrderKeep
     // rays: a render with a new seed then costs the key kernel and eight sort kernels, no allocation and no synchronisation
-    unsigned* d_sort_keys[2] = {nullptr, nullptr}; int* d_sort_spare = nullptr; unsigned* d_sort_counts = nullptr;
+    unsigned* d_sort_keys[2] = {nullptr, nullptr}; unsigned* d_sort_counts = nullptr;
     long long order_cap = 0;
     // direction-tiled shard of the seeded set (arv2_render_tiles / arv2_render_sharded): the global ids of this rank's rays
     // in direction order, cached per (seed, ray count, rank, ranks)
@@ -281,8 +281,8 @@ constexpr long long kOrderKeep = 32LL << 20;
 void free_ray_orders(arv2_ctx* c)
 {
     for (auto& o : c->order) { cudaFree(o.d); o = arv2_ctx::RayOrder{}; }
-    cudaFree(c->d_sort_keys[0]); cudaFree(c->d_sort_keys[1]); cudaFree(c->d_sort_spare); cudaFree(c->d_sort_counts);
-    c->d_sort_keys[0] = c->d_sort_keys[1] = nullptr; c->d_sort_spare = nullptr; c->d_sort_counts = nullptr; c->order_cap = 0;
+    cudaFree(c->d_sort_keys[0]); cudaFree(c->d_sort_keys[1]); cudaFree(c->d_sort_counts);
+    c->d_sort_keys[0] = c->d_sort_keys[1] = nullptr; c->d_sort_counts = nullptr; c->order_cap = 0;
 }
 
 int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
@@ -293,7 +293,8 @@ int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
         if (o.d && o.begin == ray_begin && o.n == n_rays && o.seed == c->seed) { o.stamp = ++c->order_clock; return ARV2_OK; }
         if (o.stamp < slot->stamp) slot = &o;                     // least recently used
     }
-    if (n_rays <= kOrderKeep) {
+    static const bool radix = getenv("ARV2_ORDER_RADIX") != nullptr;      // A/B: the four-pass stable radix sort of r05-r08
+    if (n_rays <= kOrderKeep && !radix) {
         // persistent buffers: grown (and both cached orders dropped) when a launch is larger than any before
         if (n_rays > c->order_cap) {
             CK(cudaStreamSynchronize(c->stream));
@@ -302,24 +303,23 @@ int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
             const size_t bytes = (size_t)n_rays * 4;
             cudaError_t e = cudaMalloc(&c->d_sort_keys[0], bytes);
             if (e == cudaSuccess) e = cudaMalloc(&c->d_sort_keys[1], bytes);
-            if (e == cudaSuccess) e = cudaMalloc(&c->d_sort_spare, bytes);
             if (e == cudaSuccess) e = cudaMalloc(&c->order[0].d, bytes);
             if (e == cudaSuccess) e = cudaMalloc(&c->order[1].d, bytes);
-            if (e == cudaSuccess) e = cudaMalloc(&c->d_sort_counts, radix_sort_scratch_bytes((int)n_rays));
+            if (e == cudaSuccess) e = cudaMalloc(&c->d_sort_counts, kCountingOrderScratch * sizeof(unsigned));      // bins + tile sums
             if (e != cudaSuccess) { free_ray_orders(c); cudaGetLastError(); set_error(std::string("ray order: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
             c->order_cap = n_rays;
         }
         slot->n = -1;
-        int* vals[2] = {slot->d, c->d_sort_spare};
-        int res = 0;
-        cudaError_t e = launch_direction_keys(c->seed, ray_begin, n_rays, c->d_sort_keys[0], vals[0], c->stream);
-        if (e == cudaSuccess) e = radix_sort_pairs(c->d_sort_keys, vals, (int)n_rays, 8, 32, &res, c->stream, c->d_sort_counts);
+        // direction keys, then a counting sort on their top bits (keys -> bins in place, ranks in the second key buffer)
+        const int bits = counting_order_bits(n_rays);
+        cudaError_t e = launch_direction_keys(c->seed, ray_begin, n_rays, c->d_sort_keys[0], nullptr, c->stream);
+        if (e == cudaSuccess) e = launch_counting_order(c->d_sort_keys[0], nullptr, n_rays, bits, c->d_sort_keys[1], c->d_sort_counts, c->d_sort_counts + ((size_t)1 << kCountingOrderMaxBits),
+                                                        slot->d, c->stream);
         if (e != cudaSuccess) { set_error(std::string("ray order: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
-        if (res == 1) std::swap(slot->d, c->d_sort_spare);
         slot->begin = ray_begin; slot->n = n_rays; slot->seed = c->seed; slot->stamp = ++c->order_clock;
         return ARV2_OK;
     }
-    // very large launches: transient workspace (2 x 8 B per ray), only the order itself is kept
+    // very large launches (and the radix A/B): transient workspace (2 x 8 B per ray), only the order itself is kept
     if (c->order_cap > 0) { CK(cudaStreamSynchronize(c->stream)); free_ray_orders(c); slot = &c->order[0]; }
     cudaFree(slot->d); slot->d = nullptr; slot->n = -1;
     unsigned* keys[2] = {nullptr, nullptr};
@@ -332,7 +332,15 @@ int ensure_ray_order(arv2_ctx* c, long long ray_begin, long long n_rays)
     }
     int res = 0;
     if (e == cudaSuccess) e = launch_direction_keys(c->seed, ray_begin, n_rays, keys[0], vals[0], c->stream);
-    if (e == cudaSuccess) e = radix_sort_pairs(keys, vals, (int)n_rays, 8, 32, &res, c->stream);
+    if (e == cudaSuccess && radix) e = radix_sort_pairs(keys, vals, (int)n_rays, 8, 32, &res, c->stream);
+    else if (e == cudaSuccess) {
+        unsigned* bins = nullptr;
+        e = cudaMalloc(&bins, kCountingOrderScratch * sizeof(unsigned));
+        if (e == cudaSuccess) e = launch_counting_order(keys[0], nullptr, n_rays, counting_order_bits(n_rays), keys[1], bins, bins + ((size_t)1 << kCountingOrderMaxBits), vals[1], c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(bins);
+        res = 1;
+    }
     if (e != cudaSuccess) { cleanup(); set_error(std::string("ray order: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
     slot->d = vals[res]; vals[res] = nullptr;
     cleanup();
@@ -375,7 +383,7 @@ int ensure_tiles(arv2_ctx* c, int rank, int n_ranks)
             if (e == cudaSuccess) e = cudaMalloc(&w.vals[k], bytes);
         }
         if (e == cudaSuccess) e = cudaMalloc(&t.d_ids, bytes);
-        if (e == cudaSuccess) e = cudaMalloc(&w.counts, radix_sort_scratch_bytes((int)cap));
+        if (e == cudaSuccess) e = cudaMalloc(&w.counts, kCountingOrderScratch * sizeof(unsigned));      // bins + tile sums of the counting sort
         if (e != cudaSuccess) { free_tiles(c); cudaGetLastError(); set_error(std::string("direction tiles: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
         w.cap = cap; w.ids_cap = cap;
     }
@@ -388,10 +396,10 @@ int ensure_tiles(arv2_ctx* c, int rank, int n_ranks)
     if (e == cudaSuccess) e = cudaMemcpyAsync(&count, w.d_count, sizeof count, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess && (long long)count > w.cap) { set_error("direction tiles: a rank's share exceeds its reservation"); return ARV2_ERR_STATE; }
-    int res = 0;
-    if (e == cudaSuccess) e = radix_sort_pairs(w.keys, w.vals, (int)count, 8, 32, &res, c->stream, w.counts);
+    // this rank's ids in direction order: counting sort on the top bits of their keys (ranks in the second key buffer)
+    if (e == cudaSuccess) e = launch_counting_order(w.keys[0], w.vals[0], (long long)count, counting_order_bits((long long)count), w.keys[1], w.counts,
+                                                    w.counts + ((size_t)1 << kCountingOrderMaxBits), t.d_ids, c->stream);
     if (e != cudaSuccess) { set_error(std::string("direction tiles: ") + cudaGetErrorString(e)); return ARV2_ERR_CUDA; }
-    std::swap(t.d_ids, w.vals[res]);                         // the sorted ids become the shard, its old buffer joins the workspace
     t.n = (long long)count; t.n_total = n_total; t.seed = c->seed; t.rank = rank; t.n_ranks = n_ranks;
     if (w.cap > kOrderKeep) {                                // very large shards: only the ids are kept
         int* keep = t.d_ids; t.d_ids = nullptr;

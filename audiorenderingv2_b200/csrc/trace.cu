@@ -1719,7 +1719,7 @@ __global__ void direction_keys_kernel(unsigned long long seed, long long ray_beg
     const unsigned iu = (unsigned)fminf(fmaxf((u * 0.5f + 0.5f) * 65536.f, 0.f), 65535.f);
     const unsigned iv = (unsigned)fminf(fmaxf((v * 0.5f + 0.5f) * 65536.f, 0.f), 65535.f);
     keys[i] = spread16(iu) | (spread16(iv) << 1);
-    vals[i] = (int)i;
+    if (vals) vals[i] = (int)i;
 }
 
 // Direction tiles of the seeded ray set (multi-GPU sharding): the top tile_bits bits of a ray's direction key name one
@@ -1754,6 +1754,28 @@ __global__ void __launch_bounds__(256) direction_select_kernel(unsigned long lon
         const long long pos = (long long)base + __popc(m & ((1u << lane) - 1u));
         if (mine && pos < capacity) { keys[pos] = key; ids[pos] = (int)i; }
     }
+}
+
+// Counting sort of (key, value) pairs on the top `bits` bits of 32-bit direction keys, in the three steps the sweeps use:
+// a pass that takes every key's bin and its arrival rank in the bin (one atomic per key), the scan of the bins
+// (sweep_tile_sums_kernel + sweep_scan_kernel), a scatter.  Within a bin the order is the arrival order -- a bin is
+// 2^-bits of the sphere of directions, far below what a warp's bundle resolves -- so this replaces the four-pass stable
+// radix sort of the ray order (410 us per 1 M rays) at a tenth of its cost.
+__global__ void __launch_bounds__(256) order_bins_kernel(unsigned* __restrict__ keys, long long n, int bits, unsigned* __restrict__ rank, unsigned* __restrict__ bins)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const unsigned b = keys[i] >> (32 - bits);
+    keys[i] = b;
+    rank[i] = atomicAdd(bins + b, 1u);
+}
+
+__global__ void __launch_bounds__(256) order_scatter_kernel(const unsigned* __restrict__ key, const unsigned* __restrict__ rank, const unsigned* __restrict__ bins,
+                                                            const int* __restrict__ vals, long long n, int* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    out[__ldg(bins + key[i]) + rank[i]] = vals ? vals[i] : (int)i;
 }
 
 __global__ void finalize_kernel(const double* __restrict__ hist, int n, int mono, float* __restrict__ l, float* __restrict__ r)
@@ -1915,6 +1937,30 @@ cudaError_t launch_direction_select(unsigned long long seed, long long n_total, 
     long long grid = (n_total + 255) / 256;
     if (grid > (long long)sm_count * 16) grid = (long long)sm_count * 16;
     direction_select_kernel<<<(unsigned)grid, 256, 0, stream>>>(seed, n_total, rank, n_ranks, tile_bits, keys, ids, counter, capacity);
+    return cudaGetLastError();
+}
+
+int counting_order_bits(long long n)
+{
+    // four bins per key up to 1 M keys, at most 2^22 bins (8 keys per bin cost 1.1 % of the trace rate at 1 M rays, one per
+    // bin 0.45 %: the order inside a bin is the arrival order), 4096 bins at least (the scan works on tiles of 4096)
+    int bits = 12;
+    while (bits < kCountingOrderMaxBits && (n >> bits) > 0) ++bits;
+    return bits + 2 > kCountingOrderMaxBits ? kCountingOrderMaxBits : bits + 2;
+}
+
+cudaError_t launch_counting_order(unsigned* keys, const int* vals, long long n, int bits, unsigned* rank, unsigned* bins, unsigned* tile_sums, int* out,
+                                  cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    const int n_bins = 1 << bits;
+    cudaError_t e = cudaMemsetAsync(bins, 0, (size_t)n_bins * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    order_bins_kernel<<<grid, 256, 0, stream>>>(keys, n, bits, rank, bins);
+    sweep_tile_sums_kernel<<<n_bins / 4096, 1024, 0, stream>>>(bins, tile_sums);
+    sweep_scan_kernel<<<n_bins / 4096, 1024, 0, stream>>>(bins, tile_sums);
+    order_scatter_kernel<<<grid, 256, 0, stream>>>(keys, rank, bins, vals, n, out);
     return cudaGetLastError();
 }
 

@@ -109,6 +109,13 @@ cudaError_t launch_finalize(const double* hist, int bands, int ir_len, int mono,
 cudaError_t launch_direction_keys(unsigned long long seed, long long ray_begin, long long n, unsigned* keys, int* vals,
                                   cudaStream_t stream);
 
+// out = vals (or 0 .. n-1) ordered by the top `bits` bits of keys (counting sort, arrival order inside a bin); keys are
+// overwritten with the bins; rank: n entries, bins: 2^bits entries, tile_sums: 2^bits / 4096 entries.
+constexpr int kCountingOrderMaxBits = 22;
+constexpr size_t kCountingOrderScratch = ((size_t)1 << kCountingOrderMaxBits) + 1024;      // unsigned entries: bins, then tile sums
+int counting_order_bits(long long n);
+cudaError_t launch_counting_order(unsigned* keys, const int* vals, long long n, int bits, unsigned* rank, unsigned* bins, unsigned* tile_sums, int* out,
+                                  cudaStream_t stream);
 // The rays of the seeded set [0, n_total) whose direction tile (top tile_bits bits of the direction key) is = rank (mod
 // n_ranks): their keys and global ids appended to keys / ids (at most `capacity`), *counter (zeroed) = how many there are.
 cudaError_t launch_direction_select(unsigned long long seed, long long n_total, int rank, int n_ranks, int tile_bits, unsigned* keys, int* ids,
