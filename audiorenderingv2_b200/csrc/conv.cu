@@ -537,7 +537,8 @@ __global__ void __launch_bounds__(kConvStepThreads) stream_step_kernel(const Con
     auto forward_fft = [&]() {
         const float* in = a.in + (size_t)src * block;
         CT_MARK(0);
-        for (int t = threadIdx.x; t < N; t += blockDim.x) bufa[t] = make_float2(t < block ? in[t] : 0.f, 0.f);
+        // (read through L2: before the wait nothing has invalidated this SM's L1, which may hold the block of an older call)
+        for (int t = threadIdx.x; t < N; t += blockDim.x) bufa[t] = make_float2(t < block ? __ldcg(in + t) : 0.f, 0.f);
         __syncthreads();
         CT_MARK(1);
         F = fft_smem(bufa, bufb, N, stw, false);
