@@ -312,3 +312,26 @@ def test_nccl_binds_at_run_time_and_needs_a_device():
     if not torch.cuda.is_available():
         with pytest.raises(arv.Arv2Error, match=r"error -3"):
             arv.Comm(0, 0, 1, uid)
+
+
+def test_direction_tile_rule_partitions_the_sphere_evenly():
+    """The default multi-GPU shard rule (host-side statement in sharding.direction_tile_rank of direction_select_kernel):
+    every direction belongs to exactly one rank, the ranks' shares of a uniform ray set are equal to a few per cent, and
+    a rank's rays are spread over the whole sphere (every octant), not one patch of it."""
+    from audiorenderingv2_b200 import sharding
+    rng = np.random.default_rng(3)
+    d = rng.standard_normal((200_000, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    assert sharding.direction_tile_bits(8_000_000) == 14 and sharding.direction_tile_bits(100_000) == 8 and sharding.direction_tile_bits(100) == 6
+    for world in (2, 3, 8):
+        r = sharding.direction_tile_rank(d, world, 14)
+        assert r.min() == 0 and r.max() == world - 1
+        share = np.bincount(r, minlength=world) / len(d)
+        assert np.all(np.abs(share * world - 1.0) < 0.05)
+        octant = (d[:, 0] > 0).astype(int) | ((d[:, 1] > 0).astype(int) << 1) | ((d[:, 2] > 0).astype(int) << 2)
+        for k in range(world):
+            assert len(np.unique(octant[r == k])) == 8
+    # neighbouring directions share a tile: the point of the rule is that a rank's rays stay dense in direction
+    base = np.array([[0.3, 0.5, 0.81]], np.float32)
+    near = base + 1e-4 * rng.standard_normal((1000, 3)).astype(np.float32)
+    assert np.mean(sharding.direction_tile_rank(near, 8, 14) == sharding.direction_tile_rank(base, 8, 14)[0]) > 0.95

@@ -141,6 +141,15 @@ def test_direction_tile_shards_cover_the_set_once(golden_scenes, golden_receiver
         l2, rr2 = r2.get_ir()
         rec2 = r2.records()
         assert tot == segs and min(sizes) > 0.5 * segs / n_ranks and max(sizes) < 1.5 * segs / n_ranks
+        if not sweeps:
+            # which rays a rank takes follows the documented rule (host-side statement: sharding.direction_tile_rank)
+            import oracle
+            from audiorenderingv2_b200 import sharding
+            n = len(rec["nseg"])
+            dirs = np.stack([oracle.ray_direction(case.seed, i) for i in range(n)])
+            owner = sharding.direction_tile_rank(dirs, n_ranks, sharding.direction_tile_bits(n))
+            for k in range(n_ranks):
+                assert abs(int(rec["nseg"][owner == k].sum()) - sizes[k]) <= 0.002 * segs
         for k in ("bin", "ear", "nseg", "energy"):
             assert np.array_equal(rec2[k], rec[k]), k
         assert np.allclose(l2, l, rtol=1e-6, atol=0) and np.allclose(rr2, rr, rtol=1e-6, atol=0)
