@@ -459,8 +459,6 @@ int ensure_wave(arv2_ctx* c, TraceParams* p, long long n_rays)
         c->wave_slots = need;
     }
     p->wave_paths = c->d_wave_paths; p->wave_cap = cap; p->wave_queues = nq; p->wave_segments = per;
-    p->wave_chunk = 32;
-    if (const char* e = getenv("ARV2_WAVE_CHUNK")) p->wave_chunk = atoi(e) >= 32 ? atoi(e) / 32 * 32 : 32;      // tuning aid
     return ARV2_OK;
 }
 

@@ -719,10 +719,9 @@ template <int NB, int MODE>
 __global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams p)
 {
     __shared__ unsigned q_tail[kWaveQueues], q_pub[kWaveQueues], q_head[kWaveQueues];
-    __shared__ int sh_alive, sh_pool_done, sh_lock;
-    __shared__ long long sh_chunk_next, sh_chunk_end;
+    __shared__ int sh_alive, sh_pool_done;
     if (threadIdx.x < kWaveQueues) { q_tail[threadIdx.x] = 0; q_pub[threadIdx.x] = 0; q_head[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) { sh_alive = 0; sh_pool_done = 0; sh_lock = 0; sh_chunk_next = 0; sh_chunk_end = 0; }
+    if (threadIdx.x == 0) { sh_alive = 0; sh_pool_done = 0; }
     __syncthreads();
     volatile unsigned* const v_pub = q_pub;
     volatile unsigned* const v_head = q_head;
@@ -755,31 +754,12 @@ __global__ void __launch_bounds__(kWaveThreads, 1) wave_kernel(const TraceParams
         unsigned long long pos = 0;
         if (lane == 0 && !*v_done && *v_alive + 32 <= cap) {
             if (atomicAdd(&sh_alive, 32) + 32 <= cap) {
-                long long b, take;
-                if (p.wave_chunk > 32) {
-                    // the SM takes the unstarted rays in chunks of wave_chunk consecutive rays of the direction order and
-                    // hands them to its warps 32 at a time: the 32 warps of an SM then walk neighbouring bundles (and
-                    // the same nodes, through the same L1) instead of every 148th batch of the order
-                    volatile long long* const c_next = &sh_chunk_next;
-                    volatile long long* const c_end = &sh_chunk_end;
-                    while (atomicCAS(&sh_lock, 0, 1) != 0) { }
-                    __threadfence_block();
-                    if (*c_next >= *c_end) {
-                        const long long g = (long long)atomicAdd(p.counters, (unsigned long long)p.wave_chunk);
-                        *c_next = g;
-                        *c_end = g + p.wave_chunk < p.n_rays ? g + p.wave_chunk : p.n_rays;
-                    }
-                    b = *c_next;
-                    take = *c_end - b;
-                    take = take < 0 ? 0 : (take > 32 ? 32 : take);
-                    *c_next = b + 32;
-                    __threadfence_block();
-                    atomicExch(&sh_lock, 0);
-                } else {
-                    b = (long long)atomicAdd(p.counters, 32ull);
-                    take = p.n_rays - b;
-                    take = take < 0 ? 0 : (take > 32 ? 32 : take);
-                }
+                // (taking the unstarted rays per SM in chunks of consecutive rays of the direction order, so that an SM's warps
+                // walk neighbouring bundles, was measured and lost: path lengths depend on the direction and the SMs that drew
+                // long-lived chunks finish late -- profiles/r09_trace_sweeps.md)
+                const long long b = (long long)atomicAdd(p.counters, 32ull);
+                long long take = p.n_rays - b;
+                take = take < 0 ? 0 : (take > 32 ? 32 : take);
                 if (take < 32) atomicSub(&sh_alive, 32 - (int)take);
                 if (take > 0) { src = -1; n = (int)take; pos = (unsigned long long)b; }
                 else {

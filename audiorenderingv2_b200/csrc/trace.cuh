@@ -51,7 +51,6 @@ struct TraceParams {
     long long wave_cap;         // ring slots per queue = most paths alive per SM
     int wave_queues;            // queue j holds paths of depth (j + 1) * wave_segments
     int wave_segments;          // segments per task
-    int wave_chunk;             // unstarted rays an SM takes per global atomic (32 = one batch; larger: consecutive batches stay on one SM)
     const int* ray_order;       // optional: the order in which the launch's rays [0, n_rays) are started (direction-sorted)
     int chunk;                  // rays a warp claims per global atomic
     int refill_below;           // lanes of a warp are refilled only while fewer than this many hold a path (32 = always)
